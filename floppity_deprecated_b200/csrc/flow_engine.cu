@@ -1,0 +1,391 @@
+// flow_engine.cu -- whole-flow entry points: Flow.log_prob forward/backward and Flow.sample.
+//
+// Stands for nflows Flow._log_prob / Flow._sample over CompositeTransform[ affine z-score,
+// T x (PiecewiseRationalQuadraticCouplingTransform(ResidualNet), LULinear) ] + StandardNormal, as built by
+// sbi build_nsf (called from /root/reference/modules.py:63) and driven by the training loop at
+// floppity.py:219, posterior.log_prob at floppityFUN.py:35 and posterior.sample at floppity.py:252.
+//
+// Upstream executes ~100 eager kernels per coupling layer.  Here a layer is
+// 2*Bk+2 GEMM launches with fused epilogues + ONE spline/LU kernel, the context projection of ALL
+// layers and blocks is ONE GEMM, there is no host synchronisation anywhere, and the backward pass is
+// written out by hand (no autograd graph), so the whole training step is a fixed launch sequence that
+// can be captured in a CUDA graph.
+#include "common.cuh"
+#include "layout.h"
+#include <math.h>
+
+namespace fp {
+
+// from the other translation units
+int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int drop_width, cudaStream_t stream);
+int launch_gemm_ctx(const fp_gemm_args* a, cudaStream_t stream);   // may route to the tcgen05 path (gemm_tc.cu)
+int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
+                     float* theta_out, float* theta_sp, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status,
+                     const float* luM, const float* luPre, float pre_sign, const float* luPost,
+                     const float* lu_logdet, cudaStream_t stream);
+int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
+                        const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
+                        int64_t R, cudaStream_t stream);
+int launch_affine_fwd(const float*, const float*, const float*, float, float*, float*, int64_t, int, cudaStream_t);
+int launch_affine_inv(const float*, const float*, const float*, float*, int64_t, int, cudaStream_t);
+int launch_affine_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
+int launch_base_logprob(const float*, const float*, float*, int64_t, int, int32_t*, cudaStream_t);
+int launch_base_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
+int launch_rows_affine(const float*, const float*, const float*, float, const float*, float*, int64_t, int, cudaStream_t);
+int launch_glu_bwd(const float*, const float*, const float*, int64_t, float*, float*, int64_t, int, int, cudaStream_t);
+int launch_ctx_reduce(const float*, float*, int64_t, int64_t, int, int, cudaStream_t);
+int launch_colsum(const float*, int64_t, int64_t, int, float*, cudaStream_t);
+int launch_sum(const float*, int64_t, float, float*, cudaStream_t);
+__global__ void k_lu_prepare(const float*, float*, fp_nsf_config);
+__global__ void k_lu_finish(const float*, const float*, float*, fp_nsf_config);
+
+#define FP_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != 0) return _r;     \
+  } while (0)
+
+static int check_cfg(const fp_nsf_config* c) {
+  if (!c) return FP_E_BADARG;
+  if (c->D < 2 || c->D > 64 || c->C < 1 || c->T < 1 || c->T > 64 || c->K < 2 || c->K > 64 || c->H < 1 || c->Bk < 0 ||
+      c->Bk > 16)
+    return FP_E_BADARG;
+  if (c->dropout_p < 0.f || c->dropout_p >= 1.f) return FP_E_BADARG;
+  return 0;
+}
+
+static fp_gemm_args gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                            int N, int64_t K, int flags) {
+  fp_gemm_args g{};
+  g.A = A; g.lda = lda; g.a_kmajor = 1; g.B = B; g.ldb = ldb; g.b_kmajor = 1;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.flags = flags; g.split_k = 1;
+  return g;
+}
+
+static int pick_split(int64_t M, int N, int64_t K) {
+  // wgrad: output is tiny (M x N), contraction K is the batch; spread over ~2 waves of CTAs
+  int64_t tiles = ((M + 127) / 128) * ((N + 63) / 64);
+  int64_t want = (2 * (int64_t)num_sms() + tiles - 1) / tiles;
+  int64_t maxs = (K + 255) / 256;  // at least 256 contraction rows per split
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  if (want > 4096) want = 4096;
+  return (int)want;
+}
+
+// dW[N_out, K_in] += dOut[R, N_out]^T @ Act[R, K_in]   (both operands row-major over the batch)
+static int wgrad(const float* dOut, int64_t ldo, int n_out, const float* act, int64_t lda, int k_in, int64_t R,
+                 float* dW, int64_t ldw, int flags_extra, float drop_p, uint64_t seed, int drop_width, cudaStream_t s) {
+  fp_gemm_args g{};
+  g.A = dOut; g.lda = ldo; g.a_kmajor = 0;   // logical A'[n_out, R], element (n, r) at dOut[r*ldo + n]
+  g.B = act; g.ldb = lda; g.b_kmajor = 0;    // logical B'[k_in, R], element (k, r) at act[r*lda + k]
+  g.C = dW; g.ldc = ldw; g.M = n_out; g.N = k_in; g.K = R;
+  g.flags = FP_G_ATOMIC | flags_extra;
+  g.split_k = pick_split(n_out, k_in, R);
+  return launch_gemm(&g, drop_p, seed, drop_width, s);
+}
+
+// dIn[R, K_in] (=|+=) dOut[R, N_out] @ W[N_out, K_in]
+static fp_gemm_args dgrad_args(const float* dOut, int64_t ldo, int n_out, const float* W, int64_t ldw, int k_in,
+                               int64_t R, float* dIn, int64_t ldi, int flags) {
+  fp_gemm_args g{};
+  g.A = dOut; g.lda = ldo; g.a_kmajor = 1;
+  g.B = W; g.ldb = ldw; g.b_kmajor = 0;      // logical B[k_in, n_out], element (k, n) at W[n*ldw + k]
+  g.C = dIn; g.ldc = ldi; g.M = R; g.N = k_in; g.K = n_out; g.flags = flags; g.split_k = 1;
+  return g;
+}
+
+static inline uint64_t layer_seed(uint64_t seed, int layer, int block) {
+  return seed * 0x9E3779B97F4A7C15ull + (uint64_t)(layer * 64 + block + 1) * 0xD6E8FEB86659FD93ull;
+}
+
+// conditioner forward of layer i: theta_i [R, D] -> spline params [R, dP_i]
+// h buffers: h(b) for b = 0..Bk (may alias when not training), t(b), u(b) (NULL when not training)
+struct CondBufs {
+  float* h[17];
+  float* t[16];
+  float* u[16];
+  float* prm;
+};
+
+static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const float* params, int i, const float* theta_i,
+                               const float* ctx_all, int64_t R, int ctx_div, const CondBufs& b, bool training,
+                               uint64_t seed, cudaStream_t s) {
+  const int H = L.H, D = L.D;
+  const float drop = training ? cfg->dropout_p : 0.f;
+  {  // initial layer: h0 = theta_i @ W0x^T + (ctx @ W0ctx^T + b0)   [the bracket is a column block of ctx_all]
+    fp_gemm_args g = gemm_nt(theta_i, D, params + L.w0x(i), D, b.h[0], H, R, H, D, FP_G_ADD_CTX);
+    g.G = ctx_all + L.ctxCol(i, 0); g.ldg = L.Nctx; g.ctx_div = ctx_div;
+    FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+  }
+  for (int k = 0; k < L.Bk; ++k) {
+    {  // t = relu(h) @ W1^T + b1
+      fp_gemm_args g = gemm_nt(b.h[k], H, params + L.w1(i, k), H, b.t[k], H, R, H, H, FP_G_RELU_A | FP_G_BIAS);
+      g.bias = params + L.b1(i, k);
+      FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+    }
+    {  // u = dropout(relu(t)) @ W2^T + b2 ; h_next = h + u * sigmoid(ctx gate)
+      int fl = FP_G_RELU_A | FP_G_BIAS | FP_G_GLU_RES | (drop > 0.f ? 512 : 0);
+      fp_gemm_args g = gemm_nt(b.t[k], H, params + L.w2(i, k), H, b.h[k + 1], H, R, H, H, fl);
+      g.bias = params + L.b2(i, k);
+      g.G = ctx_all + L.ctxCol(i, 1 + k); g.ldg = L.Nctx; g.ctx_div = ctx_div;
+      g.Rsd = b.h[k]; g.ldr = H;
+      g.U = b.u[k]; g.ldu = H;
+      FP_TRY(launch_gemm(&g, drop, layer_seed(seed, i, k), H, s));
+    }
+  }
+  {  // params = h @ Wf^T + bf
+    fp_gemm_args g = gemm_nt(b.h[L.Bk], H, params + L.wf(i), H, b.prm, L.dP(i), R, L.dP(i), H, FP_G_BIAS);
+    g.bias = params + L.bf(i);
+    FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+  }
+  return 0;
+}
+
+static int context_projection(const Layout& L, const float* params, const float* ctx, int64_t Rc, float* ctx_all,
+                              cudaStream_t s) {
+  fp_gemm_args g = gemm_nt(ctx, L.C, params + L.ctx_w, L.C, ctx_all, L.Nctx, Rc, (int)L.Nctx, L.C, FP_G_BIAS);
+  g.bias = params + L.ctx_b;
+  return launch_gemm_ctx(&g, s);
+}
+
+}  // namespace fp
+
+using namespace fp;
+
+extern "C" {
+
+int64_t fp_nsf_param_count(const fp_nsf_config* cfg) {
+  if (check_cfg(cfg)) return FP_E_BADARG;
+  return Layout(cfg).total();
+}
+int64_t fp_nsf_grad_count(const fp_nsf_config* cfg) {
+  if (check_cfg(cfg)) return FP_E_BADARG;
+  return Layout(cfg).gradTotal();
+}
+int32_t fp_nsf_dtr(const fp_nsf_config* cfg, int32_t layer) {
+  if (check_cfg(cfg)) return FP_E_BADARG;
+  return Layout(cfg).dtr(layer);
+}
+int64_t fp_nsf_param_offset(const fp_nsf_config* cfg, int32_t layer, int32_t kind, int32_t block) {
+  if (check_cfg(cfg) || layer < 0 || layer >= cfg->T) return FP_E_BADARG;
+  Layout L(cfg);
+  switch (kind) {
+    case FP_P_CTX_W: return (block < 0 || block > L.Bk) ? FP_E_BADARG : L.ctxW(layer, block);
+    case FP_P_CTX_B: return (block < 0 || block > L.Bk) ? FP_E_BADARG : L.ctxB(layer, block);
+    case FP_P_W0X: return L.w0x(layer);
+    case FP_P_W1: return (block < 0 || block >= L.Bk) ? FP_E_BADARG : L.w1(layer, block);
+    case FP_P_B1: return (block < 0 || block >= L.Bk) ? FP_E_BADARG : L.b1(layer, block);
+    case FP_P_W2: return (block < 0 || block >= L.Bk) ? FP_E_BADARG : L.w2(layer, block);
+    case FP_P_B2: return (block < 0 || block >= L.Bk) ? FP_E_BADARG : L.b2(layer, block);
+    case FP_P_WF: return L.wf(layer);
+    case FP_P_BF: return L.bf(layer);
+    case FP_P_LU_LOWER: return L.luLower(layer);
+    case FP_P_LU_UPPER: return L.luUpper(layer);
+    case FP_P_LU_DIAG: return L.luDiag(layer);
+    case FP_P_LU_BIAS: return L.luBias(layer);
+  }
+  return FP_E_BADARG;
+}
+int64_t fp_nsf_param_size(const fp_nsf_config* cfg, int32_t layer, int32_t kind) {
+  if (check_cfg(cfg) || layer < 0 || layer >= cfg->T) return FP_E_BADARG;
+  Layout L(cfg);
+  switch (kind) {
+    case FP_P_CTX_W: return (int64_t)L.H * L.C;
+    case FP_P_CTX_B: return L.H;
+    case FP_P_W0X: return (int64_t)L.H * L.D;
+    case FP_P_W1: case FP_P_W2: return (int64_t)L.H * L.H;
+    case FP_P_B1: case FP_P_B2: return L.H;
+    case FP_P_WF: return (int64_t)L.dP(layer) * L.H;
+    case FP_P_BF: return L.dP(layer);
+    case FP_P_LU_LOWER: case FP_P_LU_UPPER: return L.ntri;
+    case FP_P_LU_DIAG: case FP_P_LU_BIAS: return L.D;
+  }
+  return FP_E_BADARG;
+}
+int64_t fp_nsf_prepared_count(const fp_nsf_config* cfg) {
+  if (check_cfg(cfg)) return FP_E_BADARG;
+  return Layout(cfg).prepTotal();
+}
+int64_t fp_nsf_workspace_count(const fp_nsf_config* cfg, int64_t R, int64_t Rc, int32_t training) {
+  if (check_cfg(cfg) || R < 0 || Rc < 0) return FP_E_BADARG;
+  Layout L(cfg);
+  return Workspace(L, R, Rc, training != 0).total;
+}
+
+int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepared, void* stream) {
+  FP_TRY(check_cfg(cfg));
+  size_t sm = (size_t)3 * cfg->D * cfg->D * 4;
+  k_lu_prepare<<<cfg->T, 128, sm, (cudaStream_t)stream>>>(params, prepared, *cfg);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fp_nsf_finish_grads(const fp_nsf_config* cfg, const float* params, const float* prepared, float* grads, void* stream) {
+  FP_TRY(check_cfg(cfg));
+  size_t sm = (size_t)3 * cfg->D * cfg->D * 4;
+  k_lu_finish<<<cfg->T, 128, sm, (cudaStream_t)stream>>>(params, prepared, grads, *cfg);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const float* prepared, const float* theta,
+                           const float* ctx, int64_t R, int64_t Rc, const float* zshift, const float* zscale,
+                           float zlogdet, float* logp, float* workspace, int32_t training, uint64_t dropout_seed,
+                           int32_t* status, void* stream) {
+  FP_TRY(check_cfg(cfg));
+  if (R <= 0) return 0;
+  if (Rc <= 0 || R % Rc != 0) return FP_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  Layout L(cfg);
+  Workspace W(L, R, Rc, training != 0);
+  float* ws = workspace;
+  const int ctx_div = (int)(R / Rc);
+  const int D = L.D;
+
+  float* ctx_all = ws + W.ctx_all;
+  float* logdet = ws + W.logdet;
+  FP_TRY(context_projection(L, params, ctx, Rc, ctx_all, s));
+
+  float* th_cur = training ? ws + W.thst(0) : ws + W.th_a;
+  FP_TRY(launch_affine_fwd(theta, zshift, zscale, zlogdet, th_cur, logdet, R, D, s));
+
+  for (int i = 0; i < L.T; ++i) {
+    CondBufs b{};
+    float* th_next; float* th_sp = nullptr;
+    if (training) {
+      for (int k = 0; k <= L.Bk; ++k) b.h[k] = ws + W.hbuf(i, k);
+      for (int k = 0; k < L.Bk; ++k) { b.t[k] = ws + W.tbuf(i, k); b.u[k] = ws + W.ubuf(i, k); }
+      b.prm = ws + W.prmbuf(i);
+      th_next = ws + W.thst(i + 1);
+      th_sp = ws + W.thsp(i);
+    } else {
+      for (int k = 0; k <= L.Bk; ++k) b.h[k] = ws + W.h;     // in place: each element is read then written by one thread
+      for (int k = 0; k < L.Bk; ++k) { b.t[k] = ws + W.t; b.u[k] = nullptr; }
+      b.prm = ws + W.prm;
+      th_next = (th_cur == ws + W.th_a) ? ws + W.th_b : ws + W.th_a;
+    }
+    FP_TRY(conditioner_forward(cfg, L, params, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, s));
+    FP_TRY(launch_rqs_apply(false, cfg, i & 1, th_cur, b.prm, th_next, th_sp, logdet, nullptr, R, status,
+                            prepared + L.prepM(i), nullptr, 1.f, params + L.luBias(i), prepared + L.prepLogdet(i), s));
+    th_cur = th_next;
+  }
+  FP_TRY(launch_base_logprob(th_cur, logdet, logp, R, D, status, s));
+  return 0;
+}
+
+int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const float* prepared, const float* ctx,
+                            int64_t R, int64_t Rc, const float* zscale, const float* d_logp, float* grads,
+                            float* d_theta, float* workspace, uint64_t dropout_seed, void* stream) {
+  FP_TRY(check_cfg(cfg));
+  if (R <= 0) return 0;
+  if (Rc <= 0 || R % Rc != 0) return FP_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  Layout L(cfg);
+  Workspace W(L, R, Rc, true);
+  float* ws = workspace;
+  const int A = (int)(R / Rc);
+  const int D = L.D, H = L.H;
+  const float drop = cfg->dropout_p;
+
+  float* dth_a = ws + W.dth_a; float* dth_b = ws + W.dth_b;
+  float* dh = ws + W.dh; float* dt = ws + W.dt; float* du = ws + W.du; float* dprm = ws + W.dprm;
+  float* dctx_all = ws + W.dctx_all;
+  const float* ctx_all = ws + W.ctx_all;
+
+  // d logp / d z_T  and  sum(d_logp) for the batch-constant LU log-dets
+  FP_TRY(launch_base_bwd(ws + W.thst(L.T), d_logp, dth_a, R, D, s));
+  FP_TRY(launch_sum(d_logp, R, 1.f, grads + L.gradTailSum(), s));
+
+  for (int i = L.T - 1; i >= 0; --i) {
+    // ---- LULinear backward: y = M x + b, x = theta_sp[i]
+    FP_TRY(launch_colsum(dth_a, D, R, D, grads + L.luBias(i), s));
+    FP_TRY(wgrad(dth_a, D, D, ws + W.thsp(i), D, D, R, grads + L.gradTailDM(i), D, 0, 0.f, 0, 0, s));
+    {
+      fp_gemm_args g = dgrad_args(dth_a, D, D, prepared + L.prepM(i), D, D, R, dth_b, D, 0);
+      FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+    }
+    // ---- spline backward: d params, d theta_in (identity features pass through)
+    const int dP = L.dP(i);
+    FP_TRY(launch_rqs_backward(cfg, i & 1, ws + W.thst(i), ws + W.prmbuf(i), dth_b, d_logp, dprm, dth_a, R, s));
+    // ---- final layer
+    FP_TRY(launch_colsum(dprm, dP, R, dP, grads + L.bf(i), s));
+    FP_TRY(wgrad(dprm, dP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, 0.f, 0, 0, s));
+    {
+      fp_gemm_args g = dgrad_args(dprm, dP, dP, params + L.wf(i), H, H, R, dh, H, 0);
+      FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+    }
+    // ---- residual blocks, last to first
+    for (int k = L.Bk - 1; k >= 0; --k) {
+      const uint64_t seed = layer_seed(dropout_seed, i, k);
+      FP_TRY(launch_glu_bwd(dh, ws + W.ubuf(i, k), ctx_all + L.ctxCol(i, 1 + k), L.Nctx, du,
+                            dctx_all + L.ctxCol(i, 1 + k), Rc, A, H, s));
+      FP_TRY(launch_colsum(du, H, R, H, grads + L.b2(i, k), s));
+      FP_TRY(wgrad(du, H, H, ws + W.tbuf(i, k), H, H, R, grads + L.w2(i, k), H,
+                   FP_G_RELU_B | (drop > 0.f ? 1024 : 0), drop, seed, H, s));
+      {
+        fp_gemm_args g = dgrad_args(du, H, H, params + L.w2(i, k), H, H, R, dt, H,
+                                    FP_G_RELUMASK | (drop > 0.f ? 2048 : 0));
+        g.Msk = ws + W.tbuf(i, k); g.ldm = H;
+        FP_TRY(launch_gemm(&g, drop, seed, H, s));
+      }
+      FP_TRY(launch_colsum(dt, H, R, H, grads + L.b1(i, k), s));
+      FP_TRY(wgrad(dt, H, H, ws + W.hbuf(i, k), H, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, 0.f, 0, 0, s));
+      {
+        fp_gemm_args g = dgrad_args(dt, H, H, params + L.w1(i, k), H, H, R, dh, H, FP_G_RELUMASK | FP_G_ACCUM);
+        g.Msk = ws + W.hbuf(i, k); g.ldm = H;
+        FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+      }
+    }
+    // ---- initial layer: h0 = theta_i @ W0x^T + ctx slot 0
+    FP_TRY(launch_ctx_reduce(dh, dctx_all + L.ctxCol(i, 0), L.Nctx, Rc, A, H, s));
+    FP_TRY(wgrad(dh, H, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, 0.f, 0, 0, s));
+    {
+      fp_gemm_args g = dgrad_args(dh, H, H, params + L.w0x(i), D, D, R, dth_a, D, FP_G_ACCUM);
+      FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+    }
+  }
+  if (d_theta) FP_TRY(launch_affine_bwd(dth_a, zscale, d_theta, R, D, s));
+
+  // ---- context projection weights: dWctx += dctx_all^T @ ctx ; db += colsum(dctx_all)
+  FP_TRY(launch_colsum(dctx_all, L.Nctx, Rc, (int)L.Nctx, grads + L.ctx_b, s));
+  FP_TRY(wgrad(dctx_all, L.Nctx, (int)L.Nctx, ctx, L.C, L.C, Rc, grads + L.ctx_w, L.C, 0, 0.f, 0, 0, s));
+  return 0;
+}
+
+int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* prepared, const float* z, const float* ctx,
+                  int64_t R, int64_t Rc, const float* zshift, const float* zscale, float* theta_out, float* workspace,
+                  int32_t* status, void* stream) {
+  FP_TRY(check_cfg(cfg));
+  if (R <= 0) return 0;
+  if (Rc <= 0 || R % Rc != 0) return FP_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  Layout L(cfg);
+  Workspace W(L, R, Rc, false);
+  float* ws = workspace;
+  const int ctx_div = (Rc == 1) ? 0 : (int)(R / Rc);
+  const int D = L.D;
+  float* ctx_all = ws + W.ctx_all;
+  FP_TRY(context_projection(L, params, ctx, Rc, ctx_all, s));
+
+  // inverse of the last LULinear on the base noise
+  float* th_cur = ws + W.th_a; float* th_next = ws + W.th_b;
+  FP_TRY(launch_rows_affine(z, prepared + L.prepMinv(L.T - 1), params + L.luBias(L.T - 1), -1.f, nullptr, th_cur, R, D, s));
+  for (int i = L.T - 1; i >= 0; --i) {
+    CondBufs b{};
+    for (int k = 0; k <= L.Bk; ++k) b.h[k] = ws + W.h;
+    for (int k = 0; k < L.Bk; ++k) { b.t[k] = ws + W.t; b.u[k] = nullptr; }
+    b.prm = ws + W.prm;
+    FP_TRY(conditioner_forward(cfg, L, params, i, th_cur, ctx_all, R, ctx_div, b, false, 0, s));
+    // spline inverse of layer i fused with the inverse LULinear of layer i-1
+    const float* M = (i > 0) ? prepared + L.prepMinv(i - 1) : nullptr;
+    const float* pre = (i > 0) ? params + L.luBias(i - 1) : nullptr;
+    FP_TRY(launch_rqs_apply(true, cfg, i & 1, th_cur, b.prm, th_next, nullptr, nullptr, nullptr, R, status, M, pre, -1.f,
+                            nullptr, nullptr, s));
+    float* tmp = th_cur; th_cur = th_next; th_next = tmp;
+  }
+  FP_TRY(launch_affine_inv(th_cur, zshift, zscale, theta_out, R, D, s));
+  return 0;
+}
+
+}  // extern "C"

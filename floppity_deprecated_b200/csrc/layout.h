@@ -1,0 +1,132 @@
+// layout.h -- flat parameter / prepared / workspace layouts of one NSF (host-side arithmetic only).
+//
+// Mirrors what sbi build_nsf (called at /root/reference/modules.py:63) instantiates: T x [coupling
+// ResidualNet + LULinear].  All context-facing weights of all layers are stored contiguously
+// ([T*(1+Bk)*H, C]) so the context projection of the whole flow is ONE GEMM.
+#pragma once
+#include <stdint.h>
+#include "../../include/floppity_b200.h"
+
+#if defined(__CUDACC__)
+#define FP_LHD __host__ __device__ inline
+#else
+#define FP_LHD inline
+#endif
+
+namespace fp {
+
+FP_LHD int64_t al4_(int64_t x) { return (x + 3) & ~int64_t(3); }
+inline int64_t al4(int64_t x) { return (x + 3) & ~int64_t(3); }
+inline int64_t al32(int64_t x) { return (x + 31) & ~int64_t(31); }
+
+struct Layout {
+  int D, C, T, K, H, Bk, P, S;  // S = 1 + Bk context slots per layer
+  int64_t Nctx;                 // T * S * H
+  int64_t ctx_w, ctx_b, layers; // offsets of the regions
+  int64_t ntri;
+
+  FP_LHD explicit Layout(const fp_nsf_config* c)
+      : D(c->D), C(c->C), T(c->T), K(c->K), H(c->H), Bk(c->Bk), P(3 * c->K - 1), S(1 + c->Bk) {
+    Nctx = (int64_t)T * S * H;
+    ctx_w = 0;
+    ctx_b = al4_(Nctx * C);
+    layers = ctx_b + al4_(Nctx);
+    ntri = (int64_t)D * (D - 1) / 2;
+  }
+  FP_LHD int dtr(int i) const { return (i % 2 == 0) ? (D + 1) / 2 : D / 2; }
+  FP_LHD int dP(int i) const { return dtr(i) * P; }
+  FP_LHD int dPmax() const { return dtr(0) * P; }
+  FP_LHD int64_t block_sz() const { return al4_((int64_t)H * H) * 2 + al4_(H) * 2; }
+  FP_LHD int64_t layer_sz(int i) const {
+    return al4_((int64_t)H * D) + Bk * block_sz() + al4_((int64_t)dP(i) * H) + al4_(dP(i)) + 2 * al4_(ntri) + 2 * al4_(D);
+  }
+  FP_LHD int64_t layer_off(int i) const {
+    int64_t o = layers;
+    for (int l = 0; l < i; ++l) o += layer_sz(l);
+    return o;
+  }
+  FP_LHD int64_t total() const { return layer_off(T); }
+  // ---- per-tensor offsets
+  FP_LHD int64_t ctxW(int i, int slot) const { return ctx_w + ((int64_t)(i * S + slot) * H) * C; }
+  FP_LHD int64_t ctxB(int i, int slot) const { return ctx_b + (int64_t)(i * S + slot) * H; }
+  FP_LHD int64_t ctxCol(int i, int slot) const { return (int64_t)(i * S + slot) * H; }
+  FP_LHD int64_t w0x(int i) const { return layer_off(i); }
+  FP_LHD int64_t w1(int i, int b) const { return layer_off(i) + al4_((int64_t)H * D) + b * block_sz(); }
+  FP_LHD int64_t b1(int i, int b) const { return w1(i, b) + al4_((int64_t)H * H); }
+  FP_LHD int64_t w2(int i, int b) const { return b1(i, b) + al4_(H); }
+  FP_LHD int64_t b2(int i, int b) const { return w2(i, b) + al4_((int64_t)H * H); }
+  FP_LHD int64_t wf(int i) const { return layer_off(i) + al4_((int64_t)H * D) + Bk * block_sz(); }
+  FP_LHD int64_t bf(int i) const { return wf(i) + al4_((int64_t)dP(i) * H); }
+  FP_LHD int64_t luLower(int i) const { return bf(i) + al4_(dP(i)); }
+  FP_LHD int64_t luUpper(int i) const { return luLower(i) + al4_(ntri); }
+  FP_LHD int64_t luDiag(int i) const { return luUpper(i) + al4_(ntri); }
+  FP_LHD int64_t luBias(int i) const { return luDiag(i) + al4_(D); }
+  // ---- gradient buffer = params layout + tail: dM accumulators [T][D*D] + sum(d_logp)
+  FP_LHD int64_t gradTailDM(int i) const { return total() + (int64_t)i * al4_((int64_t)D * D); }
+  FP_LHD int64_t gradTailSum() const { return total() + (int64_t)T * al4_((int64_t)D * D); }
+  FP_LHD int64_t gradTotal() const { return gradTailSum() + 4; }
+  // ---- prepared buffer: per layer M=L*U, Minv, L, U, logdet
+  FP_LHD int64_t prepSz() const { return 4 * al4_((int64_t)D * D) + 4; }
+  FP_LHD int64_t prepM(int i) const { return (int64_t)i * prepSz(); }
+  FP_LHD int64_t prepMinv(int i) const { return prepM(i) + al4_((int64_t)D * D); }
+  FP_LHD int64_t prepL(int i) const { return prepM(i) + 2 * al4_((int64_t)D * D); }
+  FP_LHD int64_t prepU(int i) const { return prepM(i) + 3 * al4_((int64_t)D * D); }
+  FP_LHD int64_t prepLogdet(int i) const { return prepM(i) + 4 * al4_((int64_t)D * D); }
+  FP_LHD int64_t prepTotal() const { return (int64_t)T * prepSz(); }
+};
+
+// workspace carve; identical arithmetic in forward and backward so saved activations are found again
+struct Workspace {
+  int64_t ctx_all, logdet;
+  // inference
+  int64_t th_a, th_b, h, t, prm;
+  // training
+  int64_t th_st, th_sp, act;  // act: per-layer region
+  int64_t dth_a, dth_b, dh, dt, du, dprm, dctx_all;
+  int64_t total;
+  int64_t R, Rc;
+  int64_t act_layer_sz[64];
+  int64_t act_layer_off[64];
+  const Layout& L;
+
+  Workspace(const Layout& l, int64_t R_, int64_t Rc_, bool training) : R(R_), Rc(Rc_), L(l) {
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t r = o; o += al32(n); return r; };
+    ctx_all = take(Rc * L.Nctx);
+    logdet = take(R);
+    th_a = th_b = h = t = prm = th_st = th_sp = act = dth_a = dth_b = dh = dt = du = dprm = dctx_all = 0;
+    if (!training) {
+      th_a = take(R * L.D); th_b = take(R * L.D);
+      h = take(R * L.H); t = take(R * L.H); prm = take(R * L.dPmax());
+    } else {
+      th_st = take((int64_t)(L.T + 1) * R * L.D);
+      th_sp = take((int64_t)L.T * R * L.D);
+      act = o;
+      for (int i = 0; i < L.T && i < 64; ++i) {
+        act_layer_off[i] = o;
+        take((int64_t)(L.Bk + 1) * R * L.H);  // h_0..h_Bk
+        take((int64_t)L.Bk * R * L.H);        // t_b (pre-relu output of linear 0)
+        take((int64_t)L.Bk * R * L.H);        // u_b (pre-gate output of linear 1)
+        take(R * L.dP(i));                    // spline params
+        act_layer_sz[i] = o - act_layer_off[i];
+      }
+      dth_a = take(R * L.D); dth_b = take(R * L.D);
+      dh = take(R * L.H); dt = take(R * L.H); du = take(R * L.H);
+      dprm = take(R * L.dPmax());
+      dctx_all = take(Rc * L.Nctx);
+    }
+    total = o;
+  }
+  int64_t thst(int i) const { return th_st + (int64_t)i * R * L.D; }
+  int64_t thsp(int i) const { return th_sp + (int64_t)i * R * L.D; }
+  int64_t hbuf(int i, int b) const { return act_layer_off[i] + (int64_t)b * al32(0) + (int64_t)b * R * L.H; }
+  int64_t tbuf(int i, int b) const { return act_layer_off[i] + al32((int64_t)(L.Bk + 1) * R * L.H) + (int64_t)b * R * L.H; }
+  int64_t ubuf(int i, int b) const {
+    return act_layer_off[i] + al32((int64_t)(L.Bk + 1) * R * L.H) + al32((int64_t)L.Bk * R * L.H) + (int64_t)b * R * L.H;
+  }
+  int64_t prmbuf(int i) const {
+    return act_layer_off[i] + al32((int64_t)(L.Bk + 1) * R * L.H) + 2 * al32((int64_t)L.Bk * R * L.H);
+  }
+};
+
+}  // namespace fp

@@ -1,0 +1,376 @@
+// rqs_kernels.cu -- fused rational-quadratic-spline coupling kernels (forward / inverse / backward).
+//
+// Replaces nflows PiecewiseRationalQuadraticCouplingTransform._piecewise_cdf +
+// unconstrained_rational_quadratic_spline + searchsorted (reached from
+// /root/reference/modules.py:63 via sbi build_nsf; ~60 eager ATen ops + boolean-mask
+// gather/scatter per layer upstream) with ONE kernel per direction:
+//   - persistent CTAs, each streaming tiles of `rows` consecutive samples;
+//   - the [rows, d_tr, 3K-1] conditioner output of a tile is one contiguous byte range, fetched
+//     by the TMA engine as a 1-D bulk copy (cp.async.bulk) into a 2-stage shared-memory ring;
+//   - one thread per (sample, transformed feature): softmax/softplus parameterisation, bin search,
+//     RQ evaluation, all in registers, params read from smem at odd stride (conflict free);
+//   - the per-sample log-det sum and the layer's LU-linear (y = M(x+pre)+post, D<=64) are fused in
+//     a second phase that works on the tile's theta rows held in shared memory.
+// HBM traffic per sample per layer = params + theta in + theta out + logdet.
+#include "common.cuh"
+#include "rqs_math.cuh"
+#include <math.h>
+#include <algorithm>
+
+namespace fp {
+
+constexpr int RQS_STAGES = 2;
+
+struct RqsArgs {
+  const float* theta_in;
+  const float* params;
+  float* theta_out;
+  float* theta_sp;      // optional: post-spline / pre-LU rows (saved for the LU backward)
+  float* logdet;        // accumulated
+  int32_t* bin_idx;     // optional
+  int32_t* status;      // optional
+  int64_t R;
+  int D, d_tr, parity, rows;
+  RqsConsts c;
+  const float* luM;     // optional [D, D]
+  const float* luPre;   // optional [D] added before the matvec
+  const float* luPost;  // optional [D] added after
+  const float* lu_logdet;  // optional device scalar added to every row's logdet (LULinear logabsdet)
+  float pre_sign;       // luPre is multiplied by this (-1 for the inverse direction: x - b)
+};
+
+struct RqsSmem {
+  float* stage[RQS_STAGES];
+  float* rowbuf;
+  float* ladbuf;
+  float* luM;
+  uint64_t* bars;
+};
+
+__device__ __forceinline__ RqsSmem carve(unsigned char* base, int tile_floats, int rows, int D, int d_tr, bool lu) {
+  RqsSmem s;
+  float* f = reinterpret_cast<float*>(base);
+  for (int i = 0; i < RQS_STAGES; ++i) { s.stage[i] = f; f += tile_floats; }
+  s.rowbuf = f; f += rows * D;
+  s.ladbuf = f; f += rows * d_tr;
+  s.luM = f; if (lu) f += D * D;
+  uintptr_t p = (reinterpret_cast<uintptr_t>(f) + 7) & ~uintptr_t(7);
+  s.bars = reinterpret_cast<uint64_t*>(p);
+  return s;
+}
+
+static size_t rqs_smem_bytes(int tile_floats, int rows, int D, int d_tr, bool lu) {
+  size_t f = (size_t)RQS_STAGES * tile_floats + (size_t)rows * D + (size_t)rows * d_tr + (lu ? (size_t)D * D : 0);
+  return f * 4 + 8 + RQS_STAGES * 8 + 16;
+}
+
+// Issue the load of one tile into a stage: bulk TMA when the byte count allows it, otherwise a
+// cooperative plain copy (only ever the final ragged tile).  Must be called by ALL threads.
+__device__ __forceinline__ void load_tile(const RqsArgs& a, float* dst, uint64_t* bar, int64_t tile, int row_floats) {
+  int64_t r0 = tile * a.rows;
+  int rows_here = (int)min((int64_t)a.rows, a.R - r0);
+  uint32_t bytes = (uint32_t)rows_here * row_floats * 4u;
+  const float* src = a.params + r0 * row_floats;
+  if ((bytes & 15u) == 0) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(dst, src, bytes, bar);
+    }
+  } else {
+    for (int i = threadIdx.x; i < rows_here * row_floats; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) mbar_arrive(bar);  // keep the barrier phase in step with the bulk path
+  }
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int row_floats = a.d_tr * a.c.P;
+  const int tile_floats = a.rows * row_floats;
+  const bool lu = a.luM != nullptr;
+  RqsSmem s = carve(smem_raw, tile_floats, a.rows, a.D, a.d_tr, lu);
+  const int64_t ntiles = (a.R + a.rows - 1) / a.rows;
+  const int D = a.D, d_tr = a.d_tr, d_id = D - d_tr;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RQS_STAGES; ++i) mbar_init(&s.bars[i], 1);
+    mbar_fence_init();
+  }
+  if (lu) for (int i = threadIdx.x; i < D * D; i += blockDim.x) s.luM[i] = a.luM[i];
+  __syncthreads();
+
+  // prologue: fill the ring
+  for (int st = 0; st < RQS_STAGES; ++st) {
+    int64_t tile = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
+    if (tile < ntiles) load_tile(a, s.stage[st], &s.bars[st], tile, row_floats);
+  }
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = it % RQS_STAGES;
+    const uint32_t parity = (uint32_t)(it / RQS_STAGES) & 1u;
+    const int64_t r0 = tile * a.rows;
+    const int rows_here = (int)min((int64_t)a.rows, a.R - r0);
+
+    // phase 0: theta rows of the tile -> smem (coalesced)
+    for (int i = threadIdx.x; i < rows_here * D; i += blockDim.x) s.rowbuf[i] = a.theta_in[r0 * D + i];
+    mbar_wait(&s.bars[st], parity);
+    __syncthreads();
+
+    // phase 1: one (sample, transformed feature) per thread
+    const float* P = s.stage[st];
+    for (int e = threadIdx.x; e < rows_here * d_tr; e += blockDim.x) {
+      int row = e / d_tr, j = e - row * d_tr;
+      int f = 2 * j + a.parity;
+      float x = s.rowbuf[row * D + f];
+      float y, lad; int bin; bool nd = false;
+      if (INVERSE) rqs_inverse_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin, nd);
+      else rqs_forward_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin);
+      s.rowbuf[row * D + f] = y;
+      s.ladbuf[e] = lad;
+      if (a.bin_idx) a.bin_idx[(r0 + row) * d_tr + j] = bin;
+      if (a.status) {
+        if (nd) atomicAdd(&a.status[1], 1);
+        if (!isfinite(y) || !isfinite(lad)) atomicAdd(&a.status[0], 1);
+      }
+    }
+    __syncthreads();
+
+    // stage `st` is consumed: refill it with the tile RQS_STAGES iterations ahead
+    {
+      int64_t nxt = tile + (int64_t)RQS_STAGES * gridDim.x;
+      if (nxt < ntiles) load_tile(a, s.stage[st], &s.bars[st], nxt, row_floats);
+    }
+
+    // phase 2: write rows (optionally through the LU-linear) and the per-sample log-det
+    for (int i = threadIdx.x; i < rows_here * D; i += blockDim.x) {
+      int row = i / D, f = i - row * D;
+      float v = s.rowbuf[i];
+      if (a.theta_sp) a.theta_sp[r0 * D + i] = v;
+      if (lu) {
+        const float* xr = s.rowbuf + row * D;
+        const float* m = s.luM + f * D;
+        float acc = 0.f;
+        if (a.luPre) {
+          for (int k = 0; k < D; ++k) acc = fmaf(m[k], xr[k] + a.pre_sign * a.luPre[k], acc);
+        } else {
+          for (int k = 0; k < D; ++k) acc = fmaf(m[k], xr[k], acc);
+        }
+        v = acc + (a.luPost ? a.luPost[f] : 0.f);
+      }
+      a.theta_out[r0 * D + i] = v;
+    }
+    if (a.logdet) {
+      const float lu_ld = a.lu_logdet ? *a.lu_logdet : 0.f;
+      for (int row = threadIdx.x; row < rows_here; row += blockDim.x) {
+        float sum = 0.f;
+        for (int j = 0; j < d_tr; ++j) sum += s.ladbuf[row * d_tr + j];
+        a.logdet[r0 + row] += sum + lu_ld;
+      }
+    }
+    __syncthreads();
+  }
+  (void)d_id;
+}
+
+// ---- backward ----------------------------------------------------------------------------------
+struct RqsBwdArgs {
+  const float* theta_in;     // [R, D] layer input (pre-spline)
+  const float* params;       // [R, d_tr, P]
+  const float* d_theta_out;  // [R, D] grad wrt post-spline rows
+  const float* d_logdet;     // [R]
+  float* d_params;           // [R, d_tr, P]
+  float* d_theta_in;         // [R, D]
+  int64_t R;
+  int D, d_tr, parity, rows;
+  RqsConsts c;
+};
+
+__global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int row_floats = a.d_tr * a.c.P;
+  const int tile_floats = a.rows * row_floats;
+  float* stage[RQS_STAGES];
+  {
+    float* f = reinterpret_cast<float*>(smem_raw);
+    for (int i = 0; i < RQS_STAGES; ++i) { stage[i] = f; f += tile_floats; }
+  }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)RQS_STAGES * tile_floats * 4 + 7) & ~size_t(7)));
+  const int64_t ntiles = (a.R + a.rows - 1) / a.rows;
+  const int D = a.D, d_tr = a.d_tr;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RQS_STAGES; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  RqsArgs la{};  // reuse load_tile
+  la.params = a.params; la.rows = a.rows; la.R = a.R;
+  for (int st = 0; st < RQS_STAGES; ++st) {
+    int64_t tile = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
+    if (tile < ntiles) load_tile(la, stage[st], &bars[st], tile, row_floats);
+  }
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = it % RQS_STAGES;
+    const uint32_t parity = (uint32_t)(it / RQS_STAGES) & 1u;
+    const int64_t r0 = tile * a.rows;
+    const int rows_here = (int)min((int64_t)a.rows, a.R - r0);
+    mbar_wait(&bars[st], parity);
+    __syncthreads();
+
+    float* P = stage[st];
+    for (int e = threadIdx.x; e < rows_here * d_tr; e += blockDim.x) {
+      int row = e / d_tr, j = e - row * d_tr;
+      int f = 2 * j + a.parity;
+      int64_t gr = r0 + row;
+      float x = a.theta_in[gr * D + f];
+      float gy = a.d_theta_out[gr * D + f];
+      float gl = a.d_logdet[gr];
+      float* p = P + (size_t)e * a.c.P;
+      // in place: every parameter is read before its gradient overwrites it
+      float gx = rqs_backward_elem(p, a.c, x, gy, gl, p, 1);
+      a.d_theta_in[gr * D + f] = gx;
+    }
+    // identity features: gradient passes straight through the coupling
+    for (int i = threadIdx.x; i < rows_here * D; i += blockDim.x) {
+      int f = i % D;
+      if ((f & 1) != a.parity) a.d_theta_in[r0 * D + i] = a.d_theta_out[r0 * D + i];
+    }
+    // write the gradient tile: bulk store when 16B-granular, else plain
+    uint32_t bytes = (uint32_t)rows_here * row_floats * 4u;
+    float* dst = a.d_params + r0 * row_floats;
+    if ((bytes & 15u) == 0) {
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        bulk_s2g(dst, P, bytes);
+        bulk_commit();
+        bulk_wait_read<0>();   // smem may be refilled once the store has read it
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      for (int i = threadIdx.x; i < rows_here * row_floats; i += blockDim.x) dst[i] = P[i];
+      __syncthreads();
+    }
+    int64_t nxt = tile + (int64_t)RQS_STAGES * gridDim.x;
+    if (nxt < ntiles) load_tile(la, stage[st], &bars[st], nxt, row_floats);
+  }
+  if (threadIdx.x == 0) bulk_wait_all<0>();
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+RqsConsts make_rqs_consts(const fp_nsf_config* cfg) {
+  RqsConsts c;
+  c.K = cfg->K; c.P = 3 * cfg->K - 1;
+  c.tb = cfg->tail_bound; c.span = (float)(2.0 * (double)cfg->tail_bound);
+  c.mbw = cfg->min_bin_width; c.mbh = cfg->min_bin_height; c.md = cfg->min_derivative;
+  c.mixw = (float)(1.0 - (double)cfg->min_bin_width * cfg->K);
+  c.mixh = (float)(1.0 - (double)cfg->min_bin_height * cfg->K);
+  c.sqrtH = (float)sqrt((double)cfg->H);
+  c.dconst = (float)log(exp(1.0 - (double)cfg->min_derivative) - 1.0);
+  return c;
+}
+
+// rows per tile: multiple of 4 (keeps every full tile 16-byte granular), sized to ~40 KB per stage
+static int pick_rows(int row_floats, int d_tr) {
+  int rows = (40 * 1024) / (row_floats * 4);
+  rows = rows / 4 * 4;
+  if (rows < 4) rows = 4;
+  if (rows > 128) rows = 128;
+  // do not use more element slots than a 512-thread block covers in two passes
+  while (rows > 4 && rows * d_tr > 1024) rows -= 4;
+  return rows;
+}
+
+static int pick_threads(int rows, int d_tr) {
+  int e = rows * d_tr;
+  int t = (e + 31) / 32 * 32;
+  if (t > 512) t = ((e + 1) / 2 + 31) / 32 * 32;
+  if (t > 512) t = 512;
+  if (t < 64) t = 64;
+  return t;
+}
+
+int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
+                     float* theta_out, float* theta_sp, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status,
+                     const float* luM, const float* luPre, float pre_sign, const float* luPost,
+                     const float* lu_logdet, cudaStream_t stream) {
+  if (R <= 0) return 0;
+  if (cfg->K < 2 || cfg->K > 64 || cfg->D < 2 || cfg->D > 64) return FP_E_BADARG;
+  RqsArgs a{};
+  a.theta_in = theta_in; a.params = params; a.theta_out = theta_out; a.theta_sp = theta_sp;
+  a.logdet = logdet; a.bin_idx = bin_idx; a.status = status; a.R = R;
+  a.D = cfg->D; a.parity = parity & 1;
+  a.d_tr = (a.parity == 0) ? (cfg->D + 1) / 2 : cfg->D / 2;
+  a.c = make_rqs_consts(cfg);
+  a.luM = luM; a.luPre = luPre; a.luPost = luPost; a.lu_logdet = lu_logdet; a.pre_sign = pre_sign;
+  int row_floats = a.d_tr * a.c.P;
+  a.rows = pick_rows(row_floats, a.d_tr);
+  int threads = pick_threads(a.rows, a.d_tr);
+  size_t smem = rqs_smem_bytes(a.rows * row_floats, a.rows, a.D, a.d_tr, luM != nullptr);
+  auto kern = inverse ? k_rqs_apply<true> : k_rqs_apply<false>;
+  FP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  FP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+  if (occ < 1) occ = 1;
+  int64_t ntiles = (R + a.rows - 1) / a.rows;
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
+  kern<<<grid, threads, smem, stream>>>(a);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
+                        const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
+                        int64_t R, cudaStream_t stream) {
+  if (R <= 0) return 0;
+  if (cfg->K < 2 || cfg->K > 64 || cfg->D < 2 || cfg->D > 64) return FP_E_BADARG;
+  RqsBwdArgs a{};
+  a.theta_in = theta_in; a.params = params; a.d_theta_out = d_theta_out; a.d_logdet = d_logdet;
+  a.d_params = d_params; a.d_theta_in = d_theta_in; a.R = R;
+  a.D = cfg->D; a.parity = parity & 1;
+  a.d_tr = (a.parity == 0) ? (cfg->D + 1) / 2 : cfg->D / 2;
+  a.c = make_rqs_consts(cfg);
+  int row_floats = a.d_tr * a.c.P;
+  a.rows = pick_rows(row_floats, a.d_tr);
+  int threads = pick_threads(a.rows, a.d_tr);
+  size_t smem = (size_t)RQS_STAGES * a.rows * row_floats * 4 + 8 + RQS_STAGES * 8 + 16;
+  FP_CUDA_OK(cudaFuncSetAttribute(k_rqs_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  FP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rqs_backward, threads, smem));
+  if (occ < 1) occ = 1;
+  int64_t ntiles = (R + a.rows - 1) / a.rows;
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
+  k_rqs_backward<<<grid, threads, smem, stream>>>(a);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace fp
+
+extern "C" {
+
+int fp_rqs_forward(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
+                   float* theta_out, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status, void* stream) {
+  return fp::launch_rqs_apply(false, cfg, parity, theta_in, params, theta_out, nullptr, logdet, bin_idx, R, status,
+                              nullptr, nullptr, 1.f, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int fp_rqs_inverse(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
+                   float* theta_out, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status, void* stream) {
+  return fp::launch_rqs_apply(true, cfg, parity, theta_in, params, theta_out, nullptr, logdet, bin_idx, R, status,
+                              nullptr, nullptr, 1.f, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int fp_rqs_backward(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
+                    const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
+                    int64_t R, void* stream) {
+  return fp::launch_rqs_backward(cfg, parity, theta_in, params, d_theta_out, d_logdet, d_params, d_theta_in, R,
+                                 (cudaStream_t)stream);
+}
+
+}  // extern "C"

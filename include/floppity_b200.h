@@ -1,0 +1,193 @@
+/* floppity_b200.h -- C ABI of the B200-native neural-spline-flow hot path.
+ *
+ * This is the drop-in boundary.  The reference (FlopPITy) reaches the path through
+ * sbi/nflows Python objects:
+ *     modules.py:63      posterior_nn(model='nsf', ...)                  (build)
+ *     modules.py:64      SNPE_C(prior, density_estimator, device)        (trainer)
+ *     floppity.py:216    inference.append_simulations(theta, x, proposal)
+ *     floppity.py:219    inference.train(...)                            (fwd+bwd+Adam loop)
+ *     floppity.py:225    inference.build_posterior(net).set_default_x(x)
+ *     floppity.py:252    proposal.sample((n,))                           (inverse flow)
+ *     floppityFUN.py:35  posterior.log_prob(theta, x=default_x)          (forward flow)
+ * The host side of this repo (floppity_deprecated_b200/*.py) keeps those Python names and
+ * calls the functions below through ctypes.  Conventions:
+ *   - plain pointers + sizes, no torch types; every pointer is DEVICE memory owned by the
+ *     caller (row-major, contiguous, fp32 unless stated), 16-byte aligned;
+ *   - nothing is allocated or freed here; kernels are enqueued on `stream` (a cudaStream_t
+ *     passed as void*) and the call returns without synchronising;
+ *   - return value: 0 = ok, >0 = cudaError_t of a failed launch, <0 = FP_E_* below;
+ *   - `status` words are device int32[4]: {n_nonfinite, n_negative_discriminant, 0, 0},
+ *     accumulated with atomics so the Python wrapper can raise like upstream's
+ *     assert_all_finite / `assert (discriminant >= 0).all()`.
+ */
+#ifndef FLOPPITY_B200_H
+#define FLOPPITY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FP_E_BADARG   (-1)
+#define FP_E_TOOLARGE (-2)
+#define FP_E_NOTREADY (-3)
+
+/* Hyper-parameters of build_nsf (sbi.neural_nets.flow.build_nsf as called through
+ * posterior_nn at modules.py:63; flags floppity.py:34,35,48,50,57). */
+typedef struct fp_nsf_config {
+  int32_t D;              /* dim(theta)                                   */
+  int32_t C;              /* dim(context) = spectral bins after embedding */
+  int32_t T;              /* num_transforms (coupling + LU pairs)         */
+  int32_t K;              /* num_bins                                     */
+  int32_t H;              /* hidden_features                              */
+  int32_t Bk;             /* num_blocks                                   */
+  float tail_bound;       /* 3.0 (sbi default; floppity's -tail_bound is NOT forwarded) */
+  float min_bin_width;    /* 1e-3 */
+  float min_bin_height;   /* 1e-3 */
+  float min_derivative;   /* 1e-3 */
+  float lu_eps;           /* 1e-3 */
+  float dropout_p;        /* floppity.py:57 */
+} fp_nsf_config;
+
+/* ---- parameter layout (one flat fp32 buffer; grads / Adam moments share it) ---------- */
+enum fp_param_kind {
+  FP_P_CTX_W = 0,   /* [H, C]   slot `block`: 0 = context columns of initial_layer, 1+b = blocks.b.context_layer */
+  FP_P_CTX_B = 1,   /* [H]      slot `block`: 0 = initial_layer.bias,               1+b = blocks.b.context_layer.bias */
+  FP_P_W0X   = 2,   /* [H, D]   theta columns of initial_layer, expanded to all D (transform columns are structural zeros) */
+  FP_P_W1    = 3,   /* [H, H]   blocks.b.linear_layers.0.weight */
+  FP_P_B1    = 4,   /* [H] */
+  FP_P_W2    = 5,   /* [H, H]   blocks.b.linear_layers.1.weight */
+  FP_P_B2    = 6,   /* [H] */
+  FP_P_WF    = 7,   /* [d_tr*(3K-1), H] final_layer.weight */
+  FP_P_BF    = 8,   /* [d_tr*(3K-1)] */
+  FP_P_LU_LOWER = 9,  /* [D(D-1)/2] row-major strict lower */
+  FP_P_LU_UPPER = 10, /* [D(D-1)/2] row-major strict upper */
+  FP_P_LU_DIAG  = 11, /* [D] unconstrained_upper_diag */
+  FP_P_LU_BIAS  = 12  /* [D] */
+};
+int64_t fp_nsf_param_count(const fp_nsf_config* cfg);
+/* gradient buffer = parameter layout + a tail holding the LU product-matrix gradients and sum(d_logp) */
+int64_t fp_nsf_grad_count(const fp_nsf_config* cfg);
+int64_t fp_nsf_param_offset(const fp_nsf_config* cfg, int32_t layer, int32_t kind, int32_t block);
+int64_t fp_nsf_param_size(const fp_nsf_config* cfg, int32_t layer, int32_t kind);
+/* number of transformed features of coupling layer `layer` (mask alternates, even layer -> features 0,2,4..) */
+int32_t fp_nsf_dtr(const fp_nsf_config* cfg, int32_t layer);
+/* floats of the per-step derived buffer (W=L*U, L, U, logdet per layer) filled by fp_nsf_prepare */
+int64_t fp_nsf_prepared_count(const fp_nsf_config* cfg);
+/* floats of workspace for R flow rows sharing Rc context rows; training=1 keeps activations for backward */
+int64_t fp_nsf_workspace_count(const fp_nsf_config* cfg, int64_t R, int64_t Rc, int32_t training);
+
+/* ---- spline kernels: nflows rational_quadratic_spline behind
+ *      PiecewiseRationalQuadraticCouplingTransform (reached from modules.py:63) ---------- */
+/* theta_in/out: [R, D]; params: [R, d_tr, 3K-1] raw conditioner output (width/height logits are
+ * divided by sqrt(H) inside); logdet[R] is ACCUMULATED (+=); bin_idx (may be NULL): int32 [R, d_tr],
+ * -1 for inputs in the linear tails. Features f with f%2 == parity are transformed, the others copied. */
+int fp_rqs_forward(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
+                   float* theta_out, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status, void* stream);
+int fp_rqs_inverse(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
+                   float* theta_out, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status, void* stream);
+/* d_theta_out [R, D], d_logdet [R] -> d_params [R, d_tr, 3K-1] (overwritten), d_theta_in [R, D] (overwritten:
+ * transformed features get the spline input-gradient, identity features a copy of d_theta_out). */
+int fp_rqs_backward(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
+                    const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
+                    int64_t R, void* stream);
+
+/* ---- fp32 SIMT GEMM with fused conditioner epilogues (nflows ResidualNet, reached from modules.py:63) ----
+ * C[M,N] = op(A)[M,K] * op(B)[N,K]^T ; a_kmajor: A(m,k) at A[m*lda+k] else A[k*lda+m]; same for B.
+ * flags: see FP_G_* ; aux pointers per epilogue. */
+enum fp_gemm_flags {
+  FP_G_RELU_A      = 1,   /* A := max(A,0) on load */
+  FP_G_RELU_B      = 2,   /* B := max(B,0) on load */
+  FP_G_BIAS        = 4,   /* + bias[n] */
+  FP_G_ADD_CTX     = 8,   /* + G[m/ctx_div (0 if ctx_div==0), n]  (ldg) */
+  FP_G_GLU_RES     = 16,  /* U[m,n]=v (if U); C = Rsd[m,n] + v*sigmoid(G[..]) */
+  FP_G_RELUMASK    = 32,  /* C = v * (Msk[m,n] > 0) */
+  FP_G_ACCUM       = 64,  /* C += (after the above) */
+  FP_G_ATOMIC      = 128, /* split-K: atomicAdd into C */
+  FP_G_TF32X3      = 256, /* use the tcgen05 3xTF32 path when shapes allow (fp32-accurate) */
+  FP_G_DROP_A      = 512, /* inverted dropout on A on load (engine-internal; needs the engine's seed) */
+  FP_G_DROP_B      = 1024,
+  FP_G_DROPMASK    = 2048 /* dropout mask applied with FP_G_RELUMASK in the backward */
+};
+typedef struct fp_gemm_args {
+  const float* A; int64_t lda; int32_t a_kmajor;
+  const float* B; int64_t ldb; int32_t b_kmajor;
+  float* C; int64_t ldc;
+  int64_t M; int32_t N; int64_t K;
+  int32_t flags;
+  const float* bias;
+  const float* G; int64_t ldg; int32_t ctx_div;
+  const float* Rsd; int64_t ldr;
+  float* U; int64_t ldu;
+  const float* Msk; int64_t ldm;
+  int32_t split_k;
+} fp_gemm_args;
+int fp_gemm(const fp_gemm_args* args, void* stream);
+
+/* ---- whole-flow entry points --------------------------------------------------------------- */
+/* Derive per-step constants from the parameters (W = L*U, L, U, sum log diag U). */
+int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepared, void* stream);
+
+/* Flow.log_prob (nflows Flow._log_prob; floppityFUN.py:35, and the training loss floppity.py:219).
+ * theta [R, D] raw; ctx [Rc, C] ALREADY standardised; row r uses context row r / (R/Rc).
+ * zshift/zscale [D] = the theta z-score affine; zlogdet = sum log|zscale|.
+ * logp [R] out.  workspace from fp_nsf_workspace_count(cfg, R, Rc, training). */
+int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const float* prepared,
+                           const float* theta, const float* ctx, int64_t R, int64_t Rc,
+                           const float* zshift, const float* zscale, float zlogdet,
+                           float* logp, float* workspace, int32_t training, uint64_t dropout_seed,
+                           int32_t* status, void* stream);
+/* Backward of the above given d_logp [R]; ACCUMULATES into grads (same layout as params);
+ * d_theta (may be NULL) [R, D] receives dL/dtheta (raw theta). Must follow a training=1 forward
+ * with the same workspace. */
+int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const float* prepared,
+                            const float* ctx, int64_t R, int64_t Rc, const float* zscale,
+                            const float* d_logp, float* grads, float* d_theta, float* workspace,
+                            uint64_t dropout_seed, void* stream);
+/* Fold d(W=L*U) etc. accumulated by the backward into the LU parameter gradients and zero the
+ * structural zeros of W0X. Call once after all backward passes of a step. */
+int fp_nsf_finish_grads(const fp_nsf_config* cfg, const float* params, const float* prepared,
+                        float* grads, void* stream);
+
+/* Flow.sample inverse pass (nflows Flow._sample; floppity.py:252): z [R, D] base noise -> theta [R, D].
+ * ctx [Rc, C] standardised; Rc==1 is the hoisted single-observation case. */
+int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* prepared,
+                  const float* z, const float* ctx, int64_t R, int64_t Rc,
+                  const float* zshift, const float* zscale, float* theta_out, float* workspace,
+                  int32_t* status, void* stream);
+
+/* ---- SNPE-C atomic loss (sbi SNPE_C._log_prob_proposal_posterior_atomic; floppity.py:219-221) ---- */
+/* choices int32 [B, A-1]: A-1 distinct indices != b, uniform (Floyd sampling, counter RNG). */
+int fp_atom_choices(int32_t* choices, int64_t B, int32_t A, uint64_t seed, void* stream);
+/* rows [B*A, D] = cat(theta[b], theta[choices[b,:]]). */
+int fp_atom_gather(const float* theta, const int32_t* choices, float* rows, int64_t B, int32_t A, int32_t D, void* stream);
+/* logp [B, A]; atom_theta [B*A, D]; low/high [D]; masks [B] (may be NULL => 0);
+ * out_lp [B] = u0 - logsumexp(u) (+ masks*logp[:,0] if combined); d_logp [B, A] = d(-mean out_lp)/d logp (may be NULL). */
+int fp_atomic_loss(const float* logp, const float* atom_theta, const float* low, const float* high,
+                   const float* masks, int32_t combined, float* out_lp, float* d_logp,
+                   int64_t B, int32_t A, int32_t D, int32_t* status, void* stream);
+
+/* ---- optimiser: clip_grad_norm_(5.0) + Adam (sbi PosteriorEstimator.train; floppity.py:219) ------ */
+/* sumsq[0] must be zeroed by the caller before fp_grad_sumsq; fp_adam_step reads it (after an
+ * optional all-reduce) and applies clip coefficient min(1, max_norm/(sqrt(sumsq)+1e-6)) * grad_scale. */
+int fp_grad_sumsq(const float* grads, int64_t n, float* sumsq, void* stream);
+int fp_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                 float beta2, float eps, const int32_t* step_dev, float max_norm, float grad_scale,
+                 const float* sumsq, void* stream);
+
+/* ---- small utilities on the path -------------------------------------------------------------- */
+int fp_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n, int32_t width, void* stream);
+/* out = (x - mean)/std  (sbi Standardize in front of the flow) */
+int fp_standardize(const float* x, const float* mean, const float* std, float* out, int64_t n, int32_t width, void* stream);
+/* out[i] = scale*sum(x) accumulated into out[0] */
+int fp_sum(const float* x, int64_t n, float scale, float* out, void* stream);
+/* BoxUniform support test: inside[r] = all(low <= theta[r] <= high) (uint8) */
+int fp_within_box(const float* theta, const float* low, const float* high, uint8_t* inside, int64_t R, int32_t D, void* stream);
+
+const char* fp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOPPITY_B200_H */
