@@ -12,6 +12,7 @@
 // can be captured in a CUDA graph.
 #include "common.cuh"
 #include "layout.h"
+#include "prof.h"
 #include <math.h>
 
 namespace fp {
@@ -216,6 +217,7 @@ int64_t fp_nsf_workspace_count(const fp_nsf_config* cfg, int64_t R, int64_t Rc, 
 int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepared, void* stream) {
   FP_TRY(check_cfg(cfg));
   size_t sm = (size_t)3 * cfg->D * cfg->D * 4;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_lu_prepare<<<cfg->T, 128, sm, (cudaStream_t)stream>>>(params, prepared, *cfg);
   FP_LAUNCH_CHECK();
   return 0;
@@ -224,6 +226,7 @@ int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepare
 int fp_nsf_finish_grads(const fp_nsf_config* cfg, const float* params, const float* prepared, float* grads, void* stream) {
   FP_TRY(check_cfg(cfg));
   size_t sm = (size_t)3 * cfg->D * cfg->D * 4;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_lu_finish<<<cfg->T, 128, sm, (cudaStream_t)stream>>>(params, prepared, grads, *cfg);
   FP_LAUNCH_CHECK();
   return 0;

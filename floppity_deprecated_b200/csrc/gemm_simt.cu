@@ -8,6 +8,7 @@
 // forward (NT), dgrad (NN) and wgrad (TN, split-K with atomics) through the two "k-major" switches.
 // This is the exact-fp32 path; the tcgen05 path (gemm_tc.cu) takes over the large context projection.
 #include "common.cuh"
+#include "prof.h"
 #include <algorithm>
 
 namespace fp {
@@ -235,6 +236,7 @@ int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int dro
   if (nt > 65535 || split > 65535 || mt > 2147483647LL) return FP_E_TOOLARGE;
   dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)split);
   GemmDrop d{drop_p, drop_seed, drop_width};
+  ProfScope ps(TAG_GEMM_SIMT, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream);
   if (a->a_kmajor && a->b_kmajor) k_gemm<true, true><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);
   else if (a->a_kmajor && !a->b_kmajor) k_gemm<true, false><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);
   else if (!a->a_kmajor && a->b_kmajor) k_gemm<false, true><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);

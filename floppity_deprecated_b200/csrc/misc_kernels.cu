@@ -5,6 +5,7 @@
 // floppity.py:216-225,252; spec SURVEY.md Appendix A).
 #include "common.cuh"
 #include "layout.h"
+#include "prof.h"
 #include <math.h>
 #include <algorithm>
 
@@ -389,38 +390,46 @@ static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / 
 int launch_affine_fwd(const float* theta, const float* shift, const float* scale, float zlogdet, float* out, float* logdet,
                       int64_t R, int D, cudaStream_t s) {
   int64_t n = R * D > R ? R * D : R;
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_affine_fwd<<<nblk(n, 256), 256, 0, s>>>(theta, shift, scale, zlogdet, out, logdet, R, D);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_affine_inv(const float* y, const float* shift, const float* scale, float* out, int64_t R, int D, cudaStream_t s) {
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_affine_inv<<<nblk(R * D, 256), 256, 0, s>>>(y, shift, scale, out, R, D);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_affine_bwd(const float* d0, const float* scale, float* out, int64_t R, int D, cudaStream_t s) {
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_affine_bwd<<<nblk(R * D, 256), 256, 0, s>>>(d0, scale, out, R, D);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_base_logprob(const float* z, const float* logdet, float* logp, int64_t R, int D, int32_t* status, cudaStream_t s) {
   float log_z = (float)(0.5 * D * log(2.0 * M_PI));
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_base_logprob<<<nblk(R, 256), 256, 0, s>>>(z, logdet, logp, R, D, log_z, status);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_base_bwd(const float* z, const float* d_logp, float* dz, int64_t R, int D, cudaStream_t s) {
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_base_bwd<<<nblk(R * D, 256), 256, 0, s>>>(z, d_logp, dz, R, D);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_rows_affine(const float* x, const float* M, const float* pre, float sgn, const float* post, float* y, int64_t R,
                        int D, cudaStream_t s) {
   size_t sm = (size_t)(D * D + D) * 4;
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_rows_affine<<<nblk(R * D, 256), 256, sm, s>>>(x, M, pre, sgn, post, y, R, D);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_glu_bwd(const float* dh, const float* u, const float* G, int64_t ldg, float* du, float* dG, int64_t Rc, int A,
                    int H, cudaStream_t s) {
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_glu_bwd<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, u, G, ldg, du, dG, Rc, A, H);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_ctx_reduce(const float* dh, float* dG, int64_t ldg, int64_t Rc, int A, int H, cudaStream_t s) {
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_ctx_reduce<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, dG, ldg, Rc, A, H);
   FP_LAUNCH_CHECK(); return 0;
 }
@@ -430,12 +439,14 @@ int launch_colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, cud
   int64_t by = (M + rpb - 1) / rpb;
   while (by > 65535) { rpb *= 2; by = (M + rpb - 1) / rpb; }
   dim3 grid((N + 127) / 128, (unsigned)by);
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_colsum<<<grid, 128, 0, s>>>(X, ldx, M, N, out, rpb);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_sum(const float* x, int64_t n, float scale, float* out, cudaStream_t s) {
   int blocks = (int)std::min<int64_t>((n + 1023) / 1024, 4 * num_sms());
   if (blocks < 1) blocks = 1;
+  ProfScope ps(TAG_OTHER, 0.0, s);
   k_sum<<<blocks, 256, 0, s>>>(x, n, scale, out);
   FP_LAUNCH_CHECK(); return 0;
 }
@@ -448,16 +459,19 @@ extern "C" {
 
 int fp_atom_choices(int32_t* choices, int64_t B, int32_t A, uint64_t seed, void* stream) {
   if (A < 2 || A > B || A > 4096) return FP_E_BADARG;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_atom_choices<<<nblk(B, 128), 128, 0, (cudaStream_t)stream>>>(choices, B, A, seed);
   FP_LAUNCH_CHECK(); return 0;
 }
 int fp_atom_gather(const float* theta, const int32_t* choices, float* rows, int64_t B, int32_t A, int32_t D, void* stream) {
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_atom_gather<<<nblk(B * A * D, 256), 256, 0, (cudaStream_t)stream>>>(theta, choices, rows, B, A, D);
   FP_LAUNCH_CHECK(); return 0;
 }
 int fp_atomic_loss(const float* logp, const float* atom_theta, const float* low, const float* high, const float* masks,
                    int32_t combined, float* out_lp, float* d_logp, int64_t B, int32_t A, int32_t D, int32_t* status,
                    void* stream) {
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_atomic_loss<<<nblk(B, 128), 128, 0, (cudaStream_t)stream>>>(logp, atom_theta, low, high, masks, combined, out_lp,
                                                                 d_logp, B, A, D, status);
   FP_LAUNCH_CHECK(); return 0;
@@ -465,6 +479,7 @@ int fp_atomic_loss(const float* logp, const float* atom_theta, const float* low,
 int fp_grad_sumsq(const float* grads, int64_t n, float* sumsq, void* stream) {
   int blocks = (int)std::min<int64_t>((n + 1023) / 1024, 4 * num_sms());
   if (blocks < 1) blocks = 1;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_sumsq<<<blocks, 256, 0, (cudaStream_t)stream>>>(grads, n, sumsq);
   FP_LAUNCH_CHECK(); return 0;
 }
@@ -472,17 +487,20 @@ int fp_adam_step(float* params, const float* grads, float* m, float* v, int64_t 
                  float eps, const int32_t* step_dev, float max_norm, float grad_scale, const float* sumsq, void* stream) {
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 8 * num_sms());
   if (blocks < 1) blocks = 1;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr, beta1, beta2, eps, step_dev, max_norm,
                                                     grad_scale, sumsq);
   FP_LAUNCH_CHECK(); return 0;
 }
 int fp_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n, int32_t width, void* stream) {
   if (n <= 0) return 0;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_gather_rows<<<nblk(n * width, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n, width);
   FP_LAUNCH_CHECK(); return 0;
 }
 int fp_standardize(const float* x, const float* mean, const float* std, float* out, int64_t n, int32_t width, void* stream) {
   if (n <= 0) return 0;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_standardize<<<nblk(n * width, 256), 256, 0, (cudaStream_t)stream>>>(x, mean, std, out, n, width);
   FP_LAUNCH_CHECK(); return 0;
 }
@@ -491,6 +509,7 @@ int fp_sum(const float* x, int64_t n, float scale, float* out, void* stream) {
 }
 int fp_within_box(const float* theta, const float* low, const float* high, uint8_t* inside, int64_t R, int32_t D, void* stream) {
   if (R <= 0) return 0;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_within_box<<<nblk(R, 256), 256, 0, (cudaStream_t)stream>>>(theta, low, high, inside, R, D);
   FP_LAUNCH_CHECK(); return 0;
 }

@@ -14,6 +14,7 @@
 // HBM traffic per sample per layer = params + theta in + theta out + logdet.
 #include "common.cuh"
 #include "rqs_math.cuh"
+#include "prof.h"
 #include <math.h>
 #include <algorithm>
 
@@ -319,6 +320,8 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
   if (occ < 1) occ = 1;
   int64_t ntiles = (R + a.rows - 1) / a.rows;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
+  // algorithmic bytes: params + theta in + theta out (transformed features) + logdet
+  ProfScope ps(inverse ? TAG_RQS_INV : TAG_RQS_FWD, 4.0 * (double)R * ((double)row_floats + 2.0 * a.d_tr + 1.0), stream);
   kern<<<grid, threads, smem, stream>>>(a);
   FP_LAUNCH_CHECK();
   return 0;
@@ -345,6 +348,7 @@ int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta
   if (occ < 1) occ = 1;
   int64_t ntiles = (R + a.rows - 1) / a.rows;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
+  ProfScope ps(TAG_RQS_BWD, 4.0 * (double)R * (2.0 * row_floats + 3.0 * a.d_tr + 1.0), stream);
   k_rqs_backward<<<grid, threads, smem, stream>>>(a);
   FP_LAUNCH_CHECK();
   return 0;

@@ -467,16 +467,24 @@ def build_nsf(batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score
                    generator=generator)
 
 
+class _NSFBuilder:
+    """Picklable ``build_fn(batch_theta, batch_x)`` (upstream returns a closure and has to drop it when the
+    inference object is pickled at floppity.py:247; a class keeps ``-resume`` able to retrain from scratch)."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __call__(self, batch_theta, batch_x) -> NSFFlow:
+        kw = dict(self.kw)
+        return build_nsf(batch_x=batch_theta, batch_y=batch_x, z_score_x=kw.pop("z_score_theta"),
+                         z_score_y=kw.pop("z_score_x"), **kw)
+
+
 def posterior_nn(model: str, z_score_theta="independent", z_score_x="independent", hidden_features: int = 50,
                  num_transforms: int = 5, num_bins: int = 10, embedding_net: Optional[nn.Module] = None,
                  num_components: int = 10, **kwargs) -> Callable:
     """sbi ``posterior_nn`` as called at modules.py:63: returns ``build_fn(batch_theta, batch_x)``."""
     if model != "nsf":
         raise NotImplementedError("only model='nsf' is on the FlopPITy hot path (floppity.py:43 default)")
-
-    def build_fn(batch_theta, batch_x):
-        return build_nsf(batch_x=batch_theta, batch_y=batch_x, z_score_x=z_score_theta, z_score_y=z_score_x,
-                         hidden_features=hidden_features, num_transforms=num_transforms, num_bins=num_bins,
-                         embedding_net=embedding_net, **kwargs)
-
-    return build_fn
+    return _NSFBuilder(z_score_theta=z_score_theta, z_score_x=z_score_x, hidden_features=hidden_features,
+                       num_transforms=num_transforms, num_bins=num_bins, embedding_net=embedding_net, **kwargs)

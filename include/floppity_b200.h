@@ -185,6 +185,13 @@ int fp_sum(const float* x, int64_t n, float scale, float* out, void* stream);
 /* BoxUniform support test: inside[r] = all(low <= theta[r] <= high) (uint8) */
 int fp_within_box(const float* theta, const float* low, const float* high, uint8_t* inside, int64_t R, int32_t D, void* stream);
 
+/* ---- launch accounting (bench.py: gpu_launches and the live roofline numbers) -----------------------
+ * classes: 0 SIMT GEMM (work = flops), 1 tcgen05 GEMM (flops), 2 spline fwd, 3 spline inverse, 4 spline
+ * backward (work = algorithmic bytes), 5 everything else. */
+int64_t fp_launch_count(void);
+int fp_prof_enable(int32_t on);
+int fp_prof_collect(double* ms /*[6]*/, int64_t* launches /*[6]*/, double* work /*[6]*/);
+
 const char* fp_version(void);
 
 #ifdef __cplusplus

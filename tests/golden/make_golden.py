@@ -1,0 +1,101 @@
+"""Writes the golden fixtures under tests/golden/ from the CPU oracle (oracle/nsf_oracle.py) with fixed seeds.
+
+SELF-GENERATED FROM THE RESTATEMENT: the reference ships no tests or fixtures and sbi/nflows cannot be installed
+here, so these vectors pin the oracle against drift and give the CUDA path a fixed target; they do not prove
+byte-equality with upstream sbi ("parity unpinned").
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+from oracle import nsf_oracle as O  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (D, C, T, K, H, Bk, B, store_weights)
+    "c1": (10, 100, 5, 8, 50, 2, 64, True),          # BASELINE.json configs[0] hyper-parameters
+    "odd": (7, 33, 3, 5, 20, 1, 37, True),           # odd D (d_tr != d_id), ragged batch
+    "c2": (20, 500, 10, 10, 128, 2, 16, False),      # configs[1] hyper-parameters; weights re-created from the seed
+}
+
+
+def build_case(name, seed=20260101):
+    D, C, T, K, H, Bk, B, _ = CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    theta_tr = (torch.rand(512, D, generator=g) * 6 - 3)
+    x_tr = torch.randn(512, C, generator=g) * 1.5 + 0.3
+    net = O.build_nsf(theta_tr, x_tr, hidden_features=H, num_transforms=T, num_bins=K, num_blocks=Bk)
+    O.randomize_lu(net, g, 0.3 / np.sqrt(D))
+    # make the conditioner non-trivial (block second layers start at +-1e-3 upstream)
+    with torch.no_grad():
+        for c in O.coupling_layers(net):
+            for blk in c.transform_net.blocks:
+                blk.linear_layers[1].weight.add_(0.05 * torch.randn(blk.linear_layers[1].weight.shape, generator=g))
+    net.eval()
+    theta = (torch.rand(B, D, generator=g) * 6.4 - 3.2)      # a few rows land in the linear tails
+    theta[0, 0], theta[1, 1] = 3.0, -3.0                     # exactly on the boundary knots (inside)
+    x = torch.randn(B, C, generator=g) * 1.5 + 0.3
+    z = torch.randn(B, D, generator=g)
+    return net, theta_tr, x_tr, theta, x, z, g
+
+
+def run_case(name):
+    D, C, T, K, H, Bk, B, store_w = CASES[name]
+    net, theta_tr, x_tr, theta, x, z, g = build_case(name)
+    out = dict(theta_train=theta_tr.numpy(), x_train=x_tr.numpy(), theta=theta.numpy(), x=x.numpy(), z=z.numpy())
+    O.set_record_bins(net, True)
+    th = theta.clone().requires_grad_(True)
+    logp = net.log_prob(th, x)
+    out["bins"] = np.stack([np.pad(c.last_bins[0].numpy(), ((0, 0), (0, (D + 1) // 2 - c.last_bins[0].shape[1])),
+                                   constant_values=-9) for c in O.coupling_layers(net)])
+    out["knot_dist"] = np.stack([np.pad(c.last_bins[1].detach().numpy(), ((0, 0), (0, (D + 1) // 2 - c.last_bins[1].shape[1])),
+                                        constant_values=np.inf) for c in O.coupling_layers(net)])
+    O.set_record_bins(net, False)
+    out["logp"] = logp.detach().numpy()
+    loss = -logp.mean()
+    net.zero_grad()
+    loss.backward()
+    out["d_theta"] = th.grad.numpy()
+    grads = {k: p.grad.numpy().copy() for k, p in net.named_parameters()}
+    out["grad_keys"] = np.array(sorted(grads.keys()))
+    out["grad_norms"] = np.array([np.linalg.norm(grads[k]) for k in sorted(grads.keys())])
+    last = sorted(k for k in grads if k.endswith("final_layer.bias"))[-1]
+    out["grad_final_bias_key"] = np.array(last)
+    out["grad_final_bias"] = grads[last]
+    # fp64 ground truth of the same network
+    net64 = O.build_nsf(theta_tr.double(), x_tr.double(), hidden_features=H, num_transforms=T, num_bins=K, num_blocks=Bk).double()
+    net64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in net.state_dict().items()})
+    net64.eval()
+    out["logp64"] = net64.log_prob(theta.double(), x.double()).detach().numpy()
+    with torch.no_grad():
+        # sampling: one observation, fixed base noise
+        out["samples_one_x"] = net.sample(B, context=x[:1], noise=z).numpy()[0]
+        # sampling: per-row contexts (num_samples = 1 per context row)
+        out["samples_per_row"] = net.sample(1, context=x, noise=z).numpy()[:, 0]
+        # atomic loss with injected choices
+        A = 4
+        choices = torch.stack([torch.tensor([j for j in torch.randperm(B, generator=g).tolist() if j != b][:A - 1]) for b in range(B)])
+        prior = O.BoxUniform(-3.3 * torch.ones(D), 3.3 * torch.ones(D))
+        masks = (torch.rand(B, 1, generator=g) > 0.5).float()
+        out["atom_choices"] = choices.numpy()
+        out["atom_masks"] = masks.numpy()
+        out["atomic_lp"] = O.log_prob_proposal_posterior_atomic(net, prior, theta.clamp(-3.2, 3.2), x, masks, A, True, choices).numpy()
+    if store_w:
+        for k, v in net.state_dict().items():
+            out["sd/" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, f"golden_{name}.npz"), **out)
+    print(name, "logp[:3]", out["logp"][:3], "max|fp32-fp64|", np.abs(out["logp"] - out["logp64"]).max(),
+          "tails", int((np.abs(theta.numpy()) > 3).sum()))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    for n in CASES:
+        run_case(n)

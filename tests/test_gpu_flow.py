@@ -1,0 +1,195 @@
+"""GPU parity, part 2: the whole flow through the reference-facing Python surface (build_nsf / log_prob / sample /
+SNPE_C.train / DirectPosterior) against the oracle and the committed golden vectors.  Tolerance: 1e-4 relative
+(|a-b| / max(1,|b|)) for log_prob and transformed samples (BASELINE.json north_star), fp32 throughout."""
+import copy
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import floppity_deprecated_b200 as fb
+from conftest import golden_oracle_net, rel_err
+from floppity_deprecated_b200 import synthetic
+from oracle import nsf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _twin(onet, cfg):
+    """CUDA flow carrying exactly the oracle network's weights (through the upstream-keyed state_dict)."""
+    D, C, T, K, H, Bk = cfg[:6]
+    net = fb.NSFFlow(D, C, hidden_features=H, num_transforms=T, num_bins=K, num_blocks=Bk)
+    net.load_state_dict(onet.state_dict())
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize("name", ["c1", "odd", "c2"])
+def test_log_prob_matches_golden_and_oracle(name):
+    onet, g, cfg = golden_oracle_net(name)
+    net = _twin(onet, cfg)
+    theta, x = torch.tensor(g["theta"]), torch.tensor(g["x"])
+    lp = net.log_prob(theta.cuda(), x.cuda()).cpu().numpy()
+    assert rel_err(lp, g["logp"]).max() < TOL, rel_err(lp, g["logp"]).max()
+    # and not further from the fp64 truth than the fp32 oracle is (plus the bar)
+    assert rel_err(lp, g["logp64"]).max() < TOL + rel_err(g["logp"], g["logp64"]).max()
+    # single broadcast context row == repeated rows (context hoisting must not change results)
+    lp1 = net.log_prob(theta.cuda(), x[:1].cuda()).cpu().numpy()
+    with torch.no_grad():
+        want1 = onet.log_prob(theta, x[:1].expand(theta.shape[0], -1)).numpy()
+    assert rel_err(lp1, want1).max() < TOL
+
+
+@pytest.mark.parametrize("name", ["c1", "odd", "c2"])
+def test_samples_match_golden_for_fixed_noise(name):
+    onet, g, cfg = golden_oracle_net(name)
+    net = _twin(onet, cfg)
+    x, z = torch.tensor(g["x"]), torch.tensor(g["z"])
+    B = z.shape[0]
+    s1 = net.sample(B, context=x[:1].cuda(), noise=z.cuda())[0].cpu().numpy()
+    assert rel_err(s1, g["samples_one_x"]).max() < TOL, rel_err(s1, g["samples_one_x"]).max()
+    s2 = net.sample(1, context=x.cuda(), noise=z.cuda())[:, 0].cpu().numpy()
+    assert rel_err(s2, g["samples_per_row"]).max() < TOL
+    # encode -> decode round trip on the device: log_prob's z of the samples is the noise
+    lp = net.log_prob(torch.tensor(s1).cuda(), x[:1].cuda())
+    with torch.no_grad():
+        want = onet.log_prob(torch.tensor(s1), x[:1].expand(B, -1))
+    assert rel_err(lp.cpu().numpy(), want.numpy()).max() < TOL
+
+
+@pytest.mark.parametrize("name", ["c1", "odd", "c2"])
+def test_gradients_match_golden_and_oracle(name):
+    onet, g, cfg = golden_oracle_net(name)
+    net = _twin(onet, cfg)
+    net.train()
+    theta = torch.tensor(g["theta"]).cuda().requires_grad_()
+    x = torch.tensor(g["x"]).cuda()
+    loss = -net.log_prob(theta, x).mean()
+    loss.backward()
+    grads = {k: v.cpu().numpy() for k, v in net.unpack(net._flat.grad).items()}
+    keys = [str(k) for k in g["grad_keys"]]
+    assert sorted(grads) == keys
+    norms = np.array([np.linalg.norm(grads[k]) for k in keys])
+    bad = [(k, a, b) for k, a, b in zip(keys, norms, g["grad_norms"]) if abs(a - b) > 2e-3 * max(b, 1e-3)]
+    assert not bad, bad[:5]
+    kb = str(g["grad_final_bias_key"])
+    assert np.abs(grads[kb] - g["grad_final_bias"]).max() < 2e-3 * np.abs(g["grad_final_bias"]).max()
+    assert np.abs(theta.grad.cpu().numpy() - g["d_theta"]).max() < 2e-3 * np.abs(g["d_theta"]).max()
+    # full tensor-by-tensor check against the oracle's autograd
+    onet.zero_grad()
+    (-onet.log_prob(torch.tensor(g["theta"]), torch.tensor(g["x"])).mean()).backward()
+    for k, p in onet.named_parameters():
+        ref = p.grad.numpy()
+        err = np.abs(grads[k] - ref).max()
+        assert err < 2e-3 * max(np.abs(ref).max(), 1e-4), (k, err, np.abs(ref).max())
+
+
+def test_atomic_loss_path_matches_golden():
+    onet, g, cfg = golden_oracle_net("c1")
+    net = _twin(onet, cfg)
+    D = cfg[0]
+    theta = torch.tensor(g["theta"]).clamp(-3.2, 3.2)
+    x, choices, masks = torch.tensor(g["x"]), torch.tensor(g["atom_choices"]), torch.tensor(g["atom_masks"])
+    B, A = theta.shape[0], choices.shape[1] + 1
+    rows = torch.cat([theta[:, None], theta[choices]], dim=1).reshape(B * A, D)
+    lp = net.log_prob(rows.cuda(), x.cuda())              # R = B*A rows share B context rows (no repeat)
+    from floppity_deprecated_b200 import _lib
+    out = torch.empty(B, device="cuda")
+    low, high = (-3.3 * torch.ones(D)).cuda(), (3.3 * torch.ones(D)).cuda()
+    _lib.check(_lib.lib().fp_atomic_loss(_lib.ptr(lp), _lib.ptr(rows.cuda()), _lib.ptr(low), _lib.ptr(high),
+                                         _lib.ptr(masks.reshape(-1).cuda()), 1, _lib.ptr(out), None, B, A, D, None, _lib.stream()), "loss")
+    assert rel_err(out.cpu().numpy(), g["atomic_lp"]).max() < TOL
+
+
+def test_training_steps_track_the_oracle():
+    """Three optimiser steps (MLE and atomic) on identical batches: parameters stay within fp32 noise of torch Adam."""
+    torch.manual_seed(0)
+    D, C, B = 6, 12, 64
+    theta, x = torch.rand(256, D) * 6 - 3, torch.randn(256, C)
+    onet = O.build_nsf(theta, x, hidden_features=24, num_transforms=3, num_bins=6, num_blocks=2)
+    O.randomize_lu(onet, torch.Generator().manual_seed(1), 0.1)
+    prior_o = O.BoxUniform(-3 * torch.ones(D), 3 * torch.ones(D))
+    prior = fb.BoxUniform(-3 * torch.ones(D), 3 * torch.ones(D), device="cuda")
+    from floppity_deprecated_b200.inference import _TrainEngine
+    for atomic in (False, True):
+        o = copy.deepcopy(onet)
+        net = fb.NSFFlow(D, C, hidden_features=24, num_transforms=3, num_bins=6, num_blocks=2)
+        net.load_state_dict(o.state_dict())
+        net = net.cuda().train()
+        eng = _TrainEngine(net, prior, B, atomic, 5, True, 5e-4, 5.0)
+        opt = torch.optim.Adam(o.parameters(), lr=5e-4)
+        o.train()
+        masks = torch.ones(B, 1)
+        for s in range(3):
+            tb, xb = theta[s * B:(s + 1) * B], x[s * B:(s + 1) * B]
+            eng.step_on_batch(tb.cuda(), net._standardize(xb.cuda()), masks.cuda())
+            opt.zero_grad()
+            if atomic:
+                ch = eng.choices.cpu().long()
+                lp = O.log_prob_proposal_posterior_atomic(o, prior_o, tb, xb, masks, 5, True, ch)
+            else:
+                lp = o.log_prob(tb, xb)
+            (-lp.mean()).backward()
+            torch.nn.utils.clip_grad_norm_(o.parameters(), 5.0)
+            opt.step()
+        eng.check_status()
+        got = net.state_dict()
+        for k, v in o.state_dict().items():
+            if v.is_floating_point():
+                assert (got[k].cpu() - v).abs().max() < 2e-5, (atomic, k, (got[k].cpu() - v).abs().max())
+
+
+def test_snpe_c_end_to_end_multi_round():
+    """The reference's round loop (floppity.py:168-285) on the synthetic c1 task: MLE round, atomic round, posterior."""
+    torch.manual_seed(0)
+    theta, x, scaler, _ = synthetic.make_dataset("c1", 2048)
+    prior = fb.utils.BoxUniform(low=-3 * torch.ones(10), high=3 * torch.ones(10), device="cuda")
+    inference = fb.SNPE_C(prior=prior, density_estimator=fb.posterior_nn(model="nsf", num_transforms=5, hidden_features=50,
+                                                                         num_bins=8, num_blocks=2, dropout_probability=0.0), device="cuda")
+    inference.append_simulations(torch.tensor(theta), torch.tensor(x), proposal=None)
+    est = inference.train(show_train_summary=False, stop_after_epochs=2, max_num_epochs=6, num_atoms=10,
+                          force_first_round_loss=True, use_combined_loss=True, training_batch_size=256)
+    v = inference._summary["validation_log_probs"]
+    assert len(v) >= 2 and v[-1] > v[0] and np.isfinite(v).all()
+    xo, _ = synthetic.observation("c1", scaler)
+    posterior = inference.build_posterior(est).set_default_x(xo)
+    s = posterior.sample((5000,))
+    assert s.shape == (5000, 10) and s.is_cuda and prior.within(s).all()
+    lp = posterior.log_prob(s[:100], norm_posterior=False)
+    assert torch.isfinite(lp).all()
+    assert posterior.log_prob(torch.full((1, 10), 9.0)).item() == -float("inf")
+    # round 2 with the atomic loss actually exercised (force_first_round_loss=False)
+    th2 = posterior.sample((1024,)).cpu()
+    x2 = synthetic.make_dataset("c1", theta=th2.numpy(), scaler=scaler)[1]
+    inference.append_simulations(th2, torch.tensor(x2), proposal=posterior)
+    est2 = inference.train(stop_after_epochs=1, max_num_epochs=2, num_atoms=10, force_first_round_loss=False,
+                           use_combined_loss=True, training_batch_size=256)
+    assert np.isfinite(inference._summary["validation_log_probs"]).all()
+    # checkpoint objects survive torch.save / pickle (floppity.py:244-248)
+    post2 = pickle.loads(pickle.dumps(inference.build_posterior(est2).set_default_x(xo)))
+    assert post2.sample((10,)).shape == (10, 10)
+    assert pickle.loads(pickle.dumps(inference))._data_round_index == [0, 1]
+
+
+def test_density_estimator_adapter_shapes():
+    torch.manual_seed(0)
+    net = fb.build_nsf(torch.randn(128, 4), torch.randn(128, 9), hidden_features=16, num_transforms=2, num_bins=4).cuda().eval()
+    de = fb.NSFDensityEstimator(net)
+    inp, cond = torch.randn(5, 3, 4).cuda(), torch.randn(3, 9).cuda()
+    lp = de.log_prob(inp, cond)
+    assert lp.shape == (5, 3)
+    want = torch.stack([net.log_prob(inp[s], cond) for s in range(5)])
+    assert (lp - want).abs().max() < 1e-4
+    assert de.sample((7,), cond).shape == (7, 3, 4) and de.loss(inp[0], cond).shape == (3,)
+
+
+def test_map_moves_uphill():
+    torch.manual_seed(0)
+    theta, x, scaler, _ = synthetic.make_dataset("c1", 1024)
+    net = fb.build_nsf(torch.tensor(theta), torch.tensor(x), hidden_features=32, num_transforms=3, num_bins=6).cuda().eval()
+    prior = fb.BoxUniform(-3 * torch.ones(10), 3 * torch.ones(10), device="cuda")
+    post = fb.DirectPosterior(net, prior).set_default_x(x[:1])
+    init = post.sample((200,))
+    m = post.map(num_iter=20, num_to_optimize=20, num_init_samples=200)
+    assert post.log_prob(m[None], norm_posterior=False).item() >= post.log_prob(init, norm_posterior=False).max().item() - 1e-3

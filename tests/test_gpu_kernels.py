@@ -1,0 +1,268 @@
+"""GPU parity, part 1: individual C-ABI kernels (spline forward / inverse / backward, GEMM epilogues, loss,
+optimiser) against the CPU oracle on identical seeded inputs.  Bar: 1e-4 relative (fp32), bin indices exact
+except elements whose input lies within a few ulp of a knot (enumerated with the fp64 oracle)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from floppity_deprecated_b200 import _lib
+from oracle import nsf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _cfg(D, C=8, T=2, K=8, H=50, Bk=1):
+    return _lib.NsfConfig(D=D, C=C, T=T, K=K, H=H, Bk=Bk, tail_bound=3.0, min_bin_width=1e-3, min_bin_height=1e-3,
+                          min_derivative=1e-3, lu_eps=1e-3, dropout_p=0.0)
+
+
+def _oracle_coupling(theta, params, D, K, H, parity, inverse, dtype=torch.float32):
+    tr = torch.arange(parity, D, 2)
+    s = np.sqrt(H)
+    p = params.to(dtype)
+    x = theta[:, tr].to(dtype)
+    y, lad, bins, kd = O.unconstrained_rational_quadratic_spline(
+        x, p[..., :K] / s, p[..., K:2 * K] / s, p[..., 2 * K:], inverse=inverse, tail_bound=3.0, return_bins=True)
+    out = theta.clone().to(dtype)
+    out[:, tr] = y
+    return out, lad.sum(-1), bins, kd
+
+
+@pytest.mark.parametrize("D,K,H,parity,R", [(10, 8, 50, 0, 4096), (10, 8, 50, 1, 1000), (20, 10, 128, 0, 2049),
+                                             (30, 16, 512, 1, 777), (7, 5, 20, 0, 333), (7, 5, 20, 1, 1), (4, 2, 8, 0, 5)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_rqs_forward_inverse_vs_oracle(D, K, H, parity, R, inverse):
+    g = torch.Generator().manual_seed(D * 1000 + K + R)
+    d_tr = len(range(parity, D, 2))
+    P = 3 * K - 1
+    theta = torch.rand(R, D, generator=g) * 6.6 - 3.3
+    theta[0, parity] = 3.0
+    if R > 1:
+        theta[1, parity] = -3.0
+    params = torch.randn(R, d_tr, P, generator=g)
+    want, want_ld, want_bins, kd = _oracle_coupling(theta, params, D, K, H, parity, inverse)
+    want64, want_ld64, bins64, _ = _oracle_coupling(theta, params, D, K, H, parity, inverse, torch.float64)
+    cfg = _cfg(D, K=K, H=H)
+    th_d, p_d = theta.cuda(), params.cuda().contiguous()
+    out = torch.empty_like(th_d)
+    ld = torch.full((R,), 0.25, device="cuda")            # accumulated into
+    bins = torch.empty(R, d_tr, dtype=torch.int32, device="cuda")
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
+    fn = _lib.lib().fp_rqs_inverse if inverse else _lib.lib().fp_rqs_forward
+    _lib.check(fn(cfg, parity, _lib.ptr(th_d), _lib.ptr(p_d), _lib.ptr(out), _lib.ptr(ld), _lib.ptr(bins), R,
+                  _lib.ptr(status), _lib.stream()), "rqs")
+    torch.cuda.synchronize()
+    assert status.tolist()[:2] == [0, 0]
+    flips = (bins.cpu().long() != want_bins)
+    if flips.any():   # only inputs within ~4 ulp of a knot may flip; report them
+        assert kd[flips].max() < 2e-6, f"{int(flips.sum())} bin flips, max knot distance {kd[flips].max()}"
+        assert flips.sum() <= max(1, R * d_tr // 100000)
+    ok = ~flips.any(dim=1)
+    # fp32 CUDA vs fp32 oracle, with the fp64 oracle as the arbiter of how much fp32 itself can differ
+    floor = np.maximum(rel_err(want.numpy(), want64.numpy()), 0).max()
+    assert rel_err(out.cpu().numpy()[ok], want.numpy()[ok]).max() < max(TOL, 4 * floor)
+    floor_ld = rel_err(want_ld.numpy(), want_ld64.numpy()).max()
+    assert rel_err(ld.cpu().numpy()[ok] - 0.25, want_ld.numpy()[ok]).max() < max(TOL, 4 * floor_ld)
+    # identity features are copied bit-exactly
+    idf = torch.arange(1 - parity, D, 2)
+    assert torch.equal(out.cpu()[:, idf], theta[:, idf])
+
+
+def test_rqs_empty_and_roundtrip_large():
+    cfg = _cfg(20, K=10, H=128)
+    lib = _lib.lib()
+    z = torch.empty(0, 20, device="cuda")
+    assert lib.fp_rqs_forward(cfg, 0, _lib.ptr(z), _lib.ptr(z), _lib.ptr(z), None, None, 0, None, _lib.stream()) == 0
+    # size-independent property at a BASELINE-scale batch: inverse(forward(x)) == x, logdets cancel
+    R = 1 << 18
+    g = torch.Generator(device="cuda").manual_seed(0)
+    theta = torch.rand(R, 20, device="cuda", generator=g) * 6.4 - 3.2
+    params = torch.randn(R, 10, 29, device="cuda", generator=g) * 0.7
+    y, back = torch.empty_like(theta), torch.empty_like(theta)
+    ld = torch.zeros(R, device="cuda")
+    _lib.check(lib.fp_rqs_forward(cfg, 0, _lib.ptr(theta), _lib.ptr(params), _lib.ptr(y), _lib.ptr(ld), None, R, None, _lib.stream()), "f")
+    _lib.check(lib.fp_rqs_inverse(cfg, 0, _lib.ptr(y), _lib.ptr(params), _lib.ptr(back), _lib.ptr(ld), None, R, None, _lib.stream()), "i")
+    torch.cuda.synchronize()
+    assert (back - theta).abs().max().item() < 2e-4
+    assert ld.abs().max().item() < 5e-3
+    assert (y[:, 1::2] == theta[:, 1::2]).all()
+
+
+@pytest.mark.parametrize("D,K,H,parity,R", [(10, 8, 50, 0, 3000), (20, 10, 128, 1, 1025), (30, 16, 512, 0, 515), (7, 5, 20, 1, 99)])
+def test_rqs_backward_vs_oracle_autograd(D, K, H, parity, R):
+    g = torch.Generator().manual_seed(7 * D + K)
+    tr = torch.arange(parity, D, 2)
+    d_tr, P = len(tr), 3 * K - 1
+    theta = (torch.rand(R, D, generator=g) * 6.6 - 3.3)
+    params = torch.randn(R, d_tr, P, generator=g)
+    gy, gl = torch.randn(R, D, generator=g), torch.randn(R, generator=g)
+    th_r, p_r = theta.clone().requires_grad_(), params.clone().requires_grad_()
+    s = np.sqrt(H)
+    y, lad = O.unconstrained_rational_quadratic_spline(th_r[:, tr], p_r[..., :K] / s, p_r[..., K:2 * K] / s, p_r[..., 2 * K:], tail_bound=3.0)
+    idf = torch.arange(1 - parity, D, 2)
+    ((y * gy[:, tr]).sum() + (th_r[:, idf] * gy[:, idf]).sum() + (lad.sum(-1) * gl).sum()).backward()
+    cfg = _cfg(D, K=K, H=H)
+    dp = torch.empty(R, d_tr, P, device="cuda")
+    dth = torch.empty(R, D, device="cuda")
+    _lib.check(_lib.lib().fp_rqs_backward(cfg, parity, _lib.ptr(theta.cuda()), _lib.ptr(params.cuda()), _lib.ptr(gy.cuda()),
+                                         _lib.ptr(gl.cuda()), _lib.ptr(dp), _lib.ptr(dth), R, _lib.stream()), "bwd")
+    torch.cuda.synchronize()
+    ref_p, ref_t = p_r.grad.numpy(), th_r.grad.numpy()
+    # gradients of ill-conditioned elements are large; compare against the per-tensor scale
+    assert np.abs(dp.cpu().numpy() - ref_p).max() / np.abs(ref_p).max() < 5e-4
+    assert np.abs(dth.cpu().numpy() - ref_t).max() / np.abs(ref_t).max() < 5e-4
+    med = np.median(np.abs(dp.cpu().numpy() - ref_p) / (np.abs(ref_p) + 1e-6))
+    assert med < 1e-5
+
+
+def _gemm(A, B, a_k, b_k, M, N, K, flags=0, split=1, **aux):
+    args = _lib.GemmArgs()
+    keep = []
+
+    def dev(t):
+        t = t.cuda().contiguous()
+        keep.append(t)
+        return t
+    Ad, Bd = dev(A), dev(B)
+    C = aux.pop("C", None)
+    Cd = dev(C) if C is not None else torch.zeros(M, N, device="cuda")
+    args.A, args.lda, args.a_kmajor = Ad.data_ptr(), Ad.shape[1], int(a_k)
+    args.B, args.ldb, args.b_kmajor = Bd.data_ptr(), Bd.shape[1], int(b_k)
+    args.C, args.ldc, args.M, args.N, args.K, args.flags, args.split_k = Cd.data_ptr(), N, M, N, K, flags, split
+    out = {}
+    for name, ld in (("bias", None), ("G", "ldg"), ("Rsd", "ldr"), ("U", "ldu"), ("Msk", "ldm")):
+        if name in aux:
+            t = dev(aux[name])
+            setattr(args, name, t.data_ptr())
+            if ld:
+                setattr(args, ld, t.shape[1])
+            out[name] = t
+    args.ctx_div = aux.get("ctx_div", 1)
+    _lib.check(_lib.lib().fp_gemm(ctypes.byref(args), _lib.stream()), "gemm")
+    torch.cuda.synchronize()
+    return Cd.cpu(), {k: v.cpu() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 50, 50), (257, 115, 50), (1000, 128, 128), (64, 290, 128), (5, 3, 7), (1, 384, 100), (130, 64, 17)])
+def test_gemm_layouts_vs_matmul(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    want = A.double() @ B.double().t()
+    scale = want.abs().max().item()
+    for a_k, b_k in [(1, 1), (1, 0), (0, 1), (0, 0)]:
+        Ain = A if a_k else A.t().contiguous()
+        Bin = B if b_k else B.t().contiguous()
+        got, _ = _gemm(Ain, Bin, a_k, b_k, M, N, K)
+        assert (got.double() - want).abs().max().item() < 2e-5 * scale + 1e-5, (a_k, b_k)
+    # split-K with atomics accumulates into C
+    C0 = torch.randn(M, N, generator=g)
+    got, _ = _gemm(A, B, 1, 1, M, N, K, flags=_lib.G_ATOMIC, split=3, C=C0.clone())
+    assert (got.double() - (want + C0.double())).abs().max().item() < 2e-5 * scale + 1e-5
+
+
+def test_gemm_fused_epilogues():
+    g = torch.Generator().manual_seed(5)
+    M, N, K, A_atoms = 96, 50, 50, 4
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.2
+    bias, G = torch.randn(N, generator=g), torch.randn(M // A_atoms, 3 * N, generator=g)
+    Rsd, Msk = torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)
+    lin = torch.relu(A) @ B.t() + bias
+    rows = torch.arange(M) // A_atoms
+    # relu prologue + bias + GLU gate (context row shared by A_atoms consecutive rows) + residual
+    got, aux = _gemm(A, B, 1, 1, M, N, K, flags=_lib.G_RELU_A | _lib.G_BIAS | _lib.G_GLU_RES, bias=bias, G=G[:, N:].contiguous()
+                     if False else G, Rsd=Rsd, U=torch.zeros(M, N), ctx_div=A_atoms)
+    want = Rsd + lin * torch.sigmoid(G[rows][:, :N])
+    assert (got - want).abs().max() < 1e-4 and (aux["U"] - lin).abs().max() < 1e-4
+    # context add
+    got, _ = _gemm(A, B, 1, 1, M, N, K, flags=_lib.G_ADD_CTX, G=G, ctx_div=A_atoms)
+    assert (got - (A @ B.t() + G[rows][:, :N])).abs().max() < 1e-4
+    # relu mask + accumulate (backward through relu)
+    C0 = torch.randn(M, N, generator=g)
+    got, _ = _gemm(A, B, 1, 1, M, N, K, flags=_lib.G_RELUMASK | _lib.G_ACCUM, Msk=Msk, C=C0.clone())
+    assert (got - (C0 + (A @ B.t()) * (Msk > 0))).abs().max() < 1e-4
+    # relu on the B operand (wgrad of a relu'd activation)
+    got, _ = _gemm(A.t().contiguous(), B.t().contiguous(), 0, 0, M, N, K, flags=_lib.G_RELU_B)
+    assert (got - A @ torch.relu(B).t()).abs().max() < 1e-4
+
+
+def test_atomic_loss_and_choices():
+    lib = _lib.lib()
+    B, A, D = 257, 10, 6
+    choices = torch.empty(B, A - 1, dtype=torch.int32, device="cuda")
+    _lib.check(lib.fp_atom_choices(_lib.ptr(choices), B, A, 1234, _lib.stream()), "choices")
+    ch = choices.cpu().long()
+    assert ((ch >= 0) & (ch < B)).all() and (ch != torch.arange(B)[:, None]).all()
+    assert all(len(set(r.tolist())) == A - 1 for r in ch)                       # without replacement
+    counts = torch.bincount(ch.reshape(-1), minlength=B).float()
+    assert counts.std() / counts.mean() < 0.6                                   # roughly uniform
+    g = torch.Generator().manual_seed(0)
+    theta = torch.rand(B, D, generator=g) * 4 - 2
+    rows = torch.empty(B * A, D, device="cuda")
+    _lib.check(lib.fp_atom_gather(_lib.ptr(theta.cuda()), _lib.ptr(choices), _lib.ptr(rows), B, A, D, _lib.stream()), "gather")
+    want_rows = torch.cat([theta[:, None], theta[ch]], dim=1).reshape(B * A, D)
+    assert torch.equal(rows.cpu(), want_rows)
+    logp = (torch.randn(B, A, generator=g) * 3).requires_grad_()
+    masks = (torch.rand(B, generator=g) > 0.5).float()
+    low, high = -3 * torch.ones(D), 3 * torch.ones(D)
+    prior = O.BoxUniform(low, high)
+    u = logp - prior.log_prob(want_rows).reshape(B, A)
+    want = masks * logp[:, 0] + u[:, 0] - torch.logsumexp(u, -1)
+    (-want.mean()).backward()
+    out, dlp = torch.empty(B, device="cuda"), torch.empty(B, A, device="cuda")
+    status = torch.zeros(4, dtype=torch.int32, device="cuda")
+    _lib.check(lib.fp_atomic_loss(_lib.ptr(logp.detach().cuda()), _lib.ptr(rows), _lib.ptr(low.cuda()), _lib.ptr(high.cuda()),
+                                  _lib.ptr(masks.cuda()), 1, _lib.ptr(out), _lib.ptr(dlp), B, A, D, _lib.ptr(status), _lib.stream()), "loss")
+    torch.cuda.synchronize()
+    assert status[0].item() == 0
+    assert rel_err(out.cpu().numpy(), want.detach().numpy()).max() < 1e-5
+    assert (dlp.cpu() - logp.grad).abs().max() < 1e-6
+
+
+def test_clip_and_adam_match_torch():
+    torch.manual_seed(0)
+    n = 10007
+    p0, grads = torch.randn(n), [torch.randn(n) * s for s in (0.01, 3.0, 0.5)]
+    ref = p0.clone().requires_grad_()
+    opt = torch.optim.Adam([ref], lr=5e-4)
+    p = p0.clone().cuda()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sumsq = torch.zeros(1, device="cuda")
+    lib = _lib.lib()
+    for gr in grads:
+        ref.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 5.0)
+        opt.step()
+        gd = gr.cuda()
+        sumsq.zero_()
+        step += 1
+        _lib.check(lib.fp_grad_sumsq(_lib.ptr(gd), n, _lib.ptr(sumsq), _lib.stream()), "sumsq")
+        _lib.check(lib.fp_adam_step(_lib.ptr(p), _lib.ptr(gd), _lib.ptr(m), _lib.ptr(v), n, 5e-4, 0.9, 0.999, 1e-8, _lib.ptr(step),
+                                    5.0, 1.0, _lib.ptr(sumsq), _lib.stream()), "adam")
+    torch.cuda.synchronize()
+    assert (p.cpu() - ref.detach()).abs().max() < 1e-6
+
+
+def test_small_utilities():
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(2)
+    src = torch.randn(100, 37, generator=g)
+    idx = torch.randint(0, 100, (64,), generator=g)
+    dst = torch.empty(64, 37, device="cuda")
+    _lib.check(lib.fp_gather_rows(_lib.ptr(src.cuda()), _lib.ptr(idx.cuda()), _lib.ptr(dst), 64, 37, _lib.stream()), "g")
+    assert torch.equal(dst.cpu(), src[idx])
+    mean, std = torch.randn(37, generator=g), torch.rand(37, generator=g) + 0.5
+    out = torch.empty(100, 37, device="cuda")
+    _lib.check(lib.fp_standardize(_lib.ptr(src.cuda()), _lib.ptr(mean.cuda()), _lib.ptr(std.cuda()), _lib.ptr(out), 100, 37, _lib.stream()), "s")
+    assert torch.equal(out.cpu(), (src - mean) / std)
+    acc = torch.zeros(1, device="cuda")
+    _lib.check(lib.fp_sum(_lib.ptr(src.cuda()), src.numel(), -2.0, _lib.ptr(acc), _lib.stream()), "sum")
+    assert abs(acc.item() + 2 * src.double().sum().item()) < 1e-2
+    low, high = -torch.ones(37), torch.ones(37)
+    inside = torch.empty(100, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.fp_within_box(_lib.ptr(src.cuda()), _lib.ptr(low.cuda()), _lib.ptr(high.cuda()), _lib.ptr(inside), 100, 37, _lib.stream()), "w")
+    assert torch.equal(inside.cpu().bool(), ((src >= low) & (src <= high)).all(-1))
