@@ -61,7 +61,7 @@ def test_rqs_forward_inverse_vs_oracle(D, K, H, parity, R, inverse):
     if flips.any():   # only inputs within ~4 ulp of a knot may flip; report them
         assert kd[flips].max() < 2e-6, f"{int(flips.sum())} bin flips, max knot distance {kd[flips].max()}"
         assert flips.sum() <= max(1, R * d_tr // 100000)
-    ok = ~flips.any(dim=1)
+    ok = (~flips.any(dim=1)).numpy()
     # fp32 CUDA vs fp32 oracle, with the fp64 oracle as the arbiter of how much fp32 itself can differ
     floor = np.maximum(rel_err(want.numpy(), want64.numpy()), 0).max()
     assert rel_err(out.cpu().numpy()[ok], want.numpy()[ok]).max() < max(TOL, 4 * floor)
@@ -108,8 +108,9 @@ def test_rqs_backward_vs_oracle_autograd(D, K, H, parity, R):
     cfg = _cfg(D, K=K, H=H)
     dp = torch.empty(R, d_tr, P, device="cuda")
     dth = torch.empty(R, D, device="cuda")
-    _lib.check(_lib.lib().fp_rqs_backward(cfg, parity, _lib.ptr(theta.cuda()), _lib.ptr(params.cuda()), _lib.ptr(gy.cuda()),
-                                         _lib.ptr(gl.cuda()), _lib.ptr(dp), _lib.ptr(dth), R, _lib.stream()), "bwd")
+    th_d, p_d, gy_d, gl_d = theta.cuda(), params.cuda(), gy.cuda(), gl.cuda()     # keep alive across the async launch
+    _lib.check(_lib.lib().fp_rqs_backward(cfg, parity, _lib.ptr(th_d), _lib.ptr(p_d), _lib.ptr(gy_d),
+                                         _lib.ptr(gl_d), _lib.ptr(dp), _lib.ptr(dth), R, _lib.stream()), "bwd")
     torch.cuda.synchronize()
     ref_p, ref_t = p_r.grad.numpy(), th_r.grad.numpy()
     # gradients of ill-conditioned elements are large; compare against the per-tensor scale
@@ -202,7 +203,8 @@ def test_atomic_loss_and_choices():
     g = torch.Generator().manual_seed(0)
     theta = torch.rand(B, D, generator=g) * 4 - 2
     rows = torch.empty(B * A, D, device="cuda")
-    _lib.check(lib.fp_atom_gather(_lib.ptr(theta.cuda()), _lib.ptr(choices), _lib.ptr(rows), B, A, D, _lib.stream()), "gather")
+    theta_d = theta.cuda()
+    _lib.check(lib.fp_atom_gather(_lib.ptr(theta_d), _lib.ptr(choices), _lib.ptr(rows), B, A, D, _lib.stream()), "gather")
     want_rows = torch.cat([theta[:, None], theta[ch]], dim=1).reshape(B * A, D)
     assert torch.equal(rows.cpu(), want_rows)
     logp = (torch.randn(B, A, generator=g) * 3).requires_grad_()
@@ -214,8 +216,9 @@ def test_atomic_loss_and_choices():
     (-want.mean()).backward()
     out, dlp = torch.empty(B, device="cuda"), torch.empty(B, A, device="cuda")
     status = torch.zeros(4, dtype=torch.int32, device="cuda")
-    _lib.check(lib.fp_atomic_loss(_lib.ptr(logp.detach().cuda()), _lib.ptr(rows), _lib.ptr(low.cuda()), _lib.ptr(high.cuda()),
-                                  _lib.ptr(masks.cuda()), 1, _lib.ptr(out), _lib.ptr(dlp), B, A, D, _lib.ptr(status), _lib.stream()), "loss")
+    logp_d, low_d, high_d, masks_d = logp.detach().cuda(), low.cuda(), high.cuda(), masks.cuda()
+    _lib.check(lib.fp_atomic_loss(_lib.ptr(logp_d), _lib.ptr(rows), _lib.ptr(low_d), _lib.ptr(high_d),
+                                  _lib.ptr(masks_d), 1, _lib.ptr(out), _lib.ptr(dlp), B, A, D, _lib.ptr(status), _lib.stream()), "loss")
     torch.cuda.synchronize()
     assert status[0].item() == 0
     assert rel_err(out.cpu().numpy(), want.detach().numpy()).max() < 1e-5
@@ -238,6 +241,7 @@ def test_clip_and_adam_match_torch():
         torch.nn.utils.clip_grad_norm_([ref], 5.0)
         opt.step()
         gd = gr.cuda()
+        torch.cuda.synchronize()
         sumsq.zero_()
         step += 1
         _lib.check(lib.fp_grad_sumsq(_lib.ptr(gd), n, _lib.ptr(sumsq), _lib.stream()), "sumsq")
@@ -252,17 +256,20 @@ def test_small_utilities():
     g = torch.Generator().manual_seed(2)
     src = torch.randn(100, 37, generator=g)
     idx = torch.randint(0, 100, (64,), generator=g)
+    src_d, idx_d = src.cuda(), idx.cuda()
     dst = torch.empty(64, 37, device="cuda")
-    _lib.check(lib.fp_gather_rows(_lib.ptr(src.cuda()), _lib.ptr(idx.cuda()), _lib.ptr(dst), 64, 37, _lib.stream()), "g")
+    _lib.check(lib.fp_gather_rows(_lib.ptr(src_d), _lib.ptr(idx_d), _lib.ptr(dst), 64, 37, _lib.stream()), "g")
     assert torch.equal(dst.cpu(), src[idx])
     mean, std = torch.randn(37, generator=g), torch.rand(37, generator=g) + 0.5
+    mean_d, std_d = mean.cuda(), std.cuda()
     out = torch.empty(100, 37, device="cuda")
-    _lib.check(lib.fp_standardize(_lib.ptr(src.cuda()), _lib.ptr(mean.cuda()), _lib.ptr(std.cuda()), _lib.ptr(out), 100, 37, _lib.stream()), "s")
+    _lib.check(lib.fp_standardize(_lib.ptr(src_d), _lib.ptr(mean_d), _lib.ptr(std_d), _lib.ptr(out), 100, 37, _lib.stream()), "s")
     assert torch.equal(out.cpu(), (src - mean) / std)
     acc = torch.zeros(1, device="cuda")
-    _lib.check(lib.fp_sum(_lib.ptr(src.cuda()), src.numel(), -2.0, _lib.ptr(acc), _lib.stream()), "sum")
+    _lib.check(lib.fp_sum(_lib.ptr(src_d), src.numel(), -2.0, _lib.ptr(acc), _lib.stream()), "sum")
     assert abs(acc.item() + 2 * src.double().sum().item()) < 1e-2
     low, high = -torch.ones(37), torch.ones(37)
+    low_d, high_d = low.cuda(), high.cuda()
     inside = torch.empty(100, dtype=torch.uint8, device="cuda")
-    _lib.check(lib.fp_within_box(_lib.ptr(src.cuda()), _lib.ptr(low.cuda()), _lib.ptr(high.cuda()), _lib.ptr(inside), 100, 37, _lib.stream()), "w")
+    _lib.check(lib.fp_within_box(_lib.ptr(src_d), _lib.ptr(low_d), _lib.ptr(high_d), _lib.ptr(inside), 100, 37, _lib.stream()), "w")
     assert torch.equal(inside.cpu().bool(), ((src >= low) & (src <= high)).all(-1))
