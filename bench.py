@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=16384, help="resident dataset rows per GPU")
     ap.add_argument("--ref-batch", type=int, default=256, help="bounded per-step sample for the CPU arm")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     return ap.parse_args()
 
 
@@ -309,7 +310,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N == 1 only): the oracle on the host cores, bounded sample
     cpu_base = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import nsf_oracle as O
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)

@@ -120,6 +120,7 @@ def test_training_steps_track_the_oracle():
     for atomic in (False, True):
         o = copy.deepcopy(onet)
         net = fb.NSFFlow(D, C, hidden_features=24, num_transforms=3, num_bins=6, num_blocks=2).cuda().train()
+        net.load_state_dict(o.state_dict())                         # z-score buffers must be in place before the engine caches them
         eng = _TrainEngine(net, prior, B, atomic, 5, True, 5e-4, 5.0)
         opt = torch.optim.Adam(o.parameters(), lr=5e-4)
         o.train()
