@@ -83,7 +83,7 @@ __device__ __forceinline__ void load_tile(const RqsArgs& a, float* dst, uint64_t
   }
 }
 
-template <bool INVERSE>
+template <bool INVERSE, int KT>
 __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int row_floats = a.d_tr * a.c.P;
@@ -119,14 +119,20 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
     __syncthreads();
 
     // phase 1: one (sample, transformed feature) per thread
-    const float* P = s.stage[st];
+    float* P = s.stage[st];
     for (int e = threadIdx.x; e < rows_here * d_tr; e += blockDim.x) {
       int row = e / d_tr, j = e - row * d_tr;
       int f = 2 * j + a.parity;
       float x = s.rowbuf[row * D + f];
       float y, lad; int bin; bool nd = false;
-      if (INVERSE) rqs_inverse_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin, nd);
-      else rqs_forward_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin);
+      if (KT > 0) {
+        constexpr int KK = KT > 0 ? KT : 2;
+        if (INVERSE) rqs_inverse_elem_t<KK>(P + (size_t)e * (3 * KK - 1), a.c, x, y, lad, bin, nd);
+        else rqs_forward_elem_t<KK>(P + (size_t)e * (3 * KK - 1), a.c, x, y, lad, bin);
+      } else {
+        if (INVERSE) rqs_inverse_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin, nd);
+        else rqs_forward_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin);
+      }
       s.rowbuf[row * D + f] = y;
       s.ladbuf[e] = lad;
       if (a.bin_idx) a.bin_idx[(r0 + row) * d_tr + j] = bin;
@@ -187,6 +193,7 @@ struct RqsBwdArgs {
   RqsConsts c;
 };
 
+template <int KT>
 __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int row_floats = a.d_tr * a.c.P;
@@ -232,7 +239,13 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
       float gl = a.d_logdet[gr];
       float* p = P + (size_t)e * a.c.P;
       // in place: every parameter is read before its gradient overwrites it
-      float gx = rqs_backward_elem(p, a.c, x, gy, gl, p, 1);
+      float gx;
+      if (KT > 0) {
+        constexpr int KK = KT > 0 ? KT : 2;
+        gx = rqs_backward_elem_t<KK>(P + (size_t)e * (3 * KK - 1), a.c, x, gy, gl);
+      } else {
+        gx = rqs_backward_elem(p, a.c, x, gy, gl);
+      }
       a.d_theta_in[gr * D + f] = gx;
     }
     // identity features: gradient passes straight through the coupling
@@ -272,25 +285,24 @@ RqsConsts make_rqs_consts(const fp_nsf_config* cfg) {
   c.mixw = (float)(1.0 - (double)cfg->min_bin_width * cfg->K);
   c.mixh = (float)(1.0 - (double)cfg->min_bin_height * cfg->K);
   c.sqrtH = (float)sqrt((double)cfg->H);
+  c.inv_sqrtH = 1.0f / c.sqrtH;
   c.dconst = (float)log(exp(1.0 - (double)cfg->min_derivative) - 1.0);
   return c;
 }
 
-// rows per tile: multiple of 4 (keeps every full tile 16-byte granular), sized to ~40 KB per stage
+// rows per tile: multiple of 4 (keeps every full tile 16-byte granular for the bulk copy), sized to ~20 KB per
+// stage so that 4-5 CTAs stay resident per SM (the kernels are issue-bound: occupancy hides the MUFU/LDS latency)
 static int pick_rows(int row_floats, int d_tr) {
-  int rows = (40 * 1024) / (row_floats * 4);
+  int rows = (20 * 1024) / (row_floats * 4);
   rows = rows / 4 * 4;
   if (rows < 4) rows = 4;
   if (rows > 128) rows = 128;
-  // do not use more element slots than a 512-thread block covers in two passes
-  while (rows > 4 && rows * d_tr > 1024) rows -= 4;
+  while (rows > 4 && rows * d_tr > 512) rows -= 4;   // one element per thread, at most 512 threads
   return rows;
 }
 
 static int pick_threads(int rows, int d_tr) {
-  int e = rows * d_tr;
-  int t = (e + 31) / 32 * 32;
-  if (t > 512) t = ((e + 1) / 2 + 31) / 32 * 32;
+  int t = (rows * d_tr + 31) / 32 * 32;
   if (t > 512) t = 512;
   if (t < 64) t = 64;
   return t;
@@ -313,7 +325,15 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
   a.rows = pick_rows(row_floats, a.d_tr);
   int threads = pick_threads(a.rows, a.d_tr);
   size_t smem = rqs_smem_bytes(a.rows * row_floats, a.rows, a.D, a.d_tr, luM != nullptr);
-  auto kern = inverse ? k_rqs_apply<true> : k_rqs_apply<false>;
+  void (*kern)(RqsArgs);
+#define FP_RQS_PICK(KV) (inverse ? k_rqs_apply<true, KV> : k_rqs_apply<false, KV>)
+  switch (cfg->K) {
+    case 8: kern = FP_RQS_PICK(8); break;
+    case 10: kern = FP_RQS_PICK(10); break;
+    case 16: kern = FP_RQS_PICK(16); break;
+    default: kern = FP_RQS_PICK(0); break;
+  }
+#undef FP_RQS_PICK
   FP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   FP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -342,14 +362,21 @@ int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta
   a.rows = pick_rows(row_floats, a.d_tr);
   int threads = pick_threads(a.rows, a.d_tr);
   size_t smem = (size_t)RQS_STAGES * a.rows * row_floats * 4 + 8 + RQS_STAGES * 8 + 16;
-  FP_CUDA_OK(cudaFuncSetAttribute(k_rqs_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void (*kern)(RqsBwdArgs);
+  switch (cfg->K) {
+    case 8: kern = k_rqs_backward<8>; break;
+    case 10: kern = k_rqs_backward<10>; break;
+    case 16: kern = k_rqs_backward<16>; break;
+    default: kern = k_rqs_backward<0>; break;
+  }
+  FP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
-  FP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rqs_backward, threads, smem));
+  FP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) occ = 1;
   int64_t ntiles = (R + a.rows - 1) / a.rows;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
   ProfScope ps(TAG_RQS_BWD, 4.0 * (double)R * (2.0 * row_floats + 3.0 * a.d_tr + 1.0), stream);
-  k_rqs_backward<<<grid, threads, smem, stream>>>(a);
+  kern<<<grid, threads, smem, stream>>>(a);
   FP_LAUNCH_CHECK();
   return 0;
 }

@@ -58,9 +58,9 @@ def test_rqs_forward_inverse_vs_oracle(D, K, H, parity, R, inverse):
     torch.cuda.synchronize()
     assert status.tolist()[:2] == [0, 0]
     flips = (bins.cpu().long() != want_bins)
-    if flips.any():   # only inputs within ~4 ulp of a knot may flip; report them
-        assert kd[flips].max() < 2e-6, f"{int(flips.sum())} bin flips, max knot distance {kd[flips].max()}"
-        assert flips.sum() <= max(1, R * d_tr // 100000)
+    if flips.any():   # only inputs within a few ulp of a knot may flip; report them
+        assert kd[flips].max() < 1e-5, f"{int(flips.sum())} bin flips, max knot distance {kd[flips].max()}"
+        assert flips.sum() <= max(2, R * d_tr // 50000)
     ok = (~flips.any(dim=1)).numpy()
     # fp32 CUDA vs fp32 oracle, with the fp64 oracle as the arbiter of how much fp32 itself can differ
     floor = np.maximum(rel_err(want.numpy(), want64.numpy()), 0).max()
@@ -70,6 +70,30 @@ def test_rqs_forward_inverse_vs_oracle(D, K, H, parity, R, inverse):
     # identity features are copied bit-exactly
     idf = torch.arange(1 - parity, D, 2)
     assert torch.equal(out.cpu()[:, idf], theta[:, idf])
+
+
+def test_bin_index_census_at_scale():
+    """Bin indices vs the fp32 oracle over 1.3 M elements (c2 shape): exact except inputs within ~1e-5 of a knot
+    (the kernels use 1/sqrt(H) and 1/sum reciprocals and ex2.approx for the softmax; see csrc/rqs_math.cuh)."""
+    D, K, H, R = 20, 10, 128, 1 << 17
+    g = torch.Generator().manual_seed(11)
+    theta = torch.rand(R, D, generator=g) * 6 - 3
+    params = torch.randn(R, D // 2, 3 * K - 1, generator=g)
+    cfg = _cfg(D, K=K, H=H)
+    th_d, p_d = theta.cuda(), params.cuda()
+    out, ld = torch.empty_like(th_d), torch.zeros(R, device="cuda")
+    for inverse in (False, True):
+        _, _, want_bins, kd = _oracle_coupling(theta, params, D, K, H, 0, inverse)
+        bins = torch.empty(R, D // 2, dtype=torch.int32, device="cuda")
+        fn = _lib.lib().fp_rqs_inverse if inverse else _lib.lib().fp_rqs_forward
+        _lib.check(fn(cfg, 0, _lib.ptr(th_d), _lib.ptr(p_d), _lib.ptr(out), _lib.ptr(ld), _lib.ptr(bins), R, None, _lib.stream()), "rqs")
+        flips = bins.cpu().long() != want_bins
+        n = int(flips.sum())
+        print(f"bin census inverse={inverse}: {n} flips / {flips.numel()} elements; max knot distance of a flip "
+              f"{float(kd[flips].max()) if n else 0.0:.2e}")
+        assert n <= flips.numel() * 2e-5
+        if n:
+            assert kd[flips].max() < 1e-5
 
 
 def test_rqs_empty_and_roundtrip_large():
