@@ -99,14 +99,14 @@ struct Workspace {
       th_a = take(R * L.D); th_b = take(R * L.D);
       h = take(R * L.H); t = take(R * L.H); prm = take(R * L.dPmax());
     } else {
-      th_st = take((int64_t)(L.T + 1) * R * L.D);
-      th_sp = take((int64_t)L.T * R * L.D);
+      th_st = take((int64_t)(L.T + 1) * al32(R * L.D));
+      th_sp = take((int64_t)L.T * al32(R * L.D));
       act = o;
       for (int i = 0; i < L.T && i < 64; ++i) {
         act_layer_off[i] = o;
-        take((int64_t)(L.Bk + 1) * R * L.H);  // h_0..h_Bk
-        take((int64_t)L.Bk * R * L.H);        // t_b (pre-relu output of linear 0)
-        take((int64_t)L.Bk * R * L.H);        // u_b (pre-gate output of linear 1)
+        take((int64_t)(L.Bk + 1) * al32(R * L.H));  // h_0..h_Bk
+        take((int64_t)L.Bk * al32(R * L.H));        // t_b (pre-relu output of linear 0)
+        take((int64_t)L.Bk * al32(R * L.H));        // u_b (pre-gate output of linear 1)
         take(R * L.dP(i));                    // spline params
         act_layer_sz[i] = o - act_layer_off[i];
       }
@@ -117,16 +117,14 @@ struct Workspace {
     }
     total = o;
   }
-  int64_t thst(int i) const { return th_st + (int64_t)i * R * L.D; }
-  int64_t thsp(int i) const { return th_sp + (int64_t)i * R * L.D; }
-  int64_t hbuf(int i, int b) const { return act_layer_off[i] + (int64_t)b * al32(0) + (int64_t)b * R * L.H; }
-  int64_t tbuf(int i, int b) const { return act_layer_off[i] + al32((int64_t)(L.Bk + 1) * R * L.H) + (int64_t)b * R * L.H; }
+  int64_t thst(int i) const { return th_st + (int64_t)i * al32(R * L.D); }
+  int64_t thsp(int i) const { return th_sp + (int64_t)i * al32(R * L.D); }
+  int64_t hbuf(int i, int b) const { return act_layer_off[i] + (int64_t)b * al32(R * L.H); }
+  int64_t tbuf(int i, int b) const { return act_layer_off[i] + (int64_t)(L.Bk + 1) * al32(R * L.H) + (int64_t)b * al32(R * L.H); }
   int64_t ubuf(int i, int b) const {
-    return act_layer_off[i] + al32((int64_t)(L.Bk + 1) * R * L.H) + al32((int64_t)L.Bk * R * L.H) + (int64_t)b * R * L.H;
+    return act_layer_off[i] + (int64_t)(2 * L.Bk + 1) * al32(R * L.H) + (int64_t)b * al32(R * L.H);
   }
-  int64_t prmbuf(int i) const {
-    return act_layer_off[i] + al32((int64_t)(L.Bk + 1) * R * L.H) + 2 * al32((int64_t)L.Bk * R * L.H);
-  }
+  int64_t prmbuf(int i) const { return act_layer_off[i] + (int64_t)(3 * L.Bk + 1) * al32(R * L.H); }
 };
 
 }  // namespace fp

@@ -40,19 +40,24 @@ struct RqsArgs {
   float pre_sign;       // luPre is multiplied by this (-1 for the inverse direction: x - b)
 };
 
+// One stage of the ring = everything a tile needs, fetched by the TMA engine on ONE mbarrier:
+//   [ params: rows*d_tr*P floats | theta rows: rows*D floats | logdet: rows floats ]
+// The transformed values overwrite the theta rows in place; nothing is read from global by the SM's load path.
 struct RqsSmem {
   float* stage[RQS_STAGES];
-  float* rowbuf;
   float* ladbuf;
   float* luM;
   uint64_t* bars;
+  int stage_floats, th_off, ld_off;
 };
 
 __device__ __forceinline__ RqsSmem carve(unsigned char* base, int tile_floats, int rows, int D, int d_tr, bool lu) {
   RqsSmem s;
+  s.th_off = tile_floats;                       // rows % 4 == 0 -> every region starts 16-byte aligned
+  s.ld_off = tile_floats + rows * D;
+  s.stage_floats = tile_floats + rows * D + rows;
   float* f = reinterpret_cast<float*>(base);
-  for (int i = 0; i < RQS_STAGES; ++i) { s.stage[i] = f; f += tile_floats; }
-  s.rowbuf = f; f += rows * D;
+  for (int i = 0; i < RQS_STAGES; ++i) { s.stage[i] = f; f += s.stage_floats; }
   s.ladbuf = f; f += rows * d_tr;
   s.luM = f; if (lu) f += D * D;
   uintptr_t p = (reinterpret_cast<uintptr_t>(f) + 7) & ~uintptr_t(7);
@@ -61,26 +66,40 @@ __device__ __forceinline__ RqsSmem carve(unsigned char* base, int tile_floats, i
 }
 
 static size_t rqs_smem_bytes(int tile_floats, int rows, int D, int d_tr, bool lu) {
-  size_t f = (size_t)RQS_STAGES * tile_floats + (size_t)rows * D + (size_t)rows * d_tr + (lu ? (size_t)D * D : 0);
+  size_t f = (size_t)RQS_STAGES * (tile_floats + rows * D + rows) + (size_t)rows * d_tr + (lu ? (size_t)D * D : 0);
   return f * 4 + 8 + RQS_STAGES * 8 + 16;
 }
 
-// Issue the load of one tile into a stage: bulk TMA when the byte count allows it, otherwise a
-// cooperative plain copy (only ever the final ragged tile).  Must be called by ALL threads.
-__device__ __forceinline__ void load_tile(const RqsArgs& a, float* dst, uint64_t* bar, int64_t tile, int row_floats) {
+// Issue the loads of one tile into a stage: bulk TMA when byte counts and addresses allow it, otherwise a
+// cooperative plain copy (the final ragged tile, or unaligned caller buffers).  Must be called by ALL threads.
+__device__ __forceinline__ void load_chunk(float* dst, const float* src, int n_floats, uint64_t* bar, bool bulk) {
+  if (bulk) {
+    if (threadIdx.x == 0) bulk_g2s(dst, src, (uint32_t)n_floats * 4u, bar);
+  } else {
+    for (int i = threadIdx.x; i < n_floats; i += blockDim.x) dst[i] = src[i];
+  }
+}
+__device__ __forceinline__ bool bulk_ok(const void* p, int n_floats) {
+  return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((n_floats & 3) == 0);
+}
+__device__ __forceinline__ void load_tile(const RqsArgs& a, const RqsSmem& s, int st, int64_t tile, int row_floats) {
   int64_t r0 = tile * a.rows;
   int rows_here = (int)min((int64_t)a.rows, a.R - r0);
-  uint32_t bytes = (uint32_t)rows_here * row_floats * 4u;
-  const float* src = a.params + r0 * row_floats;
-  if ((bytes & 15u) == 0) {
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, bytes);
-      bulk_g2s(dst, src, bytes, bar);
-    }
-  } else {
-    for (int i = threadIdx.x; i < rows_here * row_floats; i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x == 0) mbar_arrive(bar);  // keep the barrier phase in step with the bulk path
+  const float* ps = a.params + r0 * row_floats;
+  const float* ts = a.theta_in + r0 * a.D;
+  const float* ls = a.logdet ? a.logdet + r0 : nullptr;
+  const int np = rows_here * row_floats, nt = rows_here * a.D, nl = ls ? rows_here : 0;
+  const bool bp = bulk_ok(ps, np), bt = bulk_ok(ts, nt), bl = ls && bulk_ok(ls, nl);
+  uint32_t tx = (bp ? np : 0) + (bt ? nt : 0) + (bl ? nl : 0);
+  uint64_t* bar = &s.bars[st];
+  if (threadIdx.x == 0) {
+    if (tx) mbar_expect_tx(bar, tx * 4u);
+    else mbar_arrive(bar);                       // nothing asynchronous: complete the phase by hand
   }
+  float* base = s.stage[st];
+  load_chunk(base, ps, np, bar, bp);
+  load_chunk(base + s.th_off, ts, nt, bar, bt);
+  if (ls) load_chunk(base + s.ld_off, ls, nl, bar, bl);
 }
 
 template <bool INVERSE, int KT>
@@ -91,19 +110,20 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
   const bool lu = a.luM != nullptr;
   RqsSmem s = carve(smem_raw, tile_floats, a.rows, a.D, a.d_tr, lu);
   const int64_t ntiles = (a.R + a.rows - 1) / a.rows;
-  const int D = a.D, d_tr = a.d_tr, d_id = D - d_tr;
+  const int D = a.D, d_tr = a.d_tr;
+  const float inv_dtr = 1.f / (float)d_tr, inv_D = 1.f / (float)D;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RQS_STAGES; ++i) mbar_init(&s.bars[i], 1);
     mbar_fence_init();
   }
   if (lu) for (int i = threadIdx.x; i < D * D; i += blockDim.x) s.luM[i] = a.luM[i];
+  const float lu_ld = a.lu_logdet ? *a.lu_logdet : 0.f;
   __syncthreads();
 
-  // prologue: fill the ring
-  for (int st = 0; st < RQS_STAGES; ++st) {
+  for (int st = 0; st < RQS_STAGES; ++st) {          // prologue: fill the ring
     int64_t tile = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
-    if (tile < ntiles) load_tile(a, s.stage[st], &s.bars[st], tile, row_floats);
+    if (tile < ntiles) load_tile(a, s, st, tile, row_floats);
   }
 
   int it = 0;
@@ -112,18 +132,19 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
     const uint32_t parity = (uint32_t)(it / RQS_STAGES) & 1u;
     const int64_t r0 = tile * a.rows;
     const int rows_here = (int)min((int64_t)a.rows, a.R - r0);
-
-    // phase 0: theta rows of the tile -> smem (coalesced)
-    for (int i = threadIdx.x; i < rows_here * D; i += blockDim.x) s.rowbuf[i] = a.theta_in[r0 * D + i];
-    mbar_wait(&s.bars[st], parity);
-    __syncthreads();
-
-    // phase 1: one (sample, transformed feature) per thread
     float* P = s.stage[st];
+    float* rowbuf = P + s.th_off;
+    float* ldbuf = P + s.ld_off;
+
+    mbar_wait(&s.bars[st], parity);
+    __syncthreads();                                 // (also orders the cooperative-copy fallback)
+
+    // phase 1: one (sample, transformed feature) per thread; y overwrites x in the staged theta rows
     for (int e = threadIdx.x; e < rows_here * d_tr; e += blockDim.x) {
-      int row = e / d_tr, j = e - row * d_tr;
+      int row = (int)(((float)e + 0.5f) * inv_dtr);  // e / d_tr, exact for e < 2^22
+      int j = e - row * d_tr;
       int f = 2 * j + a.parity;
-      float x = s.rowbuf[row * D + f];
+      float x = rowbuf[row * D + f];
       float y, lad; int bin; bool nd = false;
       if (KT > 0) {
         constexpr int KK = KT > 0 ? KT : 2;
@@ -133,29 +154,24 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
         if (INVERSE) rqs_inverse_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin, nd);
         else rqs_forward_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin);
       }
-      s.rowbuf[row * D + f] = y;
+      rowbuf[row * D + f] = y;
       s.ladbuf[e] = lad;
       if (a.bin_idx) a.bin_idx[(r0 + row) * d_tr + j] = bin;
       if (a.status) {
         if (nd) atomicAdd(&a.status[1], 1);
-        if (!isfinite(y) || !isfinite(lad)) atomicAdd(&a.status[0], 1);
+        if (!(fabsf(y) <= 3.0e38f) || !(fabsf(lad) <= 3.0e38f)) atomicAdd(&a.status[0], 1);
       }
     }
     __syncthreads();
 
-    // stage `st` is consumed: refill it with the tile RQS_STAGES iterations ahead
-    {
-      int64_t nxt = tile + (int64_t)RQS_STAGES * gridDim.x;
-      if (nxt < ntiles) load_tile(a, s.stage[st], &s.bars[st], nxt, row_floats);
-    }
-
     // phase 2: write rows (optionally through the LU-linear) and the per-sample log-det
     for (int i = threadIdx.x; i < rows_here * D; i += blockDim.x) {
-      int row = i / D, f = i - row * D;
-      float v = s.rowbuf[i];
+      int row = (int)(((float)i + 0.5f) * inv_D);
+      int f = i - row * D;
+      float v = rowbuf[i];
       if (a.theta_sp) a.theta_sp[r0 * D + i] = v;
       if (lu) {
-        const float* xr = s.rowbuf + row * D;
+        const float* xr = rowbuf + row * D;
         const float* m = s.luM + f * D;
         float acc = 0.f;
         if (a.luPre) {
@@ -168,16 +184,17 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
       a.theta_out[r0 * D + i] = v;
     }
     if (a.logdet) {
-      const float lu_ld = a.lu_logdet ? *a.lu_logdet : 0.f;
       for (int row = threadIdx.x; row < rows_here; row += blockDim.x) {
         float sum = 0.f;
         for (int j = 0; j < d_tr; ++j) sum += s.ladbuf[row * d_tr + j];
-        a.logdet[r0 + row] += sum + lu_ld;
+        a.logdet[r0 + row] = ldbuf[row] + sum + lu_ld;
       }
     }
     __syncthreads();
+    // stage `st` is fully consumed: refill it with the tile RQS_STAGES iterations ahead
+    int64_t nxt = tile + (int64_t)RQS_STAGES * gridDim.x;
+    if (nxt < ntiles) load_tile(a, s, st, nxt, row_floats);
   }
-  (void)d_id;
 }
 
 // ---- backward ----------------------------------------------------------------------------------
@@ -213,11 +230,21 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
   }
   __syncthreads();
 
-  RqsArgs la{};  // reuse load_tile
-  la.params = a.params; la.rows = a.rows; la.R = a.R;
+  auto load_params = [&](int st, int64_t tile) {
+    int64_t r0 = tile * a.rows;
+    int rows_here = (int)min((int64_t)a.rows, a.R - r0);
+    const float* ps = a.params + r0 * row_floats;
+    const int np = rows_here * row_floats;
+    const bool bp = bulk_ok(ps, np);
+    if (threadIdx.x == 0) {
+      if (bp) mbar_expect_tx(&bars[st], (uint32_t)np * 4u);
+      else mbar_arrive(&bars[st]);
+    }
+    load_chunk(stage[st], ps, np, &bars[st], bp);
+  };
   for (int st = 0; st < RQS_STAGES; ++st) {
     int64_t tile = (int64_t)blockIdx.x + (int64_t)st * gridDim.x;
-    if (tile < ntiles) load_tile(la, stage[st], &bars[st], tile, row_floats);
+    if (tile < ntiles) load_params(st, tile);
   }
 
   int it = 0;
@@ -256,7 +283,7 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
     // write the gradient tile: bulk store when 16B-granular, else plain
     uint32_t bytes = (uint32_t)rows_here * row_floats * 4u;
     float* dst = a.d_params + r0 * row_floats;
-    if ((bytes & 15u) == 0) {
+    if (bulk_ok(dst, rows_here * row_floats)) {
       fence_proxy_async_smem();
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -271,7 +298,7 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
       __syncthreads();
     }
     int64_t nxt = tile + (int64_t)RQS_STAGES * gridDim.x;
-    if (nxt < ntiles) load_tile(la, stage[st], &bars[st], nxt, row_floats);
+    if (nxt < ntiles) load_params(st, nxt);
   }
   if (threadIdx.x == 0) bulk_wait_all<0>();
 }
