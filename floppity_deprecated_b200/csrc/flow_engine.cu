@@ -19,14 +19,17 @@ namespace fp {
 
 // from the other translation units
 int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int drop_width, cudaStream_t stream);
-int launch_gemm_ctx(const fp_gemm_args* a, cudaStream_t stream);   // may route to the tcgen05 path (gemm_tc.cu)
+int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, cudaStream_t stream);   // gemm_tc.cu
+int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
+int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params, float* t_hi, float* t_lo, cudaStream_t stream);
+bool tc_enabled();
 int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                      float* theta_out, float* theta_sp, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status,
                      const float* luM, const float* luPre, float pre_sign, const float* luPost,
-                     const float* lu_logdet, cudaStream_t stream);
+                     const float* lu_logdet, int ldp, cudaStream_t stream);
 int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                         const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
-                        int64_t R, cudaStream_t stream);
+                        int64_t R, int ldp, cudaStream_t stream);
 int launch_affine_fwd(const float*, const float*, const float*, float, float*, float*, int64_t, int, cudaStream_t);
 int launch_affine_inv(const float*, const float*, const float*, float*, int64_t, int, cudaStream_t);
 int launch_affine_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
@@ -96,6 +99,36 @@ static fp_gemm_args dgrad_args(const float* dOut, int64_t ldo, int n_out, const 
   return g;
 }
 
+// forward GEMM against a weight matrix living at `woff` in the parameter buffer: tcgen05 3xTF32 when the shape
+// allows (pre-split weights in `prepared`), else the fp32 SIMT kernel
+static int gemm_weight(const Layout& L, const float* prepared, int64_t woff, fp_gemm_args* g, float drop_p, uint64_t seed,
+                       int drop_width, cudaStream_t s) {
+  if (drop_p == 0.f && prepared) {
+    int r = launch_gemm_tc(g, prepared + L.prepHi() + woff, prepared + L.prepLo() + woff, s);
+    if (r != FP_E_NOTREADY) return r;
+  }
+  return launch_gemm(g, drop_p, seed, drop_width, s);
+}
+
+// dIn[R, k_in] (=|+=) dOut[R, n_out] @ W[n_out, k_in] with the epilogue flags in `flags`:
+// tcgen05 against the pre-transposed + split copy W^T [k_in, ld_t] at `toff`, else SIMT against W itself
+static int dgrad_weight(const Layout& L, const float* prepared, int64_t toff, int64_t ld_t, const float* dOut, int64_t ldo,
+                        int n_out, const float* W, int64_t ldw, int k_in, int64_t R, float* dIn, int64_t ldi, int flags,
+                        const float* Msk, int64_t ldm, float drop_p, uint64_t seed, int drop_width, cudaStream_t s) {
+  if (drop_p == 0.f && prepared) {
+    fp_gemm_args g{};
+    g.A = dOut; g.lda = ldo; g.a_kmajor = 1;
+    g.B = prepared + L.prepTHi() + toff; g.ldb = ld_t; g.b_kmajor = 1;
+    g.C = dIn; g.ldc = ldi; g.M = R; g.N = k_in; g.K = n_out; g.flags = flags; g.split_k = 1;
+    g.Msk = Msk; g.ldm = ldm;
+    int r = launch_gemm_tc(&g, prepared + L.prepTHi() + toff, prepared + L.prepTLo() + toff, s);
+    if (r != FP_E_NOTREADY) return r;
+  }
+  fp_gemm_args g = dgrad_args(dOut, ldo, n_out, W, ldw, k_in, R, dIn, ldi, flags);
+  g.Msk = Msk; g.ldm = ldm;
+  return launch_gemm(&g, drop_p, seed, drop_width, s);
+}
+
 static inline uint64_t layer_seed(uint64_t seed, int layer, int block) {
   return seed * 0x9E3779B97F4A7C15ull + (uint64_t)(layer * 64 + block + 1) * 0xD6E8FEB86659FD93ull;
 }
@@ -109,7 +142,8 @@ struct CondBufs {
   float* prm;
 };
 
-static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const float* params, int i, const float* theta_i,
+static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
+                               const float* theta_i,
                                const float* ctx_all, int64_t R, int ctx_div, const CondBufs& b, bool training,
                                uint64_t seed, cudaStream_t s) {
   const int H = L.H, D = L.D;
@@ -117,13 +151,13 @@ static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const 
   {  // initial layer: h0 = theta_i @ W0x^T + (ctx @ W0ctx^T + b0)   [the bracket is a column block of ctx_all]
     fp_gemm_args g = gemm_nt(theta_i, D, params + L.w0x(i), D, b.h[0], H, R, H, D, FP_G_ADD_CTX);
     g.G = ctx_all + L.ctxCol(i, 0); g.ldg = L.Nctx; g.ctx_div = ctx_div;
-    FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+    FP_TRY(gemm_weight(L, prepared, L.w0x(i), &g, 0.f, 0, 0, s));
   }
   for (int k = 0; k < L.Bk; ++k) {
     {  // t = relu(h) @ W1^T + b1
       fp_gemm_args g = gemm_nt(b.h[k], H, params + L.w1(i, k), H, b.t[k], H, R, H, H, FP_G_RELU_A | FP_G_BIAS);
       g.bias = params + L.b1(i, k);
-      FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+      FP_TRY(gemm_weight(L, prepared, L.w1(i, k), &g, 0.f, 0, 0, s));
     }
     {  // u = dropout(relu(t)) @ W2^T + b2 ; h_next = h + u * sigmoid(ctx gate)
       int fl = FP_G_RELU_A | FP_G_BIAS | FP_G_GLU_RES | (drop > 0.f ? 512 : 0);
@@ -132,22 +166,22 @@ static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const 
       g.G = ctx_all + L.ctxCol(i, 1 + k); g.ldg = L.Nctx; g.ctx_div = ctx_div;
       g.Rsd = b.h[k]; g.ldr = H;
       g.U = b.u[k]; g.ldu = H;
-      FP_TRY(launch_gemm(&g, drop, layer_seed(seed, i, k), H, s));
+      FP_TRY(gemm_weight(L, prepared, L.w2(i, k), &g, drop, layer_seed(seed, i, k), H, s));
     }
   }
   {  // params = h @ Wf^T + bf
-    fp_gemm_args g = gemm_nt(b.h[L.Bk], H, params + L.wf(i), H, b.prm, L.dP(i), R, L.dP(i), H, FP_G_BIAS);
+    fp_gemm_args g = gemm_nt(b.h[L.Bk], H, params + L.wf(i), H, b.prm, L.ldP(i), R, L.dP(i), H, FP_G_BIAS);
     g.bias = params + L.bf(i);
-    FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
+    FP_TRY(gemm_weight(L, prepared, L.wf(i), &g, 0.f, 0, 0, s));
   }
   return 0;
 }
 
-static int context_projection(const Layout& L, const float* params, const float* ctx, int64_t Rc, float* ctx_all,
-                              cudaStream_t s) {
+static int context_projection(const Layout& L, const float* params, const float* prepared, const float* ctx, int64_t Rc,
+                              float* ctx_all, cudaStream_t s) {
   fp_gemm_args g = gemm_nt(ctx, L.C, params + L.ctx_w, L.C, ctx_all, L.Nctx, Rc, (int)L.Nctx, L.C, FP_G_BIAS);
   g.bias = params + L.ctx_b;
-  return launch_gemm_ctx(&g, s);
+  return gemm_weight(L, prepared, L.ctx_w, &g, 0.f, 0, 0, s);
 }
 
 }  // namespace fp
@@ -206,7 +240,7 @@ int64_t fp_nsf_param_size(const fp_nsf_config* cfg, int32_t layer, int32_t kind)
 }
 int64_t fp_nsf_prepared_count(const fp_nsf_config* cfg) {
   if (check_cfg(cfg)) return FP_E_BADARG;
-  return Layout(cfg).prepTotal();
+  return Layout(cfg).prepAll();
 }
 int64_t fp_nsf_workspace_count(const fp_nsf_config* cfg, int64_t R, int64_t Rc, int32_t training) {
   if (check_cfg(cfg) || R < 0 || Rc < 0) return FP_E_BADARG;
@@ -220,6 +254,11 @@ int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepare
   ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_lu_prepare<<<cfg->T, 128, sm, (cudaStream_t)stream>>>(params, prepared, *cfg);
   FP_LAUNCH_CHECK();
+  if (tc_enabled()) {   // TF32 hi / lo split of every weight, once per optimiser step
+    Layout L(cfg);
+    FP_TRY(launch_split_tf32(params, prepared + L.prepHi(), prepared + L.prepLo(), L.total(), (cudaStream_t)stream));
+    FP_TRY(launch_transpose_split_weights(cfg, params, prepared + L.prepTHi(), prepared + L.prepTLo(), (cudaStream_t)stream));
+  }
   return 0;
 }
 
@@ -248,7 +287,7 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
 
   float* ctx_all = ws + W.ctx_all;
   float* logdet = ws + W.logdet;
-  FP_TRY(context_projection(L, params, ctx, Rc, ctx_all, s));
+  FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
 
   float* th_cur = training ? ws + W.thst(0) : ws + W.th_a;
   FP_TRY(launch_affine_fwd(theta, zshift, zscale, zlogdet, th_cur, logdet, R, D, s));
@@ -268,9 +307,9 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
       b.prm = ws + W.prm;
       th_next = (th_cur == ws + W.th_a) ? ws + W.th_b : ws + W.th_a;
     }
-    FP_TRY(conditioner_forward(cfg, L, params, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, s));
+    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, s));
     FP_TRY(launch_rqs_apply(false, cfg, i & 1, th_cur, b.prm, th_next, th_sp, logdet, nullptr, R, status,
-                            prepared + L.prepM(i), nullptr, 1.f, params + L.luBias(i), prepared + L.prepLogdet(i), s));
+                            prepared + L.prepM(i), nullptr, 1.f, params + L.luBias(i), prepared + L.prepLogdet(i), L.ldP(i), s));
     th_cur = th_next;
   }
   FP_TRY(launch_base_logprob(th_cur, logdet, logp, R, D, status, s));
@@ -309,15 +348,12 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
       FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
     }
     // ---- spline backward: d params, d theta_in (identity features pass through)
-    const int dP = L.dP(i);
-    FP_TRY(launch_rqs_backward(cfg, i & 1, ws + W.thst(i), ws + W.prmbuf(i), dth_b, d_logp, dprm, dth_a, R, s));
+    const int dP = L.dP(i), ldP = L.ldP(i);
+    FP_TRY(launch_rqs_backward(cfg, i & 1, ws + W.thst(i), ws + W.prmbuf(i), dth_b, d_logp, dprm, dth_a, R, ldP, s));
     // ---- final layer
-    FP_TRY(launch_colsum(dprm, dP, R, dP, grads + L.bf(i), s));
-    FP_TRY(wgrad(dprm, dP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, 0.f, 0, 0, s));
-    {
-      fp_gemm_args g = dgrad_args(dprm, dP, dP, params + L.wf(i), H, H, R, dh, H, 0);
-      FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
-    }
+    FP_TRY(launch_colsum(dprm, ldP, R, dP, grads + L.bf(i), s));
+    FP_TRY(wgrad(dprm, ldP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, 0.f, 0, 0, s));
+    FP_TRY(dgrad_weight(L, prepared, L.tWf(i), ldP, dprm, ldP, dP, params + L.wf(i), H, H, R, dh, H, 0, nullptr, 0, 0.f, 0, 0, s));
     // ---- residual blocks, last to first
     for (int k = L.Bk - 1; k >= 0; --k) {
       const uint64_t seed = layer_seed(dropout_seed, i, k);
@@ -326,27 +362,18 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
       FP_TRY(launch_colsum(du, H, R, H, grads + L.b2(i, k), s));
       FP_TRY(wgrad(du, H, H, ws + W.tbuf(i, k), H, H, R, grads + L.w2(i, k), H,
                    FP_G_RELU_B | (drop > 0.f ? 1024 : 0), drop, seed, H, s));
-      {
-        fp_gemm_args g = dgrad_args(du, H, H, params + L.w2(i, k), H, H, R, dt, H,
-                                    FP_G_RELUMASK | (drop > 0.f ? 2048 : 0));
-        g.Msk = ws + W.tbuf(i, k); g.ldm = H;
-        FP_TRY(launch_gemm(&g, drop, seed, H, s));
-      }
+      FP_TRY(dgrad_weight(L, prepared, L.tW2(i, k), H, du, H, H, params + L.w2(i, k), H, H, R, dt, H,
+                          FP_G_RELUMASK | (drop > 0.f ? 2048 : 0), ws + W.tbuf(i, k), H, drop, seed, H, s));
       FP_TRY(launch_colsum(dt, H, R, H, grads + L.b1(i, k), s));
       FP_TRY(wgrad(dt, H, H, ws + W.hbuf(i, k), H, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, 0.f, 0, 0, s));
-      {
-        fp_gemm_args g = dgrad_args(dt, H, H, params + L.w1(i, k), H, H, R, dh, H, FP_G_RELUMASK | FP_G_ACCUM);
-        g.Msk = ws + W.hbuf(i, k); g.ldm = H;
-        FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
-      }
+      FP_TRY(dgrad_weight(L, prepared, L.tW1(i, k), H, dt, H, H, params + L.w1(i, k), H, H, R, dh, H,
+                          FP_G_RELUMASK | FP_G_ACCUM, ws + W.hbuf(i, k), H, 0.f, 0, 0, s));
     }
     // ---- initial layer: h0 = theta_i @ W0x^T + ctx slot 0
     FP_TRY(launch_ctx_reduce(dh, dctx_all + L.ctxCol(i, 0), L.Nctx, Rc, A, H, s));
     FP_TRY(wgrad(dh, H, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, 0.f, 0, 0, s));
-    {
-      fp_gemm_args g = dgrad_args(dh, H, H, params + L.w0x(i), D, D, R, dth_a, D, FP_G_ACCUM);
-      FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
-    }
+    FP_TRY(dgrad_weight(L, prepared, L.tW0(i), H, dh, H, H, params + L.w0x(i), D, D, R, dth_a, D, FP_G_ACCUM, nullptr, 0,
+                        0.f, 0, 0, s));
   }
   if (d_theta) FP_TRY(launch_affine_bwd(dth_a, zscale, d_theta, R, D, s));
 
@@ -369,7 +396,7 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
   const int ctx_div = (Rc == 1) ? 0 : (int)(R / Rc);
   const int D = L.D;
   float* ctx_all = ws + W.ctx_all;
-  FP_TRY(context_projection(L, params, ctx, Rc, ctx_all, s));
+  FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
 
   // inverse of the last LULinear on the base noise
   float* th_cur = ws + W.th_a; float* th_next = ws + W.th_b;
@@ -379,12 +406,12 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
     for (int k = 0; k <= L.Bk; ++k) b.h[k] = ws + W.h;
     for (int k = 0; k < L.Bk; ++k) { b.t[k] = ws + W.t; b.u[k] = nullptr; }
     b.prm = ws + W.prm;
-    FP_TRY(conditioner_forward(cfg, L, params, i, th_cur, ctx_all, R, ctx_div, b, false, 0, s));
+    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, false, 0, s));
     // spline inverse of layer i fused with the inverse LULinear of layer i-1
     const float* M = (i > 0) ? prepared + L.prepMinv(i - 1) : nullptr;
     const float* pre = (i > 0) ? params + L.luBias(i - 1) : nullptr;
     FP_TRY(launch_rqs_apply(true, cfg, i & 1, th_cur, b.prm, th_next, nullptr, nullptr, nullptr, R, status, M, pre, -1.f,
-                            nullptr, nullptr, s));
+                            nullptr, nullptr, L.ldP(i), s));
     float* tmp = th_cur; th_cur = th_next; th_next = tmp;
   }
   FP_TRY(launch_affine_inv(th_cur, zshift, zscale, theta_out, R, D, s));

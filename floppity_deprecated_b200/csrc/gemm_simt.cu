@@ -9,6 +9,7 @@
 // This is the exact-fp32 path; the tcgen05 path (gemm_tc.cu) takes over the large context projection.
 #include "common.cuh"
 #include "prof.h"
+#include "gemm_epilogue.cuh"
 #include <algorithm>
 
 namespace fp {
@@ -16,27 +17,6 @@ namespace fp {
 constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
 constexpr int GEMM_THREADS = (BM / TM) * (BN / TN);  // 256
 constexpr int APAD = 4, BPAD = 4;
-
-__device__ __forceinline__ uint32_t mix32(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
-}
-// keep-probability test shared by forward prologue and backward mask: element (row, col) of the
-// dropped activation matrix with `width` columns
-__device__ __forceinline__ float drop_scale(uint64_t seed, int64_t row, int col, int width, float p) {
-  uint32_t h = mix32(seed ^ (uint64_t)(row * (int64_t)width + col));
-  float u = (float)(h >> 8) * (1.0f / 16777216.0f);
-  return u < p ? 0.f : 1.f / (1.f - p);
-}
-
-struct GemmDrop {
-  float p;          // 0 => off
-  uint64_t seed;
-  int width;        // columns of the dropped activation matrix
-};
 
 template <bool A_KMAJ, bool B_KMAJ>
 __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k_chunk, GemmDrop drop) {
@@ -192,33 +172,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k
   }
 
   // ---- epilogue ----
-  const int fl = g.flags;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int64_t m = m0 + ty * TM + i;
     if (m >= g.M) continue;
-    int64_t cr = (g.ctx_div > 0) ? (m / g.ctx_div) : 0;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int n = n0 + tx * TN + j;
       if (n >= g.N) continue;
-      float v = acc[i][j];
-      if (fl & FP_G_BIAS) v += g.bias[n];
-      if (fl & FP_G_ADD_CTX) v += g.G[cr * g.ldg + n];
-      if (fl & FP_G_GLU_RES) {
-        if (g.U) g.U[m * g.ldu + n] = v;
-        float gate = g.G[cr * g.ldg + n];
-        v = g.Rsd[m * g.ldr + n] + v * (1.f / (1.f + expf(-gate)));
-      }
-      if (fl & FP_G_RELUMASK) {
-        float mk = g.Msk[m * g.ldm + n];
-        v = mk > 0.f ? v : 0.f;
-        if (drop.p > 0.f && (fl & 2048)) v *= drop_scale(drop.seed, m, n, drop.width, drop.p);
-      }
-      float* c = g.C + m * g.ldc + n;
-      if (fl & FP_G_ATOMIC) atomicAdd(c, v);
-      else if (fl & FP_G_ACCUM) *c += v;
-      else *c = v;
+      gemm_epilogue_store(g, drop, m, n, acc[i][j]);
     }
   }
 }

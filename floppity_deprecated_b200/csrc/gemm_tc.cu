@@ -1,6 +1,491 @@
-// gemm_tc.cu -- router for the context-projection GEMM.  (tcgen05 path lands here; SIMT for now.)
+// gemm_tc.cu -- conditioner GEMMs on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-accurate.
+//
+// Same contract as the SIMT kernel (gemm_simt.cu): C[M,N] = pro(A)[M,K] * B[N,K]^T with the fused ResidualNet
+// epilogues (nflows ResidualNet reached from /root/reference/modules.py:63).  The reference computes these layers in
+// fp32; a single TF32/bf16 pass would miss the 1e-4 parity bar, so every product is evaluated as the 3xTF32 split
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo ,  x_hi = tf32(x), x_lo = x - x_hi      (error ~2^-21 |a||b|)
+// accumulated in fp32 TMEM accumulators (hi*hi and the cross terms separately, see the kernel comment).
+//
+// Persistent warp-specialised CTA (320 threads, 128x128 output tiles, K in blocks of 32 fp32 = one 128-byte
+// swizzle row):
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw fp32 A tile and the pre-split B_hi / B_lo tiles
+//               (weights are split once per optimiser step) into a 3-stage shared-memory ring (SWIZZLE_128B).
+//   warp 1      MMA issuer: one elected thread issues 3 products x 4 k-steps of tcgen05.mma.kind::tf32 (M128 N128 K8)
+//               per stage from shared-memory descriptors; tcgen05.commit releases the stage / signals the epilogue.
+//   warps 2-5   splitter: relu prologue + hi/lo split of the A tile IN PLACE (elementwise, so the swizzle is
+//               irrelevant), fence.proxy.async, arrive on the stage's "ready" mbarrier.
+//   warps 6-9   epilogue: tcgen05.ld TMEM -> registers -> shared (32-column slab) -> coalesced float4 stores with
+//               bias / context-add / GLU-gate+residual / relu-mask applied; overlaps the next tile's mainloop
+//               (two accumulator sets in TMEM).
 #include "common.cuh"
+#include "prof.h"
+#include "gemm_epilogue.cuh"
+#include "layout.h"
+#include <cuda.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <stdlib.h>
+#include <algorithm>
+
 namespace fp {
+
 int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int drop_width, cudaStream_t stream);
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB: 128 rows x 128 B
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // A(raw->hi), A_lo, B_hi, B_lo
+constexpr int TC_THREADS = 448;                           // producer, MMA, 4 splitter warps, 8 epilogue warps
+constexpr int TC_CS_LD = 20;                              // epilogue staging slab: 128 rows x 16 columns (+4 pad)
+constexpr int TC_CS_BYTES = 2 * TC_BM * TC_CS_LD * 4;     // one slab per column half
+constexpr int TC_KCHUNK_BLOCKS = 32;                      // K chunk (1024) for long contractions, see k_gemm_tc_nt
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major operand tile in SWIZZLE_128B layout (rows of 128 bytes, 8-row 1024-byte atoms):
+// start address (>>4), LBO = 16 B (ignored for swizzled K-major), SBO = 1024 B, version 1, layout SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_kmajor_desc(const void* smem_tile) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Persistent kernel: CTA c processes output tiles c, c+grid, ... ; every role walks the same tile sequence.
+// TMEM (512 columns) holds two accumulator sets {hi*hi, cross terms} so the epilogue of tile i overlaps the
+// mainloop of tile i+1.  Tensor-core accumulation truncates, so its error grows with the number of chained
+// MMAs: the big hi*hi products get their own accumulator (the small cross terms cannot disturb it) and
+// contractions longer than 1024 are cut into chunks whose partial sums are added in fp32 by the epilogue
+// (only for the plain/bias epilogue, which is all the long-K context projection needs).
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+             const __grid_constant__ CUtensorMap mapBl, fp_gemm_args g, int nkb_total, int nchunks, int vec_all) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  float* Cs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES);
+  uint64_t* ready = full_raw + TC_STAGES;
+  uint64_t* empty = ready + TC_STAGES;
+  uint64_t* acc_full = empty + TC_STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (g.N + TC_BN - 1) / TC_BN;
+  const int64_t tiles_m = (g.M + TC_BM - 1) / TC_BM;
+  const int64_t n_super = tiles_m * tiles_n;
+  const int kb_per_chunk = (nkb_total + nchunks - 1) / nchunks;
+  // rasterisation: concurrently running CTAs should share tiles of the LARGER operand stream, i.e. walk the
+  // dimension of the smaller operand fastest (activations [M,K] vs weights [N,K]); the other one stays in L2
+  const bool m_fast = g.M <= (int64_t)g.N;
+  auto tile_m0 = [&](int64_t st) -> int64_t { return (m_fast ? (st % tiles_m) : (st / tiles_n)) * TC_BM; };
+  auto tile_n0 = [&](int64_t st) -> int { return (int)(m_fast ? (st / tiles_m) : (st % tiles_n)) * TC_BN; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;   // global k-block counter -> ring slot / phase
+      for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+        const int64_t m0 = tile_m0(st);
+        const int n0 = tile_n0(st);
+        for (int kb = 0; kb < nkb_total; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (it / TC_STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* sb = smem + s * TC_STAGE_BYTES;
+          mbar_expect_tx(&full_raw[s], 3 * TC_TILE_BYTES);
+          tma_load_2d(sb, &mapA, kb * TC_BK, (int)m0, &full_raw[s]);
+          tma_load_2d(sb + 2 * TC_TILE_BYTES, &mapBh, kb * TC_BK, n0, &full_raw[s]);
+          tma_load_2d(sb + 3 * TC_TILE_BYTES, &mapBl, kb * TC_BK, n0, &full_raw[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+      uint32_t it = 0, tile_it = 0;
+      for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+        for (int kc = 0; kc < nchunks; ++kc, ++tile_it) {
+          const int buf = tile_it & 1;
+          const uint32_t aph = (tile_it >> 1) & 1u;
+          mbar_wait(&acc_empty[buf], aph ^ 1u);             // epilogue has drained this accumulator set
+          tcgen05_fence_after();
+          const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256);
+          const uint32_t t_x = t_hh + 128;
+          const int kb0 = kc * kb_per_chunk;
+          const int kb1 = min(nkb_total, kb0 + kb_per_chunk);
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (it / TC_STAGES) & 1u;
+            mbar_wait(&ready[s], ph);
+            tcgen05_fence_after();
+            uint8_t* sb = smem + s * TC_STAGE_BYTES;
+            const uint64_t a_hi = make_kmajor_desc(sb), a_lo = make_kmajor_desc(sb + TC_TILE_BYTES);
+            const uint64_t b_hi = make_kmajor_desc(sb + 2 * TC_TILE_BYTES), b_lo = make_kmajor_desc(sb + 3 * TC_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per UMMA_K inside the swizzle row
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              umma_tf32(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
+              umma_tf32(t_x, a_lo + adv, b_hi + adv, idesc, acc);
+              umma_tf32(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
+            }
+            umma_commit(&empty[s]);        // ring slot reusable once these MMAs have read it
+          }
+          umma_commit(&acc_full[buf]);     // this accumulator set is complete
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== splitter warps 2..5: relu prologue + TF32 hi/lo split of the A tile, in place =====
+    const int tid_s = threadIdx.x - 64;       // 0..127
+    const bool relu_a = (g.flags & FP_G_RELU_A) != 0;
+    uint32_t it = 0;
+    for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+      for (int kb = 0; kb < nkb_total; ++kb, ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1u;
+        mbar_wait(&full_raw[s], ph);
+        float4* A = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
+        float4* Alo = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
+          const int idx = tid_s + i * 128;
+          float4 v = A[idx];
+          if (relu_a) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+          A[idx] = h;
+          Alo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+      }
+    }
+  } else {
+    // ===== epilogue warps 6..13: two warps per TMEM lane quarter, each owning one 64-column half =====
+    const int ew = warp - 6;                   // 0..7
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                  // column half
+    const int tid_h = (ew & 3) * 32 + lane;    // 0..127 within the half
+    const int row = q * 32 + lane;             // accumulator row held by this thread
+    float* slab = Cs + half * (TC_BM * TC_CS_LD);
+    const GemmDrop nodrop{0.f, 0, 0};
+    uint32_t tile_it = 0;
+    for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+      const int64_t m0 = tile_m0(st);
+      const int n0 = tile_n0(st);
+      for (int kc = 0; kc < nchunks; ++kc, ++tile_it) {
+        const int buf = tile_it & 1;
+        const uint32_t aph = (tile_it >> 1) & 1u;
+        fp_gemm_args ge = g;                     // later K chunks add onto the stored partial result
+        if (kc > 0) ge.flags = (g.flags & ~FP_G_BIAS) | FP_G_ACCUM;
+        mbar_wait(&acc_full[buf], aph);
+        tcgen05_fence_after();
+        const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16], x[16];
+          tmem_ld_32x16(t_hh + (uint32_t)c0, v);
+          tmem_ld_32x16(t_hh + 128u + (uint32_t)c0, x);
+          if (c0 + 16 == 64) {                   // all TMEM reads of this set are done: hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(&slab[row * TC_CS_LD + j]) =
+                make_float4(v[j] + x[j], v[j + 1] + x[j + 1], v[j + 2] + x[j + 2], v[j + 3] + x[j + 3]);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (tid_h >> 2) + 32 * i;
+            const int c = (tid_h & 3) * 4;
+            const int64_t m = m0 + r;
+            const int n = n0 + half * 64 + c0 + c;
+            if (m < ge.M && n < ge.N) {
+              const float4 o = *reinterpret_cast<const float4*>(&slab[r * TC_CS_LD + c]);
+              if (vec_all && n + 3 < ge.N) {
+                gemm_epilogue_store4(ge, m, n, o);
+              } else {
+                const float e[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (n + j < ge.N) gemm_epilogue_store(ge, nodrop, m, n + j, e[j]);
+              }
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- weight / activation split helper: hi = tf32(x), lo = x - hi ---------------------------------------
+__global__ void k_split_tf32(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    float h = tf32_round(v);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+// transpose + split of every weight matrix the dgrad GEMMs need, one launch: blockIdx.y = tensor id
+// (layer * (2*Bk+2) + {0: W0x, 1+2b: W1_b, 2+2b: W2_b, 2Bk+1: Wf}), blockIdx.x = 32x32 tile
+__global__ void k_transpose_split_weights(const float* __restrict__ params, float* __restrict__ t_hi,
+                                          float* __restrict__ t_lo, fp_nsf_config cfg) {
+  __shared__ float tile[32][33];
+  const Layout L(&cfg);
+  const int per = 2 * L.Bk + 2;
+  const int layer = blockIdx.y / per, which = blockIdx.y % per;
+  int rows, cols, ld_dst; int64_t src, dst;
+  if (which == 0) { rows = L.H; cols = L.D; src = L.w0x(layer); dst = L.tW0(layer); ld_dst = L.H; }
+  else if (which == per - 1) { rows = L.dP(layer); cols = L.H; src = L.wf(layer); dst = L.tWf(layer); ld_dst = L.ldP(layer); }
+  else {
+    const int b = (which - 1) / 2;
+    rows = L.H; cols = L.H; ld_dst = L.H;
+    if ((which - 1) % 2 == 0) { src = L.w1(layer, b); dst = L.tW1(layer, b); }
+    else { src = L.w2(layer, b); dst = L.tW2(layer, b); }
+  }
+  const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  if ((int)blockIdx.x >= tiles_c * tiles_r) return;
+  const int r0 = (blockIdx.x / tiles_c) * 32, c0 = (blockIdx.x % tiles_c) * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? params[src + (int64_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;      // dst[c][r]
+    if (c < cols && r < rows) {
+      float v = tile[threadIdx.x][i];
+      float h = tf32_round(v);
+      t_hi[dst + (int64_t)c * ld_dst + r] = h;
+      t_lo[dst + (int64_t)c * ld_dst + r] = v - h;
+    }
+  }
+}
+
+// ---- host side: tensor maps (cached) ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with leading dimension ld (floats); box = 32 cols x 128 rows, SWIZZLE_128B
+static bool get_tensor_map(const float* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
+  typedef std::tuple<const void*, int64_t, int64_t, int64_t> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  Key key(base, rows, cols, ld);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
+
+bool tc_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FLOPPITY_TC");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// Can this GEMM go to the tcgen05 NT kernel?  (both operands K-major, TMA-compatible strides, no dropout/split-K)
+static bool tc_supported(const fp_gemm_args* a) {
+  if (!a->a_kmajor || !a->b_kmajor) return false;
+  if ((a->lda & 3) || (a->ldb & 3)) return false;
+  if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return false;
+  if (a->flags & (FP_G_RELU_B | FP_G_DROP_A | FP_G_DROP_B | FP_G_DROPMASK | FP_G_ATOMIC)) return false;
+  if (a->split_k > 1) return false;
+  if (a->M < 1 || a->N < 1 || a->K < 1 || a->M > 2147483647LL) return false;
+  return true;
+}
+
+// B_hi / B_lo: the pre-split weight matrix, same shape and ld as a->B
+int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, cudaStream_t stream) {
+  if (!tc_enabled() || !tc_supported(a) || !B_hi || !B_lo) return FP_E_NOTREADY;
+  if ((reinterpret_cast<uintptr_t>(B_hi) & 15) || (reinterpret_cast<uintptr_t>(B_lo) & 15)) return FP_E_NOTREADY;
+  CUtensorMap mA, mBh, mBl;
+  if (!get_tensor_map(a->A, a->M, a->K, a->lda, &mA)) return FP_E_NOTREADY;
+  if (!get_tensor_map(B_hi, a->N, a->K, a->ldb, &mBh)) return FP_E_NOTREADY;
+  if (!get_tensor_map(B_lo, a->N, a->K, a->ldb, &mBl)) return FP_E_NOTREADY;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int nkb = (int)((a->K + TC_BK - 1) / TC_BK);
+  // long contractions are chunked (see the kernel comment); only the plain / bias epilogue can be accumulated
+  const bool plain = (a->flags & ~(FP_G_RELU_A | FP_G_BIAS)) == 0;
+  const int nchunks = (plain && nkb > TC_KCHUNK_BLOCKS) ? (nkb + TC_KCHUNK_BLOCKS - 1) / TC_KCHUNK_BLOCKS : 1;
+  const int64_t tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + TC_BN - 1) / TC_BN);
+  const int grid = (int)std::min<int64_t>(tiles, num_sms());
+  ProfScope ps(TAG_GEMM_TC, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream);
+  // float4 epilogue needs every pointer the flags touch to be 16-byte aligned with a leading dimension % 4 == 0
+  auto ok = [](const void* p, int64_t ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 3) == 0)); };
+  int vec_all = ok(a->C, a->ldc) ? 1 : 0;
+  if ((a->flags & FP_G_BIAS) && !ok(a->bias, 4)) vec_all = 0;
+  if ((a->flags & (FP_G_ADD_CTX | FP_G_GLU_RES)) && !ok(a->G, a->ldg)) vec_all = 0;
+  if ((a->flags & FP_G_GLU_RES) && (!ok(a->Rsd, a->ldr) || !ok(a->U, a->ldu))) vec_all = 0;
+  if ((a->flags & FP_G_RELUMASK) && !ok(a->Msk, a->ldm)) vec_all = 0;
+  k_gemm_tc_nt<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mA, mBh, mBl, *a, nkb, nchunks, vec_all);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, 8 * num_sms());
+  ProfScope ps(TAG_OTHER, 0.0, stream);
+  k_split_tf32<<<blocks, 256, 0, stream>>>(x, hi, lo, n);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params, float* t_hi, float* t_lo, cudaStream_t stream) {
+  Layout L(cfg);
+  int maxdim_r = std::max(L.H, L.dPmax()), maxdim_c = std::max(L.H, L.D);
+  int tiles = ((maxdim_r + 31) / 32) * ((maxdim_c + 31) / 32);
+  dim3 grid(tiles, L.T * (2 * L.Bk + 2));
+  ProfScope ps(TAG_OTHER, 0.0, stream);
+  k_transpose_split_weights<<<grid, dim3(32, 8), 0, stream>>>(params, t_hi, t_lo, *cfg);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+// router used by the engine for the context projection (weights split by fp_nsf_prepare)
 int launch_gemm_ctx(const fp_gemm_args* a, cudaStream_t stream) { return launch_gemm(a, 0.f, 0, 0, stream); }
+
 }  // namespace fp
+
+extern "C" {
+// Standalone entry: C = pro(A) * B^T (+ epilogue) on the tensor cores; B_hi/B_lo from fp_split_tf32.
+// Returns FP_E_NOTREADY when the shape/stride/flags are not supported by the tcgen05 kernel.
+int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, void* stream) {
+  if (!args) return FP_E_BADARG;
+  return fp::launch_gemm_tc(args, B_hi, B_lo, (cudaStream_t)stream);
+}
+int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  return fp::launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);
+}
+}

@@ -36,6 +36,8 @@ struct Layout {
   FP_LHD int dtr(int i) const { return (i % 2 == 0) ? (D + 1) / 2 : D / 2; }
   FP_LHD int dP(int i) const { return dtr(i) * P; }
   FP_LHD int dPmax() const { return dtr(0) * P; }
+  FP_LHD int ldP(int i) const { return (dP(i) + 3) & ~3; }      // padded row stride of the spline-parameter buffers
+  FP_LHD int ldPmax() const { return (dPmax() + 3) & ~3; }
   FP_LHD int64_t block_sz() const { return al4_((int64_t)H * H) * 2 + al4_(H) * 2; }
   FP_LHD int64_t layer_sz(int i) const {
     return al4_((int64_t)H * D) + Bk * block_sz() + al4_((int64_t)dP(i) * H) + al4_(dP(i)) + 2 * al4_(ntri) + 2 * al4_(D);
@@ -73,6 +75,21 @@ struct Layout {
   FP_LHD int64_t prepU(int i) const { return prepM(i) + 3 * al4_((int64_t)D * D); }
   FP_LHD int64_t prepLogdet(int i) const { return prepM(i) + 4 * al4_((int64_t)D * D); }
   FP_LHD int64_t prepTotal() const { return (int64_t)T * prepSz(); }
+  // tensor-core path: TF32 hi / lo copies of the whole parameter buffer (same offsets as the parameters)
+  FP_LHD int64_t prepHi() const { return (prepTotal() + 31) & ~int64_t(31); }
+  FP_LHD int64_t prepLo() const { return prepHi() + ((total() + 31) & ~int64_t(31)); }
+  // transposed (+ split) weight copies for the dgrad GEMMs: per layer W0x^T [D,H], per block W1^T, W2^T [H,H],
+  // Wf^T [H, ldP]; region T_hi then T_lo
+  FP_LHD int64_t tLayerSz(int i) const { return al4_((int64_t)D * H) + Bk * 2 * al4_((int64_t)H * H) + al4_((int64_t)H * ldP(i)); }
+  FP_LHD int64_t tLayerOff(int i) const { int64_t o = 0; for (int l = 0; l < i; ++l) o += tLayerSz(l); return o; }
+  FP_LHD int64_t tW0(int i) const { return tLayerOff(i); }
+  FP_LHD int64_t tW1(int i, int b) const { return tLayerOff(i) + al4_((int64_t)D * H) + (int64_t)b * 2 * al4_((int64_t)H * H); }
+  FP_LHD int64_t tW2(int i, int b) const { return tW1(i, b) + al4_((int64_t)H * H); }
+  FP_LHD int64_t tWf(int i) const { return tLayerOff(i) + al4_((int64_t)D * H) + Bk * 2 * al4_((int64_t)H * H); }
+  FP_LHD int64_t tTotal() const { return (tLayerOff(T) + 31) & ~int64_t(31); }
+  FP_LHD int64_t prepTHi() const { return prepLo() + ((total() + 31) & ~int64_t(31)); }
+  FP_LHD int64_t prepTLo() const { return prepTHi() + tTotal(); }
+  FP_LHD int64_t prepAll() const { return prepTLo() + tTotal(); }
 };
 
 // workspace carve; identical arithmetic in forward and backward so saved activations are found again
@@ -97,7 +114,7 @@ struct Workspace {
     th_a = th_b = h = t = prm = th_st = th_sp = act = dth_a = dth_b = dh = dt = du = dprm = dctx_all = 0;
     if (!training) {
       th_a = take(R * L.D); th_b = take(R * L.D);
-      h = take(R * L.H); t = take(R * L.H); prm = take(R * L.dPmax());
+      h = take(R * L.H); t = take(R * L.H); prm = take(R * L.ldPmax());
     } else {
       th_st = take((int64_t)(L.T + 1) * al32(R * L.D));
       th_sp = take((int64_t)L.T * al32(R * L.D));
@@ -107,12 +124,12 @@ struct Workspace {
         take((int64_t)(L.Bk + 1) * al32(R * L.H));  // h_0..h_Bk
         take((int64_t)L.Bk * al32(R * L.H));        // t_b (pre-relu output of linear 0)
         take((int64_t)L.Bk * al32(R * L.H));        // u_b (pre-gate output of linear 1)
-        take(R * L.dP(i));                    // spline params
+        take(R * L.ldP(i));                   // spline params (padded rows)
         act_layer_sz[i] = o - act_layer_off[i];
       }
       dth_a = take(R * L.D); dth_b = take(R * L.D);
       dh = take(R * L.H); dt = take(R * L.H); du = take(R * L.H);
-      dprm = take(R * L.dPmax());
+      dprm = take(R * L.ldPmax());
       dctx_all = take(Rc * L.Nctx);
     }
     total = o;

@@ -32,6 +32,7 @@ struct RqsArgs {
   int32_t* status;      // optional
   int64_t R;
   int D, d_tr, parity, rows;
+  int ldp;              // row stride of params in floats (>= d_tr*P; padded to a multiple of 4 by the engine)
   RqsConsts c;
   const float* luM;     // optional [D, D]
   const float* luPre;   // optional [D] added before the matvec
@@ -105,7 +106,7 @@ __device__ __forceinline__ void load_tile(const RqsArgs& a, const RqsSmem& s, in
 template <bool INVERSE, int KT>
 __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int row_floats = a.d_tr * a.c.P;
+  const int row_floats = a.ldp;
   const int tile_floats = a.rows * row_floats;
   const bool lu = a.luM != nullptr;
   RqsSmem s = carve(smem_raw, tile_floats, a.rows, a.D, a.d_tr, lu);
@@ -146,13 +147,14 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
       int f = 2 * j + a.parity;
       float x = rowbuf[row * D + f];
       float y, lad; int bin; bool nd = false;
+      float* pe = P + row * row_floats + j * a.c.P;
       if (KT > 0) {
         constexpr int KK = KT > 0 ? KT : 2;
-        if (INVERSE) rqs_inverse_elem_t<KK>(P + (size_t)e * (3 * KK - 1), a.c, x, y, lad, bin, nd);
-        else rqs_forward_elem_t<KK>(P + (size_t)e * (3 * KK - 1), a.c, x, y, lad, bin);
+        if (INVERSE) rqs_inverse_elem_t<KK>(pe, a.c, x, y, lad, bin, nd);
+        else rqs_forward_elem_t<KK>(pe, a.c, x, y, lad, bin);
       } else {
-        if (INVERSE) rqs_inverse_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin, nd);
-        else rqs_forward_elem(P + (size_t)e * a.c.P, a.c, x, y, lad, bin);
+        if (INVERSE) rqs_inverse_elem(pe, a.c, x, y, lad, bin, nd);
+        else rqs_forward_elem(pe, a.c, x, y, lad, bin);
       }
       rowbuf[row * D + f] = y;
       s.ladbuf[e] = lad;
@@ -207,13 +209,14 @@ struct RqsBwdArgs {
   float* d_theta_in;         // [R, D]
   int64_t R;
   int D, d_tr, parity, rows;
+  int ldp;                   // row stride of params / d_params in floats
   RqsConsts c;
 };
 
 template <int KT>
 __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int row_floats = a.d_tr * a.c.P;
+  const int row_floats = a.ldp;
   const int tile_floats = a.rows * row_floats;
   float* stage[RQS_STAGES];
   {
@@ -261,17 +264,17 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
       int row = e / d_tr, j = e - row * d_tr;
       int f = 2 * j + a.parity;
       int64_t gr = r0 + row;
+      float* pe = P + row * row_floats + j * a.c.P;
       float x = a.theta_in[gr * D + f];
       float gy = a.d_theta_out[gr * D + f];
       float gl = a.d_logdet[gr];
-      float* p = P + (size_t)e * a.c.P;
       // in place: every parameter is read before its gradient overwrites it
       float gx;
       if (KT > 0) {
         constexpr int KK = KT > 0 ? KT : 2;
-        gx = rqs_backward_elem_t<KK>(P + (size_t)e * (3 * KK - 1), a.c, x, gy, gl);
+        gx = rqs_backward_elem_t<KK>(pe, a.c, x, gy, gl);
       } else {
-        gx = rqs_backward_elem(p, a.c, x, gy, gl);
+        gx = rqs_backward_elem(pe, a.c, x, gy, gl);
       }
       a.d_theta_in[gr * D + f] = gx;
     }
@@ -338,7 +341,7 @@ static int pick_threads(int rows, int d_tr) {
 int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                      float* theta_out, float* theta_sp, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status,
                      const float* luM, const float* luPre, float pre_sign, const float* luPost,
-                     const float* lu_logdet, cudaStream_t stream) {
+                     const float* lu_logdet, int ldp, cudaStream_t stream) {
   if (R <= 0) return 0;
   if (cfg->K < 2 || cfg->K > 64 || cfg->D < 2 || cfg->D > 64) return FP_E_BADARG;
   RqsArgs a{};
@@ -348,7 +351,9 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
   a.d_tr = (a.parity == 0) ? (cfg->D + 1) / 2 : cfg->D / 2;
   a.c = make_rqs_consts(cfg);
   a.luM = luM; a.luPre = luPre; a.luPost = luPost; a.lu_logdet = lu_logdet; a.pre_sign = pre_sign;
-  int row_floats = a.d_tr * a.c.P;
+  if (ldp > 0 && ldp < a.d_tr * a.c.P) return FP_E_BADARG;
+  a.ldp = ldp > 0 ? ldp : a.d_tr * a.c.P;
+  int row_floats = a.ldp;
   a.rows = pick_rows(row_floats, a.d_tr);
   int threads = pick_threads(a.rows, a.d_tr);
   size_t smem = rqs_smem_bytes(a.rows * row_floats, a.rows, a.D, a.d_tr, luM != nullptr);
@@ -368,7 +373,7 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
   int64_t ntiles = (R + a.rows - 1) / a.rows;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
   // algorithmic bytes: params + theta in + theta out (transformed features) + logdet
-  ProfScope ps(inverse ? TAG_RQS_INV : TAG_RQS_FWD, 4.0 * (double)R * ((double)row_floats + 2.0 * a.d_tr + 1.0), stream);
+  ProfScope ps(inverse ? TAG_RQS_INV : TAG_RQS_FWD, 4.0 * (double)R * ((double)(a.d_tr * a.c.P) + 2.0 * a.d_tr + 1.0), stream);
   kern<<<grid, threads, smem, stream>>>(a);
   FP_LAUNCH_CHECK();
   return 0;
@@ -376,7 +381,7 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
 
 int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                         const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
-                        int64_t R, cudaStream_t stream) {
+                        int64_t R, int ldp, cudaStream_t stream) {
   if (R <= 0) return 0;
   if (cfg->K < 2 || cfg->K > 64 || cfg->D < 2 || cfg->D > 64) return FP_E_BADARG;
   RqsBwdArgs a{};
@@ -385,7 +390,9 @@ int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta
   a.D = cfg->D; a.parity = parity & 1;
   a.d_tr = (a.parity == 0) ? (cfg->D + 1) / 2 : cfg->D / 2;
   a.c = make_rqs_consts(cfg);
-  int row_floats = a.d_tr * a.c.P;
+  if (ldp > 0 && ldp < a.d_tr * a.c.P) return FP_E_BADARG;
+  a.ldp = ldp > 0 ? ldp : a.d_tr * a.c.P;
+  int row_floats = a.ldp;
   a.rows = pick_rows(row_floats, a.d_tr);
   int threads = pick_threads(a.rows, a.d_tr);
   size_t smem = (size_t)RQS_STAGES * a.rows * row_floats * 4 + 8 + RQS_STAGES * 8 + 16;
@@ -402,7 +409,7 @@ int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta
   if (occ < 1) occ = 1;
   int64_t ntiles = (R + a.rows - 1) / a.rows;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
-  ProfScope ps(TAG_RQS_BWD, 4.0 * (double)R * (2.0 * row_floats + 3.0 * a.d_tr + 1.0), stream);
+  ProfScope ps(TAG_RQS_BWD, 4.0 * (double)R * (2.0 * (a.d_tr * a.c.P) + 3.0 * a.d_tr + 1.0), stream);
   kern<<<grid, threads, smem, stream>>>(a);
   FP_LAUNCH_CHECK();
   return 0;
@@ -415,19 +422,19 @@ extern "C" {
 int fp_rqs_forward(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
                    float* theta_out, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status, void* stream) {
   return fp::launch_rqs_apply(false, cfg, parity, theta_in, params, theta_out, nullptr, logdet, bin_idx, R, status,
-                              nullptr, nullptr, 1.f, nullptr, nullptr, (cudaStream_t)stream);
+                              nullptr, nullptr, 1.f, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 int fp_rqs_inverse(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
                    float* theta_out, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status, void* stream) {
   return fp::launch_rqs_apply(true, cfg, parity, theta_in, params, theta_out, nullptr, logdet, bin_idx, R, status,
-                              nullptr, nullptr, 1.f, nullptr, nullptr, (cudaStream_t)stream);
+                              nullptr, nullptr, 1.f, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 int fp_rqs_backward(const fp_nsf_config* cfg, int32_t parity, const float* theta_in, const float* params,
                     const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
                     int64_t R, void* stream) {
-  return fp::launch_rqs_backward(cfg, parity, theta_in, params, d_theta_out, d_logdet, d_params, d_theta_in, R,
+  return fp::launch_rqs_backward(cfg, parity, theta_in, params, d_theta_out, d_logdet, d_params, d_theta_in, R, 0,
                                  (cudaStream_t)stream);
 }
 

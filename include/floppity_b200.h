@@ -124,6 +124,11 @@ typedef struct fp_gemm_args {
   int32_t split_k;
 } fp_gemm_args;
 int fp_gemm(const fp_gemm_args* args, void* stream);
+/* Same contract on the tcgen05 tensor cores with the fp32-accurate 3xTF32 split (A split in-kernel, B_hi/B_lo
+ * pre-split with fp_split_tf32).  Supports K-major A and B with 16-byte-aligned rows; returns FP_E_NOTREADY for
+ * anything else (the caller then uses fp_gemm).  Set FLOPPITY_TC=0 to disable the tensor-core path. */
+int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, void* stream);
+int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 
 /* ---- whole-flow entry points --------------------------------------------------------------- */
 /* Derive per-step constants from the parameters (W = L*U, L, U, sum log diag U). */

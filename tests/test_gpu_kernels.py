@@ -214,6 +214,82 @@ def test_gemm_fused_epilogues():
     assert (got - A @ torch.relu(B).t()).abs().max() < 1e-4
 
 
+def _gemm_tc(A, B, M, N, K, flags=0, **aux):
+    """fp_gemm_tc with K-major A [M,K] and B [N,K]; returns None when the kernel declines the shape."""
+    args = _lib.GemmArgs()
+    keep = []
+
+    def dev(t):
+        t = t.cuda().contiguous()
+        keep.append(t)
+        return t
+    Ad, Bd = dev(A), dev(B)
+    Bh, Bl = torch.empty_like(Bd), torch.empty_like(Bd)
+    _lib.check(_lib.lib().fp_split_tf32(_lib.ptr(Bd), _lib.ptr(Bh), _lib.ptr(Bl), Bd.numel(), _lib.stream()), "split")
+    assert torch.equal((Bh + Bl).cpu(), B) and (Bh.view(torch.int32) & 0x1FFF).abs().max().item() == 0
+    C = aux.pop("C", None)
+    Cd = dev(C) if C is not None else torch.zeros(M, N, device="cuda")
+    args.A, args.lda, args.a_kmajor = Ad.data_ptr(), Ad.shape[1], 1
+    args.B, args.ldb, args.b_kmajor = Bd.data_ptr(), Bd.shape[1], 1
+    args.C, args.ldc, args.M, args.N, args.K, args.flags, args.split_k = Cd.data_ptr(), N, M, N, K, flags, 1
+    out = {}
+    for name, ld in (("bias", None), ("G", "ldg"), ("Rsd", "ldr"), ("U", "ldu"), ("Msk", "ldm")):
+        if name in aux:
+            t = dev(aux[name])
+            setattr(args, name, t.data_ptr())
+            if ld:
+                setattr(args, ld, t.shape[1])
+            out[name] = t
+    args.ctx_div = aux.get("ctx_div", 1)
+    rc = _lib.lib().fp_gemm_tc(ctypes.byref(args), _lib.ptr(Bh), _lib.ptr(Bl), _lib.stream())
+    if rc == -3:
+        return None, None
+    _lib.check(rc, "gemm_tc")
+    torch.cuda.synchronize()
+    return Cd.cpu(), {k: v.cpu() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 128), (300, 128, 128), (1000, 292, 128), (4096, 3840, 500),
+                                   (257, 128, 20), (5, 8, 4), (40960, 128, 128), (777, 705 + 3, 512)])
+def test_tcgen05_gemm_is_fp32_accurate(M, N, K):
+    """3xTF32 on tcgen05 must be as close to the fp64 product as a plain fp32 GEMM is (NOT tf32/bf16-grade)."""
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    want = A.double() @ B.double().t()
+    got, _ = _gemm_tc(A, B, M, N, K)
+    assert got is not None, "tcgen05 path declined a supported shape"
+    err = (got.double() - want).abs().max().item()
+    fp32_err = ((A @ B.t()).double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err < max(4 * fp32_err, 3e-6 * scale), (err, fp32_err, scale)
+    tf32_grade = 5e-4 * scale
+    assert err < tf32_grade / 20
+
+
+def test_tcgen05_gemm_epilogues_and_fallback():
+    g = torch.Generator().manual_seed(9)
+    M, N, K, atoms = 384, 128, 128, 4
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.2
+    bias, G = torch.randn(N, generator=g), torch.randn(M // atoms, 3 * N, generator=g)
+    Rsd, Msk = torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)
+    rows = torch.arange(M) // atoms
+    lin = torch.relu(A) @ B.t() + bias
+    got, aux = _gemm_tc(A, B, M, N, K, flags=_lib.G_RELU_A | _lib.G_BIAS | _lib.G_GLU_RES, bias=bias, G=G, Rsd=Rsd,
+                        U=torch.zeros(M, N), ctx_div=atoms)
+    want = Rsd + lin * torch.sigmoid(G[rows][:, :N])
+    assert (got - want).abs().max() < 1e-4 and (aux["U"] - lin).abs().max() < 1e-4
+    got, _ = _gemm_tc(A, B, M, N, K, flags=_lib.G_RELU_A | _lib.G_BIAS, bias=bias)
+    assert (got - lin).abs().max() < 1e-4
+    got, _ = _gemm_tc(A, B, M, N, K, flags=_lib.G_ADD_CTX, G=G, ctx_div=atoms)
+    assert (got - (A @ B.t() + G[rows][:, :N])).abs().max() < 1e-4
+    C0 = torch.randn(M, N, generator=g)
+    got, _ = _gemm_tc(A, B, M, N, K, flags=_lib.G_RELUMASK | _lib.G_ACCUM, Msk=Msk, C=C0.clone())
+    assert (got - (C0 + (A @ B.t()) * (Msk > 0))).abs().max() < 1e-4
+    # rows that are not 16-byte aligned cannot be TMA sources: the kernel must decline, not misbehave
+    got, _ = _gemm_tc(torch.randn(64, 50, generator=g), torch.randn(64, 50, generator=g), 64, 64, 50)
+    assert got is None
+
+
 def test_atomic_loss_and_choices():
     lib = _lib.lib()
     B, A, D = 257, 10, 6

@@ -90,12 +90,42 @@ def gemm():
     return out
 
 
+def gemm_tc():
+    L = _lib.lib()
+    out = []
+    shapes = [("ctx_fwd_c2", 4096, 3840, 500), ("blk_fwd_c2", 40960, 128, 128), ("final_fwd_c2", 40960, 292, 128),
+              ("first_fwd_c2", 40960, 128, 20), ("ctx_fwd_c3", 4096, 38400, 2000), ("blk_fwd_c3", 4096, 512, 512),
+              ("blk_fwd_c3_big", 65536, 512, 512)]
+    for name, M, N, K in shapes:
+        A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+        Bh, Bl = torch.empty_like(B), torch.empty_like(B)
+        L.fp_split_tf32(B.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), B.numel(), _lib.stream())
+        C = torch.zeros(M, N, device="cuda")
+        a = _lib.GemmArgs()
+        a.A, a.lda, a.a_kmajor = A.data_ptr(), K, 1
+        a.B, a.ldb, a.b_kmajor = B.data_ptr(), K, 1
+        a.C, a.ldc, a.M, a.N, a.K, a.flags, a.split_k = C.data_ptr(), N, M, N, K, 0, 1
+        s = _lib.stream()
+        rc = L.fp_gemm_tc(ctypes.byref(a), Bh.data_ptr(), Bl.data_ptr(), s)
+        if rc != 0:
+            print(name, "declined", rc)
+            continue
+        ms = timeit(lambda: L.fp_gemm_tc(ctypes.byref(a), Bh.data_ptr(), Bl.data_ptr(), s))
+        tf = 2.0 * M * N * K / ms / 1e9
+        out.append(dict(kernel="gemm_tcgen05_3xtf32", shape=name, M=M, N=N, K=K, ms=round(ms, 4), tflops_fp32_equiv=round(tf, 2),
+                        tf32_tflops=round(3 * tf, 2), frac_bf16_burst=round(tf / PK["bf16_tflops"], 4)))
+        print(out[-1], flush=True)
+    return out
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rqs", "gemm"]
+    which = sys.argv[1:] or ["rqs", "gemm", "tc"]
     res = []
     if "rqs" in which:
         res += rqs()
     if "gemm" in which:
         res += gemm()
+    if "tc" in which:
+        res += gemm_tc()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "kbench.json"), "w"), indent=1)
