@@ -20,6 +20,7 @@ namespace fp {
 // from the other translation units
 int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int drop_width, cudaStream_t stream);
 int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, cudaStream_t stream);   // gemm_tc.cu
+int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream);
 int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
 int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params, float* t_hi, float* t_lo, cudaStream_t stream);
 bool tc_enabled();
@@ -85,6 +86,10 @@ static int wgrad(const float* dOut, int64_t ldo, int n_out, const float* act, in
   g.B = act; g.ldb = lda; g.b_kmajor = 0;    // logical B'[k_in, R], element (k, r) at act[r*lda + k]
   g.C = dW; g.ldc = ldw; g.M = n_out; g.N = k_in; g.K = R;
   g.flags = FP_G_ATOMIC | flags_extra;
+  if (drop_p == 0.f) {
+    int r = launch_gemm_tc_tn(&g, s);
+    if (r != FP_E_NOTREADY) return r;
+  }
   g.split_k = pick_split(n_out, k_in, R);
   return launch_gemm(&g, drop_p, seed, drop_width, s);
 }

@@ -116,9 +116,24 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(const void* smem_tile) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand tile (contraction index is the slow one): [mn group of 32 floats][k rows][128 B].
+// For 32-bit element types the only MN-major layout the tensor core accepts is SWIZZLE_128B_BASE32B: atoms of
+// 4 k-rows x 128 B with the swizzle acting on 32-byte chunks (CUTLASS Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>);
+// TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// LBO = stride between 32-float MN groups, SBO = stride between 4-row k groups (512 B)
+__device__ __forceinline__ uint64_t make_mnmajor_desc(const void* smem_tile, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // Persistent kernel: CTA c processes output tiles c, c+grid, ... ; every role walks the same tile sequence.
@@ -311,6 +326,201 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TN variant (weight gradients): C[M,N] += sum_r A[r,M] * B[r,N], both operands row-major over the batch index r
+// (MN-major for the tensor core), contraction over r split across CTAs, partial tiles added with vector atomics.
+// Work item = (output tile, k-split); every CTA walks items blockIdx.x, +gridDim.x, ...  Both operands are raw fp32
+// activations, so the splitter warps split BOTH (relu prologue on B for the relu'd activation operand).
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, fp_gemm_args g,
+             int nkb_total, int nsplit, int vec_all) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  float* Cs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES);
+  uint64_t* ready = full_raw + TC_STAGES;
+  uint64_t* empty = ready + TC_STAGES;
+  uint64_t* acc_full = empty + TC_STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (g.N + TC_BN - 1) / TC_BN;
+  const int tiles_m = (int)((g.M + TC_BM - 1) / TC_BM);
+  const int64_t n_items = (int64_t)tiles_m * tiles_n * nsplit;
+  const int kb_per_split = (nkb_total + nsplit - 1) / nsplit;
+  constexpr uint32_t GROUP_BYTES = TC_BK * 128;   // one 32-float MN group: TC_BK k-rows x 128 B
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto item_decode = [&](int64_t w, int& m0, int& n0, int& kb0, int& kb1) {
+    const int sp = (int)(w % nsplit);
+    const int64_t t = w / nsplit;
+    m0 = (int)(t / tiles_n) * TC_BM;
+    n0 = (int)(t % tiles_n) * TC_BN;
+    kb0 = sp * kb_per_split;
+    kb1 = min(nkb_total, kb0 + kb_per_split);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (it / TC_STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* sb = smem + s * TC_STAGE_BYTES;
+          mbar_expect_tx(&full_raw[s], 2 * TC_TILE_BYTES);
+#pragma unroll
+          for (int gidx = 0; gidx < 4; ++gidx) {     // four 32-float MN groups per operand
+            tma_load_2d(sb + gidx * GROUP_BYTES, &mapA, m0 + gidx * 32, kb * TC_BK, &full_raw[s]);
+            tma_load_2d(sb + 2 * TC_TILE_BYTES + gidx * GROUP_BYTES, &mapB, n0 + gidx * 32, kb * TC_BK, &full_raw[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN, 1, 1);
+      uint32_t it = 0, tile_it = 0;
+      for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
+        int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
+        if (kb0 >= kb1) { --tile_it; continue; }
+        const int buf = tile_it & 1;
+        const uint32_t aph = (tile_it >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], aph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256);
+        const uint32_t t_x = t_hh + 128;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (it / TC_STAGES) & 1u;
+          mbar_wait(&ready[s], ph);
+          tcgen05_fence_after();
+          uint8_t* sb = smem + s * TC_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint32_t koff = (uint32_t)k * 1024u;             // 8 k-rows of 128 B
+            const uint64_t a_hi = make_mnmajor_desc(sb + koff, GROUP_BYTES);
+            const uint64_t a_lo = make_mnmajor_desc(sb + TC_TILE_BYTES + koff, GROUP_BYTES);
+            const uint64_t b_hi = make_mnmajor_desc(sb + 2 * TC_TILE_BYTES + koff, GROUP_BYTES);
+            const uint64_t b_lo = make_mnmajor_desc(sb + 3 * TC_TILE_BYTES + koff, GROUP_BYTES);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            umma_tf32(t_hh, a_hi, b_hi, idesc, acc);
+            umma_tf32(t_x, a_lo, b_hi, idesc, acc);
+            umma_tf32(t_x, a_hi, b_lo, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp < 6) {
+    // splitter: raw A at +0 -> hi in place, lo at +TILE; raw B at +2*TILE -> hi in place, lo at +3*TILE
+    const int tid_s = threadIdx.x - 64;
+    const bool relu_b = (g.flags & FP_G_RELU_B) != 0;
+    uint32_t it = 0;
+    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+      int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1u;
+        mbar_wait(&full_raw[s], ph);
+        float4* A = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
+        float4* Alo = A + TC_TILE_BYTES / 16;
+        float4* B = A + 2 * (TC_TILE_BYTES / 16);
+        float4* Blo = A + 3 * (TC_TILE_BYTES / 16);
+#pragma unroll
+        for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
+          const int idx = tid_s + i * 128;
+          float4 v = A[idx];
+          float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+          A[idx] = h;
+          Alo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          float4 u = B[idx];
+          if (relu_b) { u.x = fmaxf(u.x, 0.f); u.y = fmaxf(u.y, 0.f); u.z = fmaxf(u.z, 0.f); u.w = fmaxf(u.w, 0.f); }
+          float4 hb = make_float4(tf32_round(u.x), tf32_round(u.y), tf32_round(u.z), tf32_round(u.w));
+          B[idx] = hb;
+          Blo[idx] = make_float4(u.x - hb.x, u.y - hb.y, u.z - hb.z, u.w - hb.w);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+      }
+    }
+  } else {
+    // epilogue: accumulate the partial tile into C with atomics
+    const int ew = warp - 6;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int tid_h = (ew & 3) * 32 + lane;
+    const int row = q * 32 + lane;
+    float* slab = Cs + half * (TC_BM * TC_CS_LD);
+    uint32_t tile_it = 0;
+    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
+      int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
+      if (kb0 >= kb1) { --tile_it; continue; }
+      const int buf = tile_it & 1;
+      const uint32_t aph = (tile_it >> 1) & 1u;
+      mbar_wait(&acc_full[buf], aph);
+      tcgen05_fence_after();
+      const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16], x[16];
+        tmem_ld_32x16(t_hh + (uint32_t)c0, v);
+        tmem_ld_32x16(t_hh + 128u + (uint32_t)c0, x);
+        if (c0 + 16 == 64) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(&slab[row * TC_CS_LD + j]) =
+              make_float4(v[j] + x[j], v[j + 1] + x[j + 1], v[j + 2] + x[j + 2], v[j + 3] + x[j + 3]);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (tid_h >> 2) + 32 * i;
+          const int c = (tid_h & 3) * 4;
+          const int64_t m = m0 + r;
+          const int n = n0 + half * 64 + c0 + c;
+          if (m < g.M && n < g.N) {
+            const float4 o = *reinterpret_cast<const float4*>(&slab[r * TC_CS_LD + c]);
+            float* cp = g.C + m * g.ldc + n;
+            if (vec_all && n + 3 < g.N) {
+              atomicAdd(reinterpret_cast<float4*>(cp), o);
+            } else {
+              const float e[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n + j < g.N) atomicAdd(cp + j, e[j]);
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- weight / activation split helper: hi = tf32(x), lo = x - hi ---------------------------------------
 __global__ void k_split_tf32(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -375,24 +585,26 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 row-major [rows, cols] with leading dimension ld (floats); box = 32 cols x 128 rows, SWIZZLE_128B
-static bool get_tensor_map(const float* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
-  typedef std::tuple<const void*, int64_t, int64_t, int64_t> Key;
+// 2-D fp32 row-major [rows, cols] with leading dimension ld (floats); box = 32 cols x box_rows rows, SWIZZLE_128B
+static bool get_tensor_map(const float* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out, int box_rows = TC_BM,
+                           bool atom32 = false) {
+  typedef std::tuple<const void*, int64_t, int64_t, int64_t, int, bool> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
-  Key key(base, rows, cols, ld);
+  Key key(base, rows, cols, ld, box_rows, atom32);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   if (cache.size() > 4096) cache.clear();
@@ -453,6 +665,37 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   return 0;
 }
 
+// wgrad: C[M,N] += A[R,M]^T * B[R,N]   (a_kmajor == 0, b_kmajor == 0, FP_G_ATOMIC [, FP_G_RELU_B])
+int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
+  if (!tc_enabled()) return FP_E_NOTREADY;
+  if (a->a_kmajor || a->b_kmajor) return FP_E_NOTREADY;
+  if ((a->flags & ~(FP_G_ATOMIC | FP_G_RELU_B)) != 0 || !(a->flags & FP_G_ATOMIC)) return FP_E_NOTREADY;
+  if ((a->lda & 3) || (a->ldb & 3)) return FP_E_NOTREADY;
+  if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return FP_E_NOTREADY;
+  if (a->M < 1 || a->N < 1 || a->K < 1 || a->M > 65536) return FP_E_NOTREADY;
+  CUtensorMap mA, mB;
+  if (!get_tensor_map(a->A, a->K, a->M, a->lda, &mA, TC_BK, true)) return FP_E_NOTREADY;   // [R rows, M cols]
+  if (!get_tensor_map(a->B, a->K, a->N, a->ldb, &mB, TC_BK, true)) return FP_E_NOTREADY;   // [R rows, N cols]
+  static bool attr_set = false;
+  if (!attr_set) {
+    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int nkb = (int)((a->K + TC_BK - 1) / TC_BK);
+  const int64_t tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + TC_BN - 1) / TC_BN);
+  int nsplit = (int)std::max<int64_t>(1, (num_sms() + tiles - 1) / tiles);
+  nsplit = std::min(nsplit, std::max(1, nkb / 4));         // at least 4 k-blocks (128 batch rows) per split
+  nsplit = std::max(nsplit, (nkb + TC_KCHUNK_BLOCKS - 1) / TC_KCHUNK_BLOCKS);   // bound the truncating accumulation chain
+  const int kbps = (nkb + nsplit - 1) / nsplit;
+  nsplit = (nkb + kbps - 1) / kbps;                        // no empty splits
+  const int grid = (int)std::min<int64_t>(tiles * nsplit, num_sms());
+  int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
+  ProfScope ps(TAG_GEMM_TC, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream);
+  k_gemm_tc_tn<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mA, mB, *a, nkb, nsplit, vec_all);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream) {
   if (n <= 0) return 0;
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 8 * num_sms());
@@ -484,6 +727,11 @@ extern "C" {
 int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, void* stream) {
   if (!args) return FP_E_BADARG;
   return fp::launch_gemm_tc(args, B_hi, B_lo, (cudaStream_t)stream);
+}
+// Weight-gradient form on the tensor cores: C[M,N] += A[K,M]^T * B[K,N] (a_kmajor = b_kmajor = 0, FP_G_ATOMIC).
+int fp_gemm_tc_tn(const fp_gemm_args* args, void* stream) {
+  if (!args) return FP_E_BADARG;
+  return fp::launch_gemm_tc_tn(args, (cudaStream_t)stream);
 }
 int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
   return fp::launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);

@@ -129,6 +129,9 @@ int fp_gemm(const fp_gemm_args* args, void* stream);
  * anything else (the caller then uses fp_gemm).  Set FLOPPITY_TC=0 to disable the tensor-core path. */
 int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, void* stream);
 int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* weight-gradient form: C[M,N] += A[K,M]^T * B[K,N] (a_kmajor = b_kmajor = 0, flags = FP_G_ATOMIC [| FP_G_RELU_B]);
+ * contraction split across CTAs, partial tiles added with vector atomics.  FP_E_NOTREADY -> use fp_gemm. */
+int fp_gemm_tc_tn(const fp_gemm_args* args, void* stream);
 
 /* ---- whole-flow entry points --------------------------------------------------------------- */
 /* Derive per-step constants from the parameters (W = L*U, L, U, sum log diag U). */

@@ -290,6 +290,30 @@ def test_tcgen05_gemm_epilogues_and_fallback():
     assert got is None
 
 
+@pytest.mark.parametrize("R,M,N", [(4096, 128, 128), (40960, 128, 128), (1000, 292, 128), (4096, 3840, 500), (777, 20, 20),
+                                   (5000, 128, 20), (333, 705 + 3, 512)])
+def test_tcgen05_wgrad_form(R, M, N):
+    """C[M,N] += A[R,M]^T relu(B)[R,N] on the tensor cores (split over the batch, vector atomics), fp32-accurate."""
+    g = torch.Generator().manual_seed(R + M + N)
+    A, B = torch.randn(R, M, generator=g), torch.randn(R, N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    want = C0.double() + A.double().t() @ torch.relu(B).double()
+    Ad, Bd, Cd = A.cuda(), B.cuda(), C0.clone().cuda()
+    args = _lib.GemmArgs()
+    args.A, args.lda, args.a_kmajor = Ad.data_ptr(), M, 0
+    args.B, args.ldb, args.b_kmajor = Bd.data_ptr(), N, 0
+    args.C, args.ldc, args.M, args.N, args.K = Cd.data_ptr(), N, M, N, R
+    args.flags, args.split_k = _lib.G_ATOMIC | _lib.G_RELU_B, 1
+    rc = _lib.lib().fp_gemm_tc_tn(ctypes.byref(args), _lib.stream())
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    err = (Cd.cpu().double() - want).abs().max().item()
+    fp32_err = ((C0 + A.t() @ torch.relu(B)).double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    # tensor-core accumulation truncates: allow 1e-5 of the largest output (tf32-grade would be ~5e-4)
+    assert err < max(4 * fp32_err, 1e-5 * scale), (err, fp32_err, scale)
+
+
 def test_atomic_loss_and_choices():
     lib = _lib.lib()
     B, A, D = 257, 10, 6

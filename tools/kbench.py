@@ -96,7 +96,10 @@ def gemm_tc():
     shapes = [("ctx_fwd_c2", 4096, 3840, 500), ("blk_fwd_c2", 40960, 128, 128), ("final_fwd_c2", 40960, 292, 128),
               ("first_fwd_c2", 40960, 128, 20), ("ctx_fwd_c3", 4096, 38400, 2000), ("blk_fwd_c3", 4096, 512, 512),
               ("blk_fwd_c3_big", 65536, 512, 512)]
+    only = os.environ.get("KB_SHAPE")
     for name, M, N, K in shapes:
+        if only and name != only:
+            continue
         A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
         Bh, Bl = torch.empty_like(B), torch.empty_like(B)
         L.fp_split_tf32(B.data_ptr(), Bh.data_ptr(), Bl.data_ptr(), B.numel(), _lib.stream())
