@@ -72,6 +72,7 @@ SIGNATURES = {
     "fp_gemm_tc": (c_int32, [POINTER(GemmArgs), _P, _P, _P]),
     "fp_split_tf32": (c_int32, [_P, _P, _P, c_int64, _P]),
     "fp_gemm_tc_tn": (c_int32, [POINTER(GemmArgs), _P]),
+    "fp_tc_set_trace": (c_int32, [_P]),
     "fp_nsf_prepare": (c_int32, [_CFG, _P, _P, _P]),
     "fp_nsf_logprob_forward": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, _P, _P, c_int32,
                                          c_uint64, _P, _P]),

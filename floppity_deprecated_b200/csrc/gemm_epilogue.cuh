@@ -19,16 +19,31 @@ __device__ __forceinline__ float drop_scale(uint64_t seed, int64_t row, int col,
   return u < p ? 0.f : 1.f / (1.f - p);
 }
 
+// explicit global-space reductions (a plain atomicAdd on a kernel-argument pointer compiles to the generic-address
+// path with shared-memory CAS loops)
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f32x4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 struct GemmDrop {
   float p;          // 0 => off
   uint64_t seed;
   int width;        // columns of the dropped activation matrix
 };
 
+// context row of flow row m (only evaluated when an epilogue needs it; 32-bit division -- M < 2^31 is enforced at launch)
+__device__ __forceinline__ int64_t ctx_row(const fp_gemm_args& g, int64_t m) {
+  if (g.ctx_div <= 0) return 0;
+  if (g.ctx_div == 1) return m;
+  return (int64_t)((uint32_t)m / (uint32_t)g.ctx_div);
+}
+
 // v = accumulator of element (m, n); applies the flags of fp_gemm_args and stores.
-__device__ __forceinline__ void gemm_epilogue_store(const fp_gemm_args& g, const GemmDrop& drop, int64_t m, int n, float v) {
-  const int fl = g.flags;
-  const int64_t cr = (g.ctx_div > 0) ? (m / g.ctx_div) : 0;
+__device__ __forceinline__ void gemm_epilogue_store(const fp_gemm_args& g, int fl, const GemmDrop& drop, int64_t m, int n, float v) {
+  const int64_t cr = (fl & (FP_G_ADD_CTX | FP_G_GLU_RES)) ? ctx_row(g, m) : 0;
   if (fl & FP_G_BIAS) v += g.bias[n];
   if (fl & FP_G_ADD_CTX) v += g.G[cr * g.ldg + n];
   if (fl & FP_G_GLU_RES) {
@@ -42,35 +57,55 @@ __device__ __forceinline__ void gemm_epilogue_store(const fp_gemm_args& g, const
     if (drop.p > 0.f && (fl & FP_G_DROPMASK)) v *= drop_scale(drop.seed, m, n, drop.width, drop.p);
   }
   float* c = g.C + m * g.ldc + n;
-  if (fl & FP_G_ATOMIC) atomicAdd(c, v);
+  if (fl & FP_G_ATOMIC) red_add_f32(c, v);
   else if (fl & FP_G_ACCUM) *c += v;
   else *c = v;
 }
 
+// Register snapshot of the epilogue operands (the tensor-core kernels take it once per role: reading the kernel
+// argument struct through a reference costs a generic-address load per access).
+struct EpiArgs {
+  float* C; int64_t ldc; int64_t M; int N;
+  const float* bias;
+  const float* G; int64_t ldg; int ctx_div;
+  const float* Rsd; int64_t ldr;
+  float* U; int64_t ldu;
+  const float* Msk; int64_t ldm;
+};
+__device__ __forceinline__ EpiArgs make_epi(const fp_gemm_args& g) {
+  EpiArgs e;
+  e.C = g.C; e.ldc = g.ldc; e.M = g.M; e.N = g.N; e.bias = g.bias; e.G = g.G; e.ldg = g.ldg; e.ctx_div = g.ctx_div;
+  e.Rsd = g.Rsd; e.ldr = g.ldr; e.U = g.U; e.ldu = g.ldu; e.Msk = g.Msk; e.ldm = g.ldm;
+  return e;
+}
+__device__ __forceinline__ int64_t ctx_row(const EpiArgs& g, int64_t m) {
+  if (g.ctx_div <= 0) return 0;
+  if (g.ctx_div == 1) return m;
+  return (int64_t)((uint32_t)m / (uint32_t)g.ctx_div);
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
 // Four consecutive columns n..n+3 of row m at once.  Caller guarantees n % 4 == 0, n + 3 < N and that every
 // pointer used by the flags is 16-byte aligned with a leading dimension that is a multiple of 4 (no dropout).
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ void gemm_epilogue_store4(const fp_gemm_args& g, int64_t m, int n, float4 v) {
-  const int fl = g.flags;
-  const int64_t cr = (g.ctx_div > 0) ? (m / g.ctx_div) : 0;
+__device__ __forceinline__ void gemm_epilogue_store4(const EpiArgs& g, int fl, int64_t m, int n, float4 v) {
+  const int64_t cr = (fl & (FP_G_ADD_CTX | FP_G_GLU_RES)) ? ctx_row(g, m) : 0;
   if (fl & FP_G_BIAS) {
-    const float4 b = *reinterpret_cast<const float4*>(g.bias + n);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n));
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   if (fl & FP_G_ADD_CTX) {
-    const float4 c = *reinterpret_cast<const float4*>(g.G + cr * g.ldg + n);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(g.G + cr * g.ldg + n));
     v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
   }
   if (fl & FP_G_GLU_RES) {
-    const float4 gt = *reinterpret_cast<const float4*>(g.G + cr * g.ldg + n);
+    const float4 gt = __ldg(reinterpret_cast<const float4*>(g.G + cr * g.ldg + n));
     const float4 rs = *reinterpret_cast<const float4*>(g.Rsd + m * g.ldr + n);
     if (g.U) *reinterpret_cast<float4*>(g.U + m * g.ldu + n) = v;
     v.x = rs.x + v.x * sigmoid_acc(gt.x); v.y = rs.y + v.y * sigmoid_acc(gt.y);
     v.z = rs.z + v.z * sigmoid_acc(gt.z); v.w = rs.w + v.w * sigmoid_acc(gt.w);
   }
   if (fl & FP_G_RELUMASK) {
-    const float4 mk = *reinterpret_cast<const float4*>(g.Msk + m * g.ldm + n);
+    const float4 mk = __ldg(reinterpret_cast<const float4*>(g.Msk + m * g.ldm + n));
     v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
     v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
   }
@@ -80,6 +115,26 @@ __device__ __forceinline__ void gemm_epilogue_store4(const fp_gemm_args& g, int6
     v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
   }
   *reinterpret_cast<float4*>(c) = v;
+}
+
+// out-of-line scalar fallback for up to 4 consecutive columns (ragged N, unaligned rows): keeps the hot vector
+// path of the tensor-core epilogues small.  Same semantics as gemm_epilogue_store without dropout / atomics.
+static __device__ __noinline__ void gemm_epilogue_store_slow(EpiArgs g, int fl, int64_t m, int n, float4 v4, int cnt) {
+  const float e[4] = {v4.x, v4.y, v4.z, v4.w};
+  const int64_t cr = (fl & (FP_G_ADD_CTX | FP_G_GLU_RES)) ? ctx_row(g, m) : 0;
+  for (int j = 0; j < cnt; ++j) {
+    const int nn = n + j;
+    float v = e[j];
+    if (fl & FP_G_BIAS) v += g.bias[nn];
+    if (fl & FP_G_ADD_CTX) v += g.G[cr * g.ldg + nn];
+    if (fl & FP_G_GLU_RES) {
+      if (g.U) g.U[m * g.ldu + nn] = v;
+      v = g.Rsd[m * g.ldr + nn] + v * sigmoid_acc(g.G[cr * g.ldg + nn]);
+    }
+    if (fl & FP_G_RELUMASK) v = g.Msk[m * g.ldm + nn] > 0.f ? v : 0.f;
+    float* c = g.C + m * g.ldc + nn;
+    if (fl & FP_G_ACCUM) *c += v; else *c = v;
+  }
 }
 
 }  // namespace fp

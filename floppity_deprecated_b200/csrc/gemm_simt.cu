@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k
     for (int j = 0; j < TN; ++j) {
       int n = n0 + tx * TN + j;
       if (n >= g.N) continue;
-      gemm_epilogue_store(g, drop, m, n, acc[i][j]);
+      gemm_epilogue_store(g, g.flags, drop, m, n, acc[i][j]);
     }
   }
 }
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k
 int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int drop_width, cudaStream_t stream) {
   if (a->M <= 0 || a->N <= 0) return 0;
   if (a->K <= 0) return FP_E_BADARG;
+  if (a->M > 2147483647LL && (a->flags & (FP_G_ADD_CTX | FP_G_GLU_RES))) return FP_E_TOOLARGE;
   int split = a->split_k > 0 ? a->split_k : 1;
   if (split > 1 && !(a->flags & FP_G_ATOMIC)) return FP_E_BADARG;
   int64_t kc = (a->K + split - 1) / split;

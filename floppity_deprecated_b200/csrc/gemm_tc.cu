@@ -136,6 +136,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+#define FP_TRACE(slot) do { if (trace && blockIdx.x == 0) trace[(slot)] = clock64(); } while (0)
+
 // Persistent kernel: CTA c processes output tiles c, c+grid, ... ; every role walks the same tile sequence.
 // TMEM (512 columns) holds two accumulator sets {hi*hi, cross terms} so the epilogue of tile i overlaps the
 // mainloop of tile i+1.  Tensor-core accumulation truncates, so its error grows with the number of chained
@@ -144,10 +146,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 
 // (only for the plain/bias epilogue, which is all the long-K context projection needs).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
-             const __grid_constant__ CUtensorMap mapBl, fp_gemm_args g, int nkb_total, int nchunks, int vec_all) {
+             const __grid_constant__ CUtensorMap mapBl, const fp_gemm_args g, int nkb_total, int nchunks, int vec_all,
+             long long* trace) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-  float* Cs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  const uint32_t smem_a = smem_u32(smem);                                  // shared-space address of the ring
+  const uint32_t cs_a = smem_a + TC_STAGES * TC_STAGE_BYTES;              // epilogue staging slabs
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES);
   uint64_t* ready = full_raw + TC_STAGES;
   uint64_t* empty = ready + TC_STAGES;
@@ -167,6 +171,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   auto tile_n0 = [&](int64_t st) -> int { return (int)(m_fast ? (st / tiles_m) : (st % tiles_n)) * TC_BN; };
 
   if (threadIdx.x == 0) {
+    FP_TRACE(500);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_fence_init();
@@ -179,6 +184,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) FP_TRACE(501);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -196,6 +202,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           tma_load_2d(sb, &mapA, kb * TC_BK, (int)m0, &full_raw[s]);
           tma_load_2d(sb + 2 * TC_TILE_BYTES, &mapBh, kb * TC_BK, n0, &full_raw[s]);
           tma_load_2d(sb + 3 * TC_TILE_BYTES, &mapBl, kb * TC_BK, n0, &full_raw[s]);
+          if (it < 60) FP_TRACE(it * 8 + 0);
         }
       }
     }
@@ -219,6 +226,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const uint32_t ph = (it / TC_STAGES) & 1u;
             mbar_wait(&ready[s], ph);
             tcgen05_fence_after();
+            if (it < 60) FP_TRACE(it * 8 + 3);
             uint8_t* sb = smem + s * TC_STAGE_BYTES;
             const uint64_t a_hi = make_kmajor_desc(sb), a_lo = make_kmajor_desc(sb + TC_TILE_BYTES);
             const uint64_t b_hi = make_kmajor_desc(sb + 2 * TC_TILE_BYTES), b_lo = make_kmajor_desc(sb + 3 * TC_TILE_BYTES);
@@ -231,6 +239,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               umma_tf32(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
             }
             umma_commit(&empty[s]);        // ring slot reusable once these MMAs have read it
+            if (it < 60) FP_TRACE(it * 8 + 4);
           }
           umma_commit(&acc_full[buf]);     // this accumulator set is complete
         }
@@ -246,20 +255,23 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1u;
         mbar_wait(&full_raw[s], ph);
-        float4* A = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
-        float4* Alo = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+        if (tid_s == 0 && it < 60) FP_TRACE(it * 8 + 1);
+        const uint32_t aA = smem_a + (uint32_t)(s * TC_STAGE_BYTES) + (uint32_t)tid_s * 16u;
+        float4 v[TC_TILE_BYTES / 16 / 128];
+#pragma unroll
+        for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) v[i] = lds128(aA + (uint32_t)i * 2048u);
 #pragma unroll
         for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
-          const int idx = tid_s + i * 128;
-          float4 v = A[idx];
-          if (relu_a) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-          A[idx] = h;
-          Alo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          float4 w = v[i];
+          if (relu_a) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+          const float4 h = make_float4(tf32_round(w.x), tf32_round(w.y), tf32_round(w.z), tf32_round(w.w));
+          sts128(aA + (uint32_t)i * 2048u, h);
+          sts128(aA + (uint32_t)i * 2048u + TC_TILE_BYTES, make_float4(w.x - h.x, w.y - h.y, w.z - h.z, w.w - h.w));
         }
         fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[s]);
+        if (tid_s == 0 && it < 60) FP_TRACE(it * 8 + 2);
       }
     }
   } else {
@@ -269,8 +281,9 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int half = ew >> 2;                  // column half
     const int tid_h = (ew & 3) * 32 + lane;    // 0..127 within the half
     const int row = q * 32 + lane;             // accumulator row held by this thread
-    float* slab = Cs + half * (TC_BM * TC_CS_LD);
-    const GemmDrop nodrop{0.f, 0, 0};
+    const uint32_t slab = cs_a + (uint32_t)(half * (TC_BM * TC_CS_LD * 4));
+    const EpiArgs ea = make_epi(g);
+    const int g_flags = g.flags;
     uint32_t tile_it = 0;
     for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
       const int64_t m0 = tile_m0(st);
@@ -278,16 +291,18 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       for (int kc = 0; kc < nchunks; ++kc, ++tile_it) {
         const int buf = tile_it & 1;
         const uint32_t aph = (tile_it >> 1) & 1u;
-        fp_gemm_args ge = g;                     // later K chunks add onto the stored partial result
-        if (kc > 0) ge.flags = (g.flags & ~FP_G_BIAS) | FP_G_ACCUM;
+        // later K chunks add onto the stored partial result
+        const int fl_e = (kc > 0) ? ((g_flags & ~FP_G_BIAS) | FP_G_ACCUM) : g_flags;
         mbar_wait(&acc_full[buf], aph);
         tcgen05_fence_after();
+        if (threadIdx.x == 192 && tile_it < 8) FP_TRACE(480 + tile_it * 2);
         const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 16) {
           float v[16], x[16];
           tmem_ld_32x16(t_hh + (uint32_t)c0, v);
           tmem_ld_32x16(t_hh + 128u + (uint32_t)c0, x);
+          if (threadIdx.x == 192 && tile_it < 4) FP_TRACE(400 + tile_it * 16 + (c0 >> 4) * 4 + 0);
           if (c0 + 16 == 64) {                   // all TMEM reads of this set are done: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
@@ -295,34 +310,33 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           }
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(&slab[row * TC_CS_LD + j]) =
-                make_float4(v[j] + x[j], v[j + 1] + x[j + 1], v[j + 2] + x[j + 2], v[j + 3] + x[j + 3]);
+            sts128(slab + (uint32_t)((row * TC_CS_LD + j) * 4),
+                   make_float4(v[j] + x[j], v[j + 1] + x[j + 1], v[j + 2] + x[j + 2], v[j + 3] + x[j + 3]));
           asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          if (threadIdx.x == 192 && tile_it < 4) FP_TRACE(400 + tile_it * 16 + (c0 >> 4) * 4 + 1);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = (tid_h >> 2) + 32 * i;
             const int c = (tid_h & 3) * 4;
             const int64_t m = m0 + r;
             const int n = n0 + half * 64 + c0 + c;
-            if (m < ge.M && n < ge.N) {
-              const float4 o = *reinterpret_cast<const float4*>(&slab[r * TC_CS_LD + c]);
-              if (vec_all && n + 3 < ge.N) {
-                gemm_epilogue_store4(ge, m, n, o);
-              } else {
-                const float e[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (n + j < ge.N) gemm_epilogue_store(ge, nodrop, m, n + j, e[j]);
-              }
+            if (m < ea.M && n < ea.N) {
+              const float4 o = lds128(slab + (uint32_t)((r * TC_CS_LD + c) * 4));
+              if (vec_all && n + 3 < ea.N) gemm_epilogue_store4(ea, fl_e, m, n, o);
+              else gemm_epilogue_store_slow(ea, fl_e, m, n, o, min(4, ea.N - n));
             }
           }
+          if (threadIdx.x == 192 && tile_it < 4) FP_TRACE(400 + tile_it * 16 + (c0 >> 4) * 4 + 2);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          if (threadIdx.x == 192 && tile_it < 4) FP_TRACE(400 + tile_it * 16 + (c0 >> 4) * 4 + 3);
         }
+        if (threadIdx.x == 192 && tile_it < 8) FP_TRACE(480 + tile_it * 2 + 1);
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FP_TRACE(502);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -332,11 +346,12 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 // Work item = (output tile, k-split); every CTA walks items blockIdx.x, +gridDim.x, ...  Both operands are raw fp32
 // activations, so the splitter warps split BOTH (relu prologue on B for the relu'd activation operand).
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, fp_gemm_args g,
+k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const fp_gemm_args g,
              int nkb_total, int nsplit, int vec_all) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-  float* Cs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  const uint32_t smem_a = smem_u32(smem);                                  // shared-space address of the ring
+  const uint32_t cs_a = smem_a + TC_STAGES * TC_STAGE_BYTES;              // epilogue staging slabs
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES);
   uint64_t* ready = full_raw + TC_STAGES;
   uint64_t* empty = ready + TC_STAGES;
@@ -439,22 +454,19 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1u;
         mbar_wait(&full_raw[s], ph);
-        float4* A = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
-        float4* Alo = A + TC_TILE_BYTES / 16;
-        float4* B = A + 2 * (TC_TILE_BYTES / 16);
-        float4* Blo = A + 3 * (TC_TILE_BYTES / 16);
-#pragma unroll
+        const uint32_t aA = smem_a + (uint32_t)(s * TC_STAGE_BYTES) + (uint32_t)tid_s * 16u;
+#pragma unroll 4
         for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
-          const int idx = tid_s + i * 128;
-          float4 v = A[idx];
-          float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-          A[idx] = h;
-          Alo[idx] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-          float4 u = B[idx];
+          const uint32_t off = aA + (uint32_t)i * 2048u;
+          const float4 v = lds128(off);
+          float4 u = lds128(off + 2 * TC_TILE_BYTES);
+          const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+          sts128(off, h);
+          sts128(off + TC_TILE_BYTES, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
           if (relu_b) { u.x = fmaxf(u.x, 0.f); u.y = fmaxf(u.y, 0.f); u.z = fmaxf(u.z, 0.f); u.w = fmaxf(u.w, 0.f); }
-          float4 hb = make_float4(tf32_round(u.x), tf32_round(u.y), tf32_round(u.z), tf32_round(u.w));
-          B[idx] = hb;
-          Blo[idx] = make_float4(u.x - hb.x, u.y - hb.y, u.z - hb.z, u.w - hb.w);
+          const float4 hb = make_float4(tf32_round(u.x), tf32_round(u.y), tf32_round(u.z), tf32_round(u.w));
+          sts128(off + 2 * TC_TILE_BYTES, hb);
+          sts128(off + 3 * TC_TILE_BYTES, make_float4(u.x - hb.x, u.y - hb.y, u.z - hb.z, u.w - hb.w));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -468,7 +480,8 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int half = ew >> 2;
     const int tid_h = (ew & 3) * 32 + lane;
     const int row = q * 32 + lane;
-    float* slab = Cs + half * (TC_BM * TC_CS_LD);
+    const uint32_t slab = cs_a + (uint32_t)(half * (TC_BM * TC_CS_LD * 4));
+    float* const gC = g.C; const int64_t g_ldc = g.ldc, gM = g.M; const int gN = g.N;
     uint32_t tile_it = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
       int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
@@ -490,8 +503,8 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(&slab[row * TC_CS_LD + j]) =
-              make_float4(v[j] + x[j], v[j + 1] + x[j + 1], v[j + 2] + x[j + 2], v[j + 3] + x[j + 3]);
+          sts128(slab + (uint32_t)((row * TC_CS_LD + j) * 4),
+                 make_float4(v[j] + x[j], v[j + 1] + x[j + 1], v[j + 2] + x[j + 2], v[j + 3] + x[j + 3]));
         asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -499,16 +512,14 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const int c = (tid_h & 3) * 4;
           const int64_t m = m0 + r;
           const int n = n0 + half * 64 + c0 + c;
-          if (m < g.M && n < g.N) {
-            const float4 o = *reinterpret_cast<const float4*>(&slab[r * TC_CS_LD + c]);
-            float* cp = g.C + m * g.ldc + n;
-            if (vec_all && n + 3 < g.N) {
-              atomicAdd(reinterpret_cast<float4*>(cp), o);
+          if (m < gM && n < gN) {
+            const float4 o = lds128(slab + (uint32_t)((r * TC_CS_LD + c) * 4));
+            float* cp = gC + m * g_ldc + n;
+            if (vec_all && n + 3 < gN) {
+              red_add_f32x4(cp, o);
             } else {
               const float e[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (n + j < g.N) atomicAdd(cp + j, e[j]);
+              for (int j = 0; j < 4 && n + j < gN; ++j) red_add_f32(cp + j, e[j]);
             }
           }
         }
@@ -613,6 +624,8 @@ static bool get_tensor_map(const float* base, int64_t rows, int64_t cols, int64_
   return true;
 }
 
+static long long* g_tc_trace = nullptr;
+
 bool tc_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -660,7 +673,7 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   if ((a->flags & (FP_G_ADD_CTX | FP_G_GLU_RES)) && !ok(a->G, a->ldg)) vec_all = 0;
   if ((a->flags & FP_G_GLU_RES) && (!ok(a->Rsd, a->ldr) || !ok(a->U, a->ldu))) vec_all = 0;
   if ((a->flags & FP_G_RELUMASK) && !ok(a->Msk, a->ldm)) vec_all = 0;
-  k_gemm_tc_nt<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mA, mBh, mBl, *a, nkb, nchunks, vec_all);
+  k_gemm_tc_nt<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace);
   FP_LAUNCH_CHECK();
   return 0;
 }
@@ -722,6 +735,8 @@ int launch_gemm_ctx(const fp_gemm_args* a, cudaStream_t stream) { return launch_
 }  // namespace fp
 
 extern "C" {
+// debug: device buffer of >= 512 int64 receiving SM-clock stamps of CTA 0 (NULL switches tracing off)
+int fp_tc_set_trace(void* buf) { fp::g_tc_trace = reinterpret_cast<long long*>(buf); return 0; }
 // Standalone entry: C = pro(A) * B^T (+ epilogue) on the tensor cores; B_hi/B_lo from fp_split_tf32.
 // Returns FP_E_NOTREADY when the shape/stride/flags are not supported by the tcgen05 kernel.
 int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, void* stream) {

@@ -132,6 +132,8 @@ int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream)
 /* weight-gradient form: C[M,N] += A[K,M]^T * B[K,N] (a_kmajor = b_kmajor = 0, flags = FP_G_ATOMIC [| FP_G_RELU_B]);
  * contraction split across CTAs, partial tiles added with vector atomics.  FP_E_NOTREADY -> use fp_gemm. */
 int fp_gemm_tc_tn(const fp_gemm_args* args, void* stream);
+/* debug: SM-clock stamps of CTA 0 of the next fp_gemm_tc launches into a device int64[512] buffer (NULL = off) */
+int fp_tc_set_trace(void* buf);
 
 /* ---- whole-flow entry points --------------------------------------------------------------- */
 /* Derive per-step constants from the parameters (W = L*U, L, U, sum log diag U). */
