@@ -137,4 +137,45 @@ static __device__ __noinline__ void gemm_epilogue_store_slow(EpiArgs g, int fl, 
   }
 }
 
+// ---- compile-time-specialised vector epilogue (tensor-core kernels) ---------------------------------------
+// The run-time-flag version above costs ~200 issue slots per float4 (every operand's address arithmetic is
+// emitted and predicated off); the skinny conditioner GEMMs are epilogue-bound, so the tcgen05 kernels are
+// instantiated per flag combination (FL >= 0) and only fall back to run-time flags (FL < 0) for unusual ones.
+constexpr int FP_EPI_MASK = FP_G_BIAS | FP_G_ADD_CTX | FP_G_GLU_RES | FP_G_RELUMASK | FP_G_ACCUM;
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// The auxiliary operands of one float4 (context/gate row, residual, relu mask, old C).  They are loaded for a
+// whole batch of rows BEFORE any of the batch is stored: a load placed after a store that may alias it cannot be
+// hoisted by the compiler, and one exposed L2/HBM round trip per row made the fused epilogues latency-bound.
+struct EpiAux { float4 ctx, rsd, msk, old; };
+
+template <int FL>
+__device__ __forceinline__ void epi_load4(const EpiArgs& g, int fl_rt, int64_t m, int64_t cr, int n, EpiAux& a) {
+  const int fl = (FL >= 0) ? FL : fl_rt;
+  if (fl & (FP_G_ADD_CTX | FP_G_GLU_RES)) a.ctx = __ldg(reinterpret_cast<const float4*>(g.G + cr * g.ldg + n));
+  if (fl & FP_G_GLU_RES) a.rsd = *reinterpret_cast<const float4*>(g.Rsd + m * g.ldr + n);   // may alias C (in-place eval)
+  if (fl & FP_G_RELUMASK) a.msk = __ldg(reinterpret_cast<const float4*>(g.Msk + m * g.ldm + n));
+  if (fl & FP_G_ACCUM) a.old = *reinterpret_cast<const float4*>(g.C + m * g.ldc + n);
+}
+
+// v = four consecutive accumulator columns n..n+3 of row m; bias4 = bias[n..n+3] (hoisted by the caller)
+template <int FL>
+__device__ __forceinline__ void epi_store4(const EpiArgs& g, int fl_rt, int64_t m, int n, float4 bias4, const EpiAux& a, float4 v) {
+  const int fl = (FL >= 0) ? FL : fl_rt;
+  if (fl & FP_G_BIAS) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+  if (fl & FP_G_ADD_CTX) { v.x += a.ctx.x; v.y += a.ctx.y; v.z += a.ctx.z; v.w += a.ctx.w; }
+  if (fl & FP_G_GLU_RES) {
+    if (g.U) *reinterpret_cast<float4*>(g.U + m * g.ldu + n) = v;
+    v.x = fmaf(v.x, sigmoid_fast(a.ctx.x), a.rsd.x); v.y = fmaf(v.y, sigmoid_fast(a.ctx.y), a.rsd.y);
+    v.z = fmaf(v.z, sigmoid_fast(a.ctx.z), a.rsd.z); v.w = fmaf(v.w, sigmoid_fast(a.ctx.w), a.rsd.w);
+  }
+  if (fl & FP_G_RELUMASK) {
+    v.x = a.msk.x > 0.f ? v.x : 0.f; v.y = a.msk.y > 0.f ? v.y : 0.f;
+    v.z = a.msk.z > 0.f ? v.z : 0.f; v.w = a.msk.w > 0.f ? v.w : 0.f;
+  }
+  if (fl & FP_G_ACCUM) { v.x += a.old.x; v.y += a.old.y; v.z += a.old.z; v.w += a.old.w; }
+  *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = v;
+}
+
 }  // namespace fp

@@ -36,8 +36,8 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB: 128 rows x 128 B
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // A(raw->hi), A_lo, B_hi, B_lo
 constexpr int TC_THREADS = 448;                           // producer, MMA, 4 splitter warps, 8 epilogue warps
-constexpr int TC_CS_LD = 20;                              // epilogue staging slab: 128 rows x 16 columns (+4 pad)
-constexpr int TC_CS_BYTES = 2 * TC_BM * TC_CS_LD * 4;     // one slab per column half
+constexpr int TC_CS_WARP_BYTES = 32 * 128;                // epilogue staging: per warp 32 rows x 32 columns, XOR-swizzled
+constexpr int TC_CS_BYTES = 8 * TC_CS_WARP_BYTES;         // eight epilogue warps
 constexpr int TC_KCHUNK_BLOCKS = 32;                      // K chunk (1024) for long contractions, see k_gemm_tc_nt
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -99,6 +99,29 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two 32x16 loads in flight, one wait (the wait is part of the same asm statement, so no consumer can be
+// scheduled between the loads and the wait)
+__device__ __forceinline__ void tmem_ld_2x16(uint32_t ta, uint32_t tb, float (&v)[16], float (&x)[16]) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+        "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r[i]); x[i] = __uint_as_float(q[i]); }
+}
+// asynchronous L2 prefetch of a contiguous global range (16-byte aligned address, size a multiple of 16)
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -144,6 +167,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 
 // MMAs: the big hi*hi products get their own accumulator (the small cross terms cannot disturb it) and
 // contractions longer than 1024 are cut into chunks whose partial sums are added in fp32 by the epilogue
 // (only for the plain/bias epilogue, which is all the long-K context projection needs).
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
              const __grid_constant__ CUtensorMap mapBl, const fp_gemm_args g, int nkb_total, int nchunks, int vec_all,
@@ -249,11 +273,25 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // ===== splitter warps 2..5: relu prologue + TF32 hi/lo split of the A tile, in place =====
     const int tid_s = threadIdx.x - 64;       // 0..127
     const bool relu_a = (g.flags & FP_G_RELU_A) != 0;
+    const int pf_fl = (EPI >= 0 ? EPI : g.flags) & (FP_G_GLU_RES | FP_G_RELUMASK | FP_G_ACCUM);
+    const int pf_bytes = (pf_fl && vec_all) ? TC_BN * 4 : 0;
     uint32_t it = 0;
     for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
       for (int kb = 0; kb < nkb_total; ++kb, ++it) {
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1u;
+        if (kb == 0 && pf_bytes > 0) {
+          // L2 prefetch of this tile's epilogue operands (one row segment per thread): the epilogue warps can only
+          // keep ~4 KB of loads in flight each, so at HBM latency they are bandwidth-starved; at L2-hit latency not
+          const int64_t m = tile_m0(st) + tid_s;
+          const int n0p = tile_n0(st);
+          const uint32_t nb = (uint32_t)min(pf_bytes, (g.N - n0p) * 4) & ~15u;
+          if (m < g.M && nb > 0) {
+            if (pf_fl & FP_G_GLU_RES) l2_prefetch(g.Rsd + m * g.ldr + n0p, nb);
+            if (pf_fl & FP_G_RELUMASK) l2_prefetch(g.Msk + m * g.ldm + n0p, nb);
+            if (pf_fl & FP_G_ACCUM) l2_prefetch(g.C + m * g.ldc + n0p, nb);
+          }
+        }
         mbar_wait(&full_raw[s], ph);
         if (tid_s == 0 && it < 60) FP_TRACE(it * 8 + 1);
         const uint32_t aA = smem_a + (uint32_t)(s * TC_STAGE_BYTES) + (uint32_t)tid_s * 16u;
@@ -276,59 +314,113 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
   } else {
     // ===== epilogue warps 6..13: two warps per TMEM lane quarter, each owning one 64-column half =====
+    // Warp-private: 32 accumulator rows x 32 columns go TMEM -> registers -> this warp's XOR-swizzled slab ->
+    // registers with 8 lanes per row, so every global access of a warp covers four full 128-byte row segments.
     const int ew = warp - 6;                   // 0..7
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int half = ew >> 2;                  // column half
-    const int tid_h = (ew & 3) * 32 + lane;    // 0..127 within the half
-    const int row = q * 32 + lane;             // accumulator row held by this thread
-    const uint32_t slab = cs_a + (uint32_t)(half * (TC_BM * TC_CS_LD * 4));
+    const uint32_t slabw = cs_a + (uint32_t)ew * (uint32_t)TC_CS_WARP_BYTES;
+    const uint32_t st_base = slabw + (uint32_t)lane * 128u;
+    const uint32_t sw_st = (uint32_t)(lane & 7);
+    const int rsub = lane >> 3;                // row within a group of four
+    const int cch = lane & 7;                  // float4 chunk within the 32-column slab row
     const EpiArgs ea = make_epi(g);
-    const int g_flags = g.flags;
+    const int fl_rt = g.flags & FP_EPI_MASK;
+    const bool need_ctx = ((EPI >= 0 ? EPI : fl_rt) & (FP_G_ADD_CTX | FP_G_GLU_RES)) != 0;
+    const uint32_t cdiv = ea.ctx_div <= 0 ? 0xFFFFFFFFu : (uint32_t)ea.ctx_div;
+    // slab read addresses of this thread's eight rows (row r = rsub + 4 i, so r & 7 only depends on i & 1)
+    const uint32_t ld_even = slabw + (uint32_t)rsub * 128u + ((uint32_t)(cch ^ rsub) << 4);
+    const uint32_t ld_odd = slabw + (uint32_t)(rsub + 4) * 128u + ((uint32_t)(cch ^ (rsub + 4)) << 4);
     uint32_t tile_it = 0;
     for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
       const int64_t m0 = tile_m0(st);
       const int n0 = tile_n0(st);
+      const int64_t mrow = m0 + q * 32 + rsub;                              // first of this thread's 8 rows
+      const bool full = (m0 + TC_BM <= ea.M);
+      uint32_t cr8[8];                                                      // context rows of the 8 rows
+      if (need_ctx) {
+        uint32_t cr = (uint32_t)mrow / cdiv, rem = (uint32_t)mrow - cr * cdiv;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          cr8[i] = cr;
+          rem += 4u;
+          while (rem >= cdiv) { rem -= cdiv; ++cr; }
+        }
+      }
       for (int kc = 0; kc < nchunks; ++kc, ++tile_it) {
         const int buf = tile_it & 1;
         const uint32_t aph = (tile_it >> 1) & 1u;
-        // later K chunks add onto the stored partial result
-        const int fl_e = (kc > 0) ? ((g_flags & ~FP_G_BIAS) | FP_G_ACCUM) : g_flags;
         mbar_wait(&acc_full[buf], aph);
         tcgen05_fence_after();
         if (threadIdx.x == 192 && tile_it < 8) FP_TRACE(480 + tile_it * 2);
         const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          float v[16], x[16];
-          tmem_ld_32x16(t_hh + (uint32_t)c0, v);
-          tmem_ld_32x16(t_hh + 128u + (uint32_t)c0, x);
-          if (threadIdx.x == 192 && tile_it < 4) FP_TRACE(400 + tile_it * 16 + (c0 >> 4) * 4 + 0);
-          if (c0 + 16 == 64) {                   // all TMEM reads of this set are done: hand it back to the MMA warp
+        for (int chunk = 0; chunk < 2; ++chunk) {
+          const int n = n0 + half * 64 + chunk * 32 + cch * 4;
+          const bool vec = vec_all && (n + 3 < ea.N);
+          const bool fast = full && vec && kc == 0;
+          // the auxiliary operands of the first four rows are requested before the TMEM read-out
+          EpiAux aux[4];
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (fast) {
+            if ((EPI >= 0 ? EPI : fl_rt) & FP_G_BIAS) bias4 = __ldg(reinterpret_cast<const float4*>(ea.bias + n));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) epi_load4<EPI>(ea, fl_rt, mrow + 4 * i, need_ctx ? (int64_t)cr8[i] : 0, n, aux[i]);
+          }
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            float v[16], x[16];
+            const uint32_t tc = t_hh + (uint32_t)(chunk * 32 + p * 16);
+            tmem_ld_2x16(tc, tc + 128u, v, x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128(st_base + ((((uint32_t)(p * 4 + j)) ^ sw_st) << 4),
+                     make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
+                                 v[4 * j + 3] + x[4 * j + 3]));
+          }
+          if (chunk == 1) {                       // all TMEM reads of this set are done: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
+          __syncwarp();
+          if (fast) {
+            // straight-line code, four independent rows at a time (the epilogue warps are few, so instruction-level
+            // parallelism across rows is what hides the MUFU / shared / global latencies)
+            float4 o[4];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            sts128(slab + (uint32_t)((row * TC_CS_LD + j) * 4),
-                   make_float4(v[j] + x[j], v[j + 1] + x[j + 1], v[j + 2] + x[j + 2], v[j + 3] + x[j + 3]));
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-          if (threadIdx.x == 192 && tile_it < 4) FP_TRACE(400 + tile_it * 16 + (c0 >> 4) * 4 + 1);
+            for (int i = 0; i < 4; ++i) o[i] = lds128(((i & 1) ? ld_odd : ld_even) + (uint32_t)(i >> 1) * 1024u);
+            EpiAux aux2[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (tid_h >> 2) + 32 * i;
-            const int c = (tid_h & 3) * 4;
-            const int64_t m = m0 + r;
-            const int n = n0 + half * 64 + c0 + c;
-            if (m < ea.M && n < ea.N) {
-              const float4 o = lds128(slab + (uint32_t)((r * TC_CS_LD + c) * 4));
-              if (vec_all && n + 3 < ea.N) gemm_epilogue_store4(ea, fl_e, m, n, o);
-              else gemm_epilogue_store_slow(ea, fl_e, m, n, o, min(4, ea.N - n));
+            for (int i = 0; i < 4; ++i) epi_load4<EPI>(ea, fl_rt, mrow + 16 + 4 * i, need_ctx ? (int64_t)cr8[4 + i] : 0, n, aux2[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) epi_store4<EPI>(ea, fl_rt, mrow + 4 * i, n, bias4, aux[i], o[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = lds128(((i & 1) ? ld_odd : ld_even) + (uint32_t)(2 + (i >> 1)) * 1024u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) epi_store4<EPI>(ea, fl_rt, mrow + 16 + 4 * i, n, bias4, aux2[i], o[i]);
+          } else if (n < ea.N) {
+            // ragged tiles, unaligned operands and the later chunks of a long contraction: run-time flags, row by row
+            const int fl_s = (EPI >= 0 ? EPI : fl_rt);
+            const int fl_g = (kc == 0) ? fl_s : ((fl_s & ~FP_G_BIAS) | FP_G_ACCUM);
+            if (vec && (fl_g & FP_G_BIAS)) bias4 = __ldg(reinterpret_cast<const float4*>(ea.bias + n));
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const int r = rsub + 4 * i;
+              const int64_t m = mrow + 4 * i;
+              if (m < ea.M) {
+                const float4 o = lds128(slabw + (uint32_t)r * 128u + ((uint32_t)(cch ^ (r & 7)) << 4));
+                if (vec) {
+                  EpiAux a1;
+                  epi_load4<-1>(ea, fl_g, m, need_ctx ? (int64_t)cr8[i] : 0, n, a1);
+                  epi_store4<-1>(ea, fl_g, m, n, bias4, a1, o);
+                } else {
+                  gemm_epilogue_store_slow(ea, fl_g, m, n, o, min(4, ea.N - n));
+                }
+              }
             }
           }
-          if (threadIdx.x == 192 && tile_it < 4) FP_TRACE(400 + tile_it * 16 + (c0 >> 4) * 4 + 2);
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-          if (threadIdx.x == 192 && tile_it < 4) FP_TRACE(400 + tile_it * 16 + (c0 >> 4) * 4 + 3);
+          __syncwarp();
         }
         if (threadIdx.x == 192 && tile_it < 8) FP_TRACE(480 + tile_it * 2 + 1);
       }
@@ -474,13 +566,15 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       }
     }
   } else {
-    // epilogue: accumulate the partial tile into C with atomics
+    // epilogue: accumulate the partial tile into C with vector reductions (warp-private staging, full 128-byte
+    // row segments per access -- same scheme as the NT kernel)
     const int ew = warp - 6;
     const int q = warp & 3;
     const int half = ew >> 2;
-    const int tid_h = (ew & 3) * 32 + lane;
-    const int row = q * 32 + lane;
-    const uint32_t slab = cs_a + (uint32_t)(half * (TC_BM * TC_CS_LD * 4));
+    const uint32_t slabw = cs_a + (uint32_t)ew * (uint32_t)TC_CS_WARP_BYTES;
+    const uint32_t st_base = slabw + (uint32_t)lane * 128u;
+    const uint32_t sw_st = (uint32_t)(lane & 7);
+    const int rsub = lane >> 3, cch = lane & 7;
     float* const gC = g.C; const int64_t g_ldc = g.ldc, gM = g.M; const int gN = g.N;
     uint32_t tile_it = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
@@ -492,38 +586,58 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       tcgen05_fence_after();
       const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        float v[16], x[16];
-        tmem_ld_32x16(t_hh + (uint32_t)c0, v);
-        tmem_ld_32x16(t_hh + 128u + (uint32_t)c0, x);
-        if (c0 + 16 == 64) {
+      for (int chunk = 0; chunk < 2; ++chunk) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          float v[16], x[16];
+          const uint32_t tc = t_hh + (uint32_t)(chunk * 32 + p * 16);
+          tmem_ld_2x16(tc, tc + 128u, v, x);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(st_base + ((((uint32_t)(p * 4 + j)) ^ sw_st) << 4),
+                   make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
+                               v[4 * j + 3] + x[4 * j + 3]));
+        }
+        if (chunk == 1) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        __syncwarp();
+        const int n = n0 + half * 64 + chunk * 32 + cch * 4;
+        const bool vec = vec_all && (n + 3 < gN);
+        const int64_t mrow = (int64_t)m0 + q * 32 + rsub;
+        if (vec && m0 + TC_BM <= gM) {            // full tile: straight-line, four rows in flight
+          float* cp = gC + mrow * g_ldc + n;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          sts128(slab + (uint32_t)((row * TC_CS_LD + j) * 4),
-                 make_float4(v[j] + x[j], v[j + 1] + x[j + 1], v[j + 2] + x[j + 2], v[j + 3] + x[j + 3]));
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+          for (int b = 0; b < 2; ++b) {
+            float4 o[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (tid_h >> 2) + 32 * i;
-          const int c = (tid_h & 3) * 4;
-          const int64_t m = m0 + r;
-          const int n = n0 + half * 64 + c0 + c;
-          if (m < gM && n < gN) {
-            const float4 o = lds128(slab + (uint32_t)((r * TC_CS_LD + c) * 4));
-            float* cp = gC + m * g_ldc + n;
-            if (vec_all && n + 3 < gN) {
-              red_add_f32x4(cp, o);
-            } else {
-              const float e[4] = {o.x, o.y, o.z, o.w};
-              for (int j = 0; j < 4 && n + j < gN; ++j) red_add_f32(cp + j, e[j]);
+            for (int i = 0; i < 4; ++i) {
+              const int r = rsub + 4 * (4 * b + i);
+              o[i] = lds128(slabw + (uint32_t)r * 128u + ((uint32_t)(cch ^ (r & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red_add_f32x4(cp + (int64_t)(4 * (4 * b + i)) * g_ldc, o[i]);
+          }
+        } else if (n < gN) {
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            const int r = rsub + 4 * i;
+            const int64_t m = mrow + 4 * i;
+            if (m < gM) {
+              const float4 o = lds128(slabw + (uint32_t)r * 128u + ((uint32_t)(cch ^ (r & 7)) << 4));
+              float* cp = gC + m * g_ldc + n;
+              if (vec) {
+                red_add_f32x4(cp, o);
+              } else {
+                const float e[4] = {o.x, o.y, o.z, o.w};
+                for (int j = 0; j < 4 && n + j < gN; ++j) red_add_f32(cp + j, e[j]);
+              }
             }
           }
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        __syncwarp();
       }
     }
   }
@@ -654,11 +768,6 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   if (!get_tensor_map(a->A, a->M, a->K, a->lda, &mA)) return FP_E_NOTREADY;
   if (!get_tensor_map(B_hi, a->N, a->K, a->ldb, &mBh)) return FP_E_NOTREADY;
   if (!get_tensor_map(B_lo, a->N, a->K, a->ldb, &mBl)) return FP_E_NOTREADY;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
   const int nkb = (int)((a->K + TC_BK - 1) / TC_BK);
   // long contractions are chunked (see the kernel comment); only the plain / bias epilogue can be accumulated
   const bool plain = (a->flags & ~(FP_G_RELU_A | FP_G_BIAS)) == 0;
@@ -673,7 +782,34 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   if ((a->flags & (FP_G_ADD_CTX | FP_G_GLU_RES)) && !ok(a->G, a->ldg)) vec_all = 0;
   if ((a->flags & FP_G_GLU_RES) && (!ok(a->Rsd, a->ldr) || !ok(a->U, a->ldu))) vec_all = 0;
   if ((a->flags & FP_G_RELUMASK) && !ok(a->Msk, a->ldm)) vec_all = 0;
-  k_gemm_tc_nt<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace);
+  // one instantiation per epilogue the engine uses (compile-time flags), run-time flags for anything else
+#define FP_TC_NT_CASE(E)                                                                                              \
+  case (E): {                                                                                                         \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E)>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    k_gemm_tc_nt<(E)><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace); \
+    break;                                                                                                            \
+  }
+  int epi = a->flags & FP_EPI_MASK;
+  switch (epi) {
+    case 0: case FP_G_BIAS: case FP_G_ADD_CTX: case FP_G_BIAS | FP_G_GLU_RES: case FP_G_RELUMASK:
+    case FP_G_RELUMASK | FP_G_ACCUM: case FP_G_ACCUM: break;
+    default: epi = -1;
+  }
+  switch (epi) {
+    FP_TC_NT_CASE(0)
+    FP_TC_NT_CASE(FP_G_BIAS)
+    FP_TC_NT_CASE(FP_G_ADD_CTX)
+    FP_TC_NT_CASE(FP_G_BIAS | FP_G_GLU_RES)
+    FP_TC_NT_CASE(FP_G_RELUMASK)
+    FP_TC_NT_CASE(FP_G_RELUMASK | FP_G_ACCUM)
+    FP_TC_NT_CASE(FP_G_ACCUM)
+    FP_TC_NT_CASE(-1)
+  }
+#undef FP_TC_NT_CASE
   FP_LAUNCH_CHECK();
   return 0;
 }

@@ -110,15 +110,43 @@ __global__ void k_ctx_reduce(const float* __restrict__ dh, float* __restrict__ d
 }
 
 // ---- column sums (bias gradients): out[n] += sum_m X[m, n] ----------------------------------------------
-__global__ void k_colsum(const float* __restrict__ X, int64_t ldx, int64_t M, int N, float* __restrict__ out,
-                         int rows_per_block) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t m0 = (int64_t)blockIdx.y * rows_per_block;
-  int64_t m1 = min(M, m0 + rows_per_block);
-  if (n >= N) return;
-  float acc = 0.f;
-  for (int64_t m = m0; m < m1; ++m) acc += X[m * ldx + n];
-  atomicAdd(&out[n], acc);
+// Block = 32 column lanes x 8 row lanes; a block covers 32*VEC columns x rows_per_block rows.  Each thread keeps
+// eight independent loads in flight (the old one-thread-per-column loop was a serial chain of dependent loads),
+// row lanes are combined through shared memory, one atomic per column per block.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ X, int64_t ldx, int64_t M, int N,
+                                                float* __restrict__ out, int rows_per_block) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + tx) * VEC;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t m1 = min(M, m0 + rows_per_block);
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  if (n < N) {
+#pragma unroll 8
+    for (int64_t m = m0 + ty; m < m1; m += 8) {
+      if (VEC == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(X + m * ldx + n));
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      } else {
+        acc[0] += __ldg(X + m * ldx + n);
+      }
+    }
+  }
+  __shared__ float red[8][32 * VEC + 1];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) red[ty][tx * VEC + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    const int nn = blockIdx.x * 32 * VEC + c;
+    if (nn < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += red[r][c];
+      atomicAdd(&out[nn], t);
+    }
+  }
 }
 
 // ---- sum reduction: out[0] += scale * sum(x) ----------------------------------------------------------------
@@ -435,12 +463,19 @@ int launch_ctx_reduce(const float* dh, float* dG, int64_t ldg, int64_t Rc, int A
 }
 int launch_colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, cudaStream_t s) {
   if (M <= 0 || N <= 0) return 0;
-  int rpb = 256;
+  // float4 columns when every row segment is 16-byte aligned and N is a multiple of 4
+  const bool vec = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 3) == 0) && ((N & 3) == 0);
+  const int cols = vec ? 128 : 32;
+  const int bx = (N + cols - 1) / cols;
+  // enough blocks for ~4 per SM, at least 64 rows each
+  int rpb = 64;
+  while ((M + rpb - 1) / rpb * bx > 8 * (int64_t)num_sms() && rpb < (1 << 20)) rpb *= 2;
   int64_t by = (M + rpb - 1) / rpb;
   while (by > 65535) { rpb *= 2; by = (M + rpb - 1) / rpb; }
-  dim3 grid((N + 127) / 128, (unsigned)by);
+  dim3 grid(bx, (unsigned)by);
   ProfScope ps(TAG_OTHER, 0.0, s);
-  k_colsum<<<grid, 128, 0, s>>>(X, ldx, M, N, out, rpb);
+  if (vec) k_colsum<4><<<grid, 256, 0, s>>>(X, ldx, M, N, out, rpb);
+  else k_colsum<1><<<grid, 256, 0, s>>>(X, ldx, M, N, out, rpb);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_sum(const float* x, int64_t n, float scale, float* out, cudaStream_t s) {
