@@ -40,6 +40,7 @@ def parse():
                          "the reference actually takes (force_first_round_loss=True, floppity.py:220)")
     ap.add_argument("--rows", type=int, default=16384, help="resident dataset rows per GPU")
     ap.add_argument("--ref-batch", type=int, default=256, help="bounded per-step sample for the CPU arm")
+    ap.add_argument("--graph", type=int, default=0, help="replay the optimiser step from a CUDA graph")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     return ap.parse_args()
@@ -194,7 +195,7 @@ def main():
     prior = fb.BoxUniform(-3 * torch.ones(cfg.D), 3 * torch.ones(cfg.D), device=dev)
     B, K, W = args.batch, args.steps, args.warmup
     atomic = args.loss == "atomic"
-    eng = _TrainEngine(net, prior, B, atomic, cfg.atoms, True, 5e-4, 5.0, use_graph=False)
+    eng = _TrainEngine(net, prior, B, atomic, cfg.atoms, True, 5e-4, 5.0, use_graph=bool(args.graph))
     theta_dev = theta.to(dev).contiguous()
     x_dev = net._standardize(x.to(dev))
     masks_dev = torch.zeros(args.rows, device=dev)
@@ -230,9 +231,12 @@ def main():
     n0 = L.fp_launch_count()
     ms = timed(step, K)
     launches = int(L.fp_launch_count() - n0)
+    if eng.graph is not None:            # replays do not pass through the launch counter: kernels per captured step x K
+        launches = eng.launches_per_step * K
     clk = clocks.stop()
     eng.check_status()
     value = world * B * K / (ms * 1e-3)
+    print(f"[bench] rank {rank}: {ms / K:.3f} ms/step, {value:.0f} pairs/s", file=sys.stderr, flush=True)
 
     # ---- e2e: host (pinned) batch -> H2D -> standardise -> step -> D2H loss, through the host-facing step call
     th_pin = [theta[b.cpu()].pin_memory() for b in batches[:4]]
@@ -256,8 +260,9 @@ def main():
     # ---- per-kernel-class CUDA-event timing inside a second pass over the same K steps
     out_extra = {}
     L.fp_prof_enable(1)
-    for i in range(K):
-        step(i)
+    for i in range(K):      # plain launches (a graph replay would bypass the per-launch event hooks)
+        eng.idx.copy_(batches[i % len(batches)])
+        eng._step_body(theta_dev, x_dev, masks_dev)
     import ctypes
     pms, pl, pw = (ctypes.c_double * 6)(), (ctypes.c_int64 * 6)(), (ctypes.c_double * 6)()
     _lib.check(L.fp_prof_collect(pms, pl, pw), "prof")

@@ -80,6 +80,7 @@ SIGNATURES = {
     "fp_nsf_finish_grads": (c_int32, [_CFG, _P, _P, _P, _P]),
     "fp_nsf_sample": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "fp_atom_choices": (c_int32, [_P, c_int64, c_int32, c_uint64, _P]),
+    "fp_atom_choices_step": (c_int32, [_P, c_int64, c_int32, c_uint64, _P, _P]),
     "fp_atom_gather": (c_int32, [_P, _P, _P, c_int64, c_int32, c_int32, _P]),
     "fp_atomic_loss": (c_int32, [_P, _P, _P, _P, _P, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "fp_grad_sumsq": (c_int32, [_P, c_int64, _P, _P]),

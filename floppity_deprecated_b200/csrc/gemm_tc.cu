@@ -122,6 +122,9 @@ __device__ __forceinline__ void tmem_ld_2x16(uint32_t ta, uint32_t tb, float (&v
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -183,6 +186,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+  pdl_launch_dependents();      // the next kernel in the stream may start its own prologue as SMs free up
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (g.N + TC_BN - 1) / TC_BN;
   const int64_t tiles_m = (g.M + TC_BM - 1) / TC_BM;
@@ -208,6 +212,9 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are only
+  // touched below this point
+  pdl_wait();
   if (threadIdx.x == 0) FP_TRACE(501);
 
   if (warp == 0) {
@@ -451,6 +458,7 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+  pdl_launch_dependents();      // the next kernel in the stream may start its own prologue as SMs free up
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (g.N + TC_BN - 1) / TC_BN;
   const int tiles_m = (int)((g.M + TC_BM - 1) / TC_BM);
@@ -470,6 +478,9 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are only
+  // touched below this point
+  pdl_wait();
 
   auto item_decode = [&](int64_t w, int& m0, int& n0, int& kb0, int& kb1) {
     const int sp = (int)(w % nsplit);
@@ -740,6 +751,26 @@ static bool get_tensor_map(const float* base, int64_t rows, int64_t cols, int64_
 
 static long long* g_tc_trace = nullptr;
 
+// Launch with programmatic stream serialisation: the kernel may begin (barrier init, TMEM allocation, tensor-map
+// prefetch) while the previous kernel in the stream drains; it calls griddepcontrol.wait before touching memory.
+// FLOPPITY_PDL=0 falls back to plain stream order.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, cudaStream_t stream, Args... args) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FLOPPITY_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 bool tc_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -790,7 +821,7 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
       FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E)>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    k_gemm_tc_nt<(E)><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace); \
+    FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E)>, grid, stream, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace));       \
     break;                                                                                                            \
   }
   int epi = a->flags & FP_EPI_MASK;
@@ -840,7 +871,7 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   const int grid = (int)std::min<int64_t>(tiles * nsplit, num_sms());
   int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
   ProfScope ps(TAG_GEMM_TC, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream);
-  k_gemm_tc_tn<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mA, mB, *a, nkb, nsplit, vec_all);
+  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, mA, mB, *a, nkb, nsplit, vec_all));
   FP_LAUNCH_CHECK();
   return 0;
 }

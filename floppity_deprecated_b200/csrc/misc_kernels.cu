@@ -292,9 +292,10 @@ __device__ __forceinline__ uint64_t splitmix(uint64_t& s) {
   return z ^ (z >> 31);
 }
 // Floyd's algorithm: A-1 distinct values from {0..B-2}, then skip self.
-__global__ void k_atom_choices(int32_t* __restrict__ choices, int64_t B, int A, uint64_t seed) {
+__global__ void k_atom_choices(int32_t* __restrict__ choices, int64_t B, int A, uint64_t seed, const int32_t* __restrict__ step) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  if (step) seed += (uint64_t)(uint32_t)step[0] * 0x9E3779B97F4A7C15ull;   // device-side stream position (CUDA-graph replay)
   uint64_t s = seed * 0xD1342543DE82EF95ull + (uint64_t)b * 0x2545F4914F6CDD1Dull + 1;
   int n = A - 1;
   int64_t Nn = B - 1;
@@ -495,7 +496,13 @@ extern "C" {
 int fp_atom_choices(int32_t* choices, int64_t B, int32_t A, uint64_t seed, void* stream) {
   if (A < 2 || A > B || A > 4096) return FP_E_BADARG;
   ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
-  k_atom_choices<<<nblk(B, 128), 128, 0, (cudaStream_t)stream>>>(choices, B, A, seed);
+  k_atom_choices<<<nblk(B, 128), 128, 0, (cudaStream_t)stream>>>(choices, B, A, seed, nullptr);
+  FP_LAUNCH_CHECK(); return 0;
+}
+int fp_atom_choices_step(int32_t* choices, int64_t B, int32_t A, uint64_t seed, const int32_t* step_counter, void* stream) {
+  if (A < 2 || A > B || A > 4096 || !step_counter) return FP_E_BADARG;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
+  k_atom_choices<<<nblk(B, 128), 128, 0, (cudaStream_t)stream>>>(choices, B, A, seed, step_counter);
   FP_LAUNCH_CHECK(); return 0;
 }
 int fp_atom_gather(const float* theta, const int32_t* choices, float* rows, int64_t B, int32_t A, int32_t D, void* stream) {

@@ -128,7 +128,10 @@ class _TrainEngine:
             self.seed += 1
         _lib.check(L.fp_nsf_prepare(c, _lib.ptr(net._flat), _lib.ptr(self.prepared), s), "prepare")
         if self.atomic:
-            _lib.check(L.fp_atom_choices(_lib.ptr(self.choices), self.B, self.A, self._choice_seed(), s), "choices")
+            if self.use_graph:   # draw position from the device step counter: fresh atoms on every graph replay
+                _lib.check(L.fp_atom_choices_step(_lib.ptr(self.choices), self.B, self.A, 12345, _lib.ptr(self.step_dev), s), "choices")
+            else:
+                _lib.check(L.fp_atom_choices(_lib.ptr(self.choices), self.B, self.A, self._choice_seed(), s), "choices")
             _lib.check(L.fp_atom_gather(_lib.ptr(self.theta_b), _lib.ptr(self.choices), _lib.ptr(self.atom_rows), self.B, self.A, net.D, s), "atom gather")
             theta = self.atom_rows
         else:
@@ -149,7 +152,7 @@ class _TrainEngine:
     _choice_counter = 0
 
     def _choice_seed(self) -> int:
-        # inside a CUDA graph the seed is frozen at capture; graphs are therefore only used for the MLE loss
+        # host-side stream position (plain launches); graph replays use the device step counter instead
         self._choice_counter += 1
         return (self._choice_counter * 0x9E3779B1 + 12345) & 0xFFFFFFFFFFFF
 
@@ -182,7 +185,7 @@ class _TrainEngine:
     def step(self, idx: Tensor, theta_all: Tensor, x_all: Tensor, masks_all: Optional[Tensor]):
         """One optimiser step on the rows ``idx`` of the resident dataset."""
         self.idx.copy_(idx)
-        if self.use_graph and not self.atomic:
+        if self.use_graph:
             if self.graph is None:
                 # warm-up on a side stream, then capture
                 s = torch.cuda.Stream()
@@ -192,8 +195,10 @@ class _TrainEngine:
                 torch.cuda.current_stream().wait_stream(s)
                 self._graph_data = (theta_all, x_all, masks_all)
                 g = torch.cuda.CUDAGraph()
+                n0 = _lib.lib().fp_launch_count()
                 with torch.cuda.graph(g):
                     self._step_body(theta_all, x_all, masks_all)
+                self.launches_per_step = int(_lib.lib().fp_launch_count() - n0)
                 self.graph = g
             if self._graph_data[0] is not theta_all or self._graph_data[1] is not x_all:
                 raise RuntimeError("graph was captured for a different resident dataset")

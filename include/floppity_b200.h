@@ -170,6 +170,9 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
 /* ---- SNPE-C atomic loss (sbi SNPE_C._log_prob_proposal_posterior_atomic; floppity.py:219-221) ---- */
 /* choices int32 [B, A-1]: A-1 distinct indices != b, uniform (Floyd sampling, counter RNG). */
 int fp_atom_choices(int32_t* choices, int64_t B, int32_t A, uint64_t seed, void* stream);
+/* same, with the draw position taken from a device counter (seed + step_counter[0]): the launch can sit in a CUDA
+ * graph and still draw fresh atoms on every replay */
+int fp_atom_choices_step(int32_t* choices, int64_t B, int32_t A, uint64_t seed, const int32_t* step_counter, void* stream);
 /* rows [B*A, D] = cat(theta[b], theta[choices[b,:]]). */
 int fp_atom_gather(const float* theta, const int32_t* choices, float* rows, int64_t B, int32_t A, int32_t D, void* stream);
 /* logp [B, A]; atom_theta [B*A, D]; low/high [D]; masks [B] (may be NULL => 0);
