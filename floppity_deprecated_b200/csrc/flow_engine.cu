@@ -30,7 +30,8 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
                      const float* lu_logdet, int ldp, cudaStream_t stream);
 int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                         const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
-                        int64_t R, int ldp, cudaStream_t stream);
+                        int64_t R, int ldp, cudaStream_t stream, const float* luM, const float* theta_sp, float* dM,
+                        float* dbias);
 int launch_affine_fwd(const float*, const float*, const float*, float, float*, float*, int64_t, int, cudaStream_t);
 int launch_affine_inv(const float*, const float*, const float*, float*, int64_t, int, cudaStream_t);
 int launch_affine_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
@@ -345,16 +346,12 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
   FP_TRY(launch_sum(d_logp, R, 1.f, grads + L.gradTailSum(), s));
 
   for (int i = L.T - 1; i >= 0; --i) {
-    // ---- LULinear backward: y = M x + b, x = theta_sp[i]
-    FP_TRY(launch_colsum(dth_a, D, R, D, grads + L.luBias(i), s));
-    FP_TRY(wgrad(dth_a, D, D, ws + W.thsp(i), D, D, R, grads + L.gradTailDM(i), D, 0, 0.f, 0, 0, s));
-    {
-      fp_gemm_args g = dgrad_args(dth_a, D, D, prepared + L.prepM(i), D, D, R, dth_b, D, 0);
-      FP_TRY(launch_gemm(&g, 0.f, 0, 0, s));
-    }
-    // ---- spline backward: d params, d theta_in (identity features pass through)
+    // ---- LULinear backward (y = M x + b, x = theta_sp[i]: dx = M^T dy, dM += dy^T x, db += colsum dy) fused into the
+    //      spline backward: d params, d theta_in (identity features pass through)
     const int dP = L.dP(i), ldP = L.ldP(i);
-    FP_TRY(launch_rqs_backward(cfg, i & 1, ws + W.thst(i), ws + W.prmbuf(i), dth_b, d_logp, dprm, dth_a, R, ldP, s));
+    FP_TRY(launch_rqs_backward(cfg, i & 1, ws + W.thst(i), ws + W.prmbuf(i), dth_a, d_logp, dprm, dth_b, R, ldP, s,
+                               prepared + L.prepM(i), ws + W.thsp(i), grads + L.gradTailDM(i), grads + L.luBias(i)));
+    { float* t = dth_a; dth_a = dth_b; dth_b = t; }
     // ---- final layer
     FP_TRY(launch_colsum(dprm, ldP, R, dP, grads + L.bf(i), s));
     FP_TRY(wgrad(dprm, ldP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, 0.f, 0, 0, s));

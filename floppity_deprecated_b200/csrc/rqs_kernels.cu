@@ -211,6 +211,11 @@ struct RqsBwdArgs {
   int D, d_tr, parity, rows;
   int ldp;                   // row stride of params / d_params in floats
   RqsConsts c;
+  // optional fused LULinear backward (y = M x + b after the spline): d_theta_out is then the gradient wrt y
+  const float* luM;          // [D, D]  (NULL: no LU, d_theta_out is the gradient wrt the spline output)
+  const float* theta_sp;     // [R, D]  spline output x saved by the forward
+  float* dM;                 // [D, D] += dy^T x
+  float* dbias;              // [D]    += colsum(dy)
 };
 
 template <int KT>
@@ -226,10 +231,22 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)RQS_STAGES * tile_floats * 4 + 7) & ~size_t(7)));
   const int64_t ntiles = (a.R + a.rows - 1) / a.rows;
   const int D = a.D, d_tr = a.d_tr;
+  const bool lu = a.luM != nullptr;
+  // LU scratch behind the barriers: M, dM accumulator, bias accumulator, dy tile, x tile, dx tile
+  float* luM = reinterpret_cast<float*>(bars + RQS_STAGES);
+  float* accM = luM + D * D;
+  float* accb = accM + D * D;
+  float* dyb = accb + D;
+  float* xsb = dyb + a.rows * D;
+  float* dxb = xsb + a.rows * D;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RQS_STAGES; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
+  }
+  if (lu) {
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) { luM[i] = a.luM[i]; accM[i] = 0.f; }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) accb[i] = 0.f;
   }
   __syncthreads();
 
@@ -256,6 +273,33 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
     const uint32_t parity = (uint32_t)(it / RQS_STAGES) & 1u;
     const int64_t r0 = tile * a.rows;
     const int rows_here = (int)min((int64_t)a.rows, a.R - r0);
+    if (lu) {
+      // LULinear backward on this tile: dx = M^T dy (feeds the spline backward), dM += dy^T x, dbias += colsum(dy)
+      const int nrd = rows_here * D;
+      for (int i = threadIdx.x; i < nrd; i += blockDim.x) {
+        dyb[i] = a.d_theta_out[r0 * D + i];
+        xsb[i] = a.theta_sp[r0 * D + i];
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < nrd; i += blockDim.x) {
+        const int row = i / D, k = i - row * D;
+        const float* dy = dyb + row * D;
+        float acc = 0.f;
+        for (int f = 0; f < D; ++f) acc = fmaf(luM[f * D + k], dy[f], acc);
+        dxb[i] = acc;
+      }
+      for (int p = threadIdx.x; p < D * D; p += blockDim.x) {      // each thread owns fixed (f, k) entries
+        const int f = p / D, k = p - f * D;
+        float acc = 0.f;
+        for (int row = 0; row < rows_here; ++row) acc = fmaf(dyb[row * D + f], xsb[row * D + k], acc);
+        accM[p] += acc;
+      }
+      for (int f = threadIdx.x; f < D; f += blockDim.x) {
+        float acc = 0.f;
+        for (int row = 0; row < rows_here; ++row) acc += dyb[row * D + f];
+        accb[f] += acc;
+      }
+    }
     mbar_wait(&bars[st], parity);
     __syncthreads();
 
@@ -266,7 +310,7 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
       int64_t gr = r0 + row;
       float* pe = P + row * row_floats + j * a.c.P;
       float x = a.theta_in[gr * D + f];
-      float gy = a.d_theta_out[gr * D + f];
+      float gy = lu ? dxb[row * D + f] : a.d_theta_out[gr * D + f];
       float gl = a.d_logdet[gr];
       // in place: every parameter is read before its gradient overwrites it
       float gx;
@@ -281,7 +325,7 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
     // identity features: gradient passes straight through the coupling
     for (int i = threadIdx.x; i < rows_here * D; i += blockDim.x) {
       int f = i % D;
-      if ((f & 1) != a.parity) a.d_theta_in[r0 * D + i] = a.d_theta_out[r0 * D + i];
+      if ((f & 1) != a.parity) a.d_theta_in[r0 * D + i] = lu ? dxb[i] : a.d_theta_out[r0 * D + i];
     }
     // write the gradient tile: bulk store when 16B-granular, else plain
     uint32_t bytes = (uint32_t)rows_here * row_floats * 4u;
@@ -304,6 +348,11 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
     if (nxt < ntiles) load_params(st, nxt);
   }
   if (threadIdx.x == 0) bulk_wait_all<0>();
+  if (lu) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) atomicAdd(&a.dM[i], accM[i]);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(&a.dbias[i], accb[i]);
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -381,12 +430,15 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
 
 int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                         const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
-                        int64_t R, int ldp, cudaStream_t stream) {
+                        int64_t R, int ldp, cudaStream_t stream, const float* luM, const float* theta_sp, float* dM,
+                        float* dbias) {
   if (R <= 0) return 0;
   if (cfg->K < 2 || cfg->K > 64 || cfg->D < 2 || cfg->D > 64) return FP_E_BADARG;
   RqsBwdArgs a{};
   a.theta_in = theta_in; a.params = params; a.d_theta_out = d_theta_out; a.d_logdet = d_logdet;
   a.d_params = d_params; a.d_theta_in = d_theta_in; a.R = R;
+  if (luM && (!theta_sp || !dM || !dbias)) return FP_E_BADARG;
+  a.luM = luM; a.theta_sp = theta_sp; a.dM = dM; a.dbias = dbias;
   a.D = cfg->D; a.parity = parity & 1;
   a.d_tr = (a.parity == 0) ? (cfg->D + 1) / 2 : cfg->D / 2;
   a.c = make_rqs_consts(cfg);
@@ -396,6 +448,7 @@ int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta
   a.rows = pick_rows(row_floats, a.d_tr);
   int threads = pick_threads(a.rows, a.d_tr);
   size_t smem = (size_t)RQS_STAGES * a.rows * row_floats * 4 + 8 + RQS_STAGES * 8 + 16;
+  smem += ((size_t)2 * a.D * a.D + a.D + (size_t)3 * a.rows * a.D) * 4;      // LU scratch (see the kernel)
   void (*kern)(RqsBwdArgs);
   switch (cfg->K) {
     case 8: kern = k_rqs_backward<8>; break;
@@ -435,7 +488,7 @@ int fp_rqs_backward(const fp_nsf_config* cfg, int32_t parity, const float* theta
                     const float* d_theta_out, const float* d_logdet, float* d_params, float* d_theta_in,
                     int64_t R, void* stream) {
   return fp::launch_rqs_backward(cfg, parity, theta_in, params, d_theta_out, d_logdet, d_params, d_theta_in, R, 0,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"
