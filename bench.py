@@ -264,27 +264,41 @@ def main():
         eng.idx.copy_(batches[i % len(batches)])
         eng._step_body(theta_dev, x_dev, masks_dev)
     import ctypes
-    pms, pl, pw = (ctypes.c_double * 6)(), (ctypes.c_int64 * 6)(), (ctypes.c_double * 6)()
-    _lib.check(L.fp_prof_collect(pms, pl, pw), "prof")
+    pms, pl, pw, pb = (ctypes.c_double * 6)(), (ctypes.c_int64 * 6)(), (ctypes.c_double * 6)(), (ctypes.c_double * 6)()
+    _lib.check(L.fp_prof_collect2(pms, pl, pw, pb), "prof")
     L.fp_prof_enable(0)
     tot = sum(pms) or 1.0
+    # 3xTF32: three TF32 passes per fp32-accurate product; TF32 dense peak = half the measured bf16 peak
+    tf32x3_peak = PK["tf_sust"] / 2.0 / 3.0
     classes = {}
     for i, name in enumerate(CLASS_NAMES):
         if pl[i] == 0:
             continue
         d = {"share": pms[i] / tot, "launches_per_step": pl[i] / K, "avg_us": 1e3 * pms[i] / pl[i]}
         if i in (0, 1):
-            d["achieved_tflops"] = pw[i] / (pms[i] * 1e-3) / 1e12
-            d["frac_of_bf16_sustained_peak"] = d["achieved_tflops"] / PK["tf_sust"]
+            d["achieved_tflops_fp32_equiv"] = pw[i] / (pms[i] * 1e-3) / 1e12
+            d["frac_of_3xtf32_tensor_peak"] = d["achieved_tflops_fp32_equiv"] / tf32x3_peak
+            d["achieved_gbs"] = pb[i] / (pms[i] * 1e-3) / 1e9
+            d["frac_of_hbm_peak"] = d["achieved_gbs"] / PK["hbm"]
         elif i in (2, 3, 4):
             d["achieved_gbs"] = pw[i] / (pms[i] * 1e-3) / 1e9
             d["frac_of_hbm_peak"] = d["achieved_gbs"] / PK["hbm"]
         classes[name] = d
     dom = max(range(6), key=lambda i: pms[i])
     if dom in (0, 1):
-        ach = pw[dom] / (pms[dom] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": PK["tf_sust"], "unit": "TFLOP/s", "frac": ach / PK["tf_sust"],
-                "traffic": None, "kernel": CLASS_NAMES[dom], "peak_source": PK["source"] + ", sustained (kernel timed inside the step)"}
+        # The conditioner GEMMs of this workload are skinny (hidden 128): arithmetic intensity ~32 flop/B in fp32, i.e.
+        # below the ridge even at three TF32 passes.  Both fractions are measured; the binding one is reported.
+        ach_t = pw[dom] / (pms[dom] * 1e-3) / 1e12
+        ach_b = pb[dom] / (pms[dom] * 1e-3) / 1e9
+        if ach_b / PK["hbm"] >= ach_t / tf32x3_peak:
+            roof = {"bound": "hbm", "achieved": ach_b, "peak": PK["hbm"], "unit": "GB/s", "frac": ach_b / PK["hbm"],
+                    "traffic": None, "kernel": CLASS_NAMES[dom], "peak_source": PK["source"],
+                    "tensor_frac_3xtf32": ach_t / tf32x3_peak}
+        else:
+            roof = {"bound": "tensor", "achieved": ach_t, "peak": tf32x3_peak, "unit": "TFLOP/s", "frac": ach_t / tf32x3_peak,
+                    "traffic": None, "kernel": CLASS_NAMES[dom],
+                    "peak_source": PK["source"] + ": bf16 sustained / 2 (TF32) / 3 (passes of the fp32-accurate split)",
+                    "hbm_frac": ach_b / PK["hbm"]}
     else:
         ach = pw[dom] / (pms[dom] * 1e-3) / 1e9 if pw[dom] else 0.0
         roof = {"bound": "hbm", "achieved": ach, "peak": PK["hbm"], "unit": "GB/s", "frac": ach / PK["hbm"], "traffic": None,

@@ -92,6 +92,7 @@ SIGNATURES = {
     "fp_launch_count": (c_int64, []),
     "fp_prof_enable": (c_int32, [c_int32]),
     "fp_prof_collect": (c_int32, [_P, _P, _P]),
+    "fp_prof_collect2": (c_int32, [_P, _P, _P, _P]),
     "fp_version": (c_char_p, []),
 }
 

@@ -28,6 +28,16 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// algorithmic HBM bytes of one GEMM launch: operands once, result once, plus whatever the epilogue streams
+inline double gemm_algo_bytes(const fp_gemm_args* a) {
+  const double M = (double)a->M, N = (double)a->N, K = (double)a->K;
+  double b = M * K + N * K + M * N;
+  if (a->flags & FP_G_GLU_RES) b += M * N * (a->U ? 2.0 : 1.0);      // residual in, pre-gate activation out
+  if (a->flags & FP_G_RELUMASK) b += M * N;
+  if (a->flags & (FP_G_ACCUM | FP_G_ATOMIC)) b += M * N;
+  return 4.0 * b;
+}
+
 struct GemmDrop {
   float p;          // 0 => off
   uint64_t seed;

@@ -199,7 +199,7 @@ int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int dro
   if (nt > 65535 || split > 65535 || mt > 2147483647LL) return FP_E_TOOLARGE;
   dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)split);
   GemmDrop d{drop_p, drop_seed, drop_width};
-  ProfScope ps(TAG_GEMM_SIMT, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream);
+  ProfScope ps(TAG_GEMM_SIMT, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
   if (a->a_kmajor && a->b_kmajor) k_gemm<true, true><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);
   else if (a->a_kmajor && !a->b_kmajor) k_gemm<true, false><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);
   else if (!a->a_kmajor && a->b_kmajor) k_gemm<false, true><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);

@@ -204,6 +204,8 @@ int fp_within_box(const float* theta, const float* low, const float* high, uint8
 int64_t fp_launch_count(void);
 int fp_prof_enable(int32_t on);
 int fp_prof_collect(double* ms /*[6]*/, int64_t* launches /*[6]*/, double* work /*[6]*/);
+/* same, plus the algorithmic HBM bytes of the GEMM classes (operands + result + epilogue streams, each once) */
+int fp_prof_collect2(double* ms /*[6]*/, int64_t* launches /*[6]*/, double* work /*[6]*/, double* bytes /*[6]*/);
 
 const char* fp_version(void);
 
