@@ -1,0 +1,26 @@
+#!/usr/bin/env bash
+# One-GPU evidence run: parity tests, bench lines for every config, c5 sweep, ncu launch list + full capture.
+# usage (under gpurun): bash tools/gpu_round.sh <tag>
+set -uo pipefail
+TAG="${1:-r1x}"
+OUT="gpurun_out/${TAG}"
+mkdir -p "${OUT}"
+python -m pytest tests -m gpu -x -q > "${OUT}/gpu_tests.log" 2>&1; echo "pytest rc=$?" | tee -a "${OUT}/gpu_tests.log"
+tail -3 "${OUT}/gpu_tests.log"
+python bench.py --steps 20 --warmup 5 > "${OUT}/bench_c2.json" 2> "${OUT}/bench_c2.err"; echo "bench c2 rc=$?"
+python bench.py --steps 20 --warmup 5 --graph 1 --no-cpu --no-extras > "${OUT}/bench_c2_graph.json" 2> "${OUT}/bench_c2_graph.err"; echo "bench c2 graph rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > "${OUT}/bench_ref.json" 2> "${OUT}/bench_ref.err"; echo "bench ref rc=$?"
+for c in c1 c4 c3; do
+  timeout 600 python bench.py --config $c --steps 6 --warmup 3 --no-cpu > "${OUT}/bench_${c}.json" 2> "${OUT}/bench_${c}.err"; echo "bench $c rc=$?"
+done
+timeout 900 python tools/sweep_c5.py > "${OUT}/sweep_c5.jsonl" 2> "${OUT}/sweep_c5.err"; echo "sweep rc=$?"
+tail -2 "${OUT}"/bench_*.err | tail -30
+# ncu: launch list of one step + full capture of the dominant GEMM (same command ran plain right before)
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras"
+$CMD > "${OUT}/plain.log" 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 700 --csv --log-file "${OUT}/launches.csv" $CMD > "${OUT}/ncu_list.log" 2>&1
+echo "ncu list rc=$?"
+$CMD > "${OUT}/plain2.log" 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc_nt -s 200 -c 3 -o "${OUT}/prof_gemm_tc" $CMD > "${OUT}/ncu_full.log" 2>&1
+echo "ncu full rc=$?"
+ls -la "${OUT}"
