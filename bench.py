@@ -316,9 +316,15 @@ def main():
         ms_s = timed(lambda i: net.inverse_rows(z, ctx_std), 5)
         out_extra["posterior_draws_per_s"] = world * n_draw * 5 / (ms_s * 1e-3)
         th_q = theta_dev[torch.randint(0, args.rows, (n_draw,), device=dev)]
+        x1 = x[:1].to(dev)
+
+        def lp_eval(i):
+            with torch.no_grad():       # posterior.log_prob (floppityFUN.py:35): no gradient, rows chunked by the flow
+                net.log_prob(th_q, x1)
+
         for _ in range(2):
-            net.log_prob(th_q, x[:1].to(dev))
-        ms_l = timed(lambda i: net.log_prob(th_q, x[:1].to(dev)), 5)
+            lp_eval(0)
+        ms_l = timed(lp_eval, 5)
         out_extra["log_prob_per_s"] = world * n_draw * 5 / (ms_l * 1e-3)
         net.train()
         eng2 = _TrainEngine(net, prior, B, not atomic, cfg.atoms, True, 5e-4, 5.0, use_graph=False)

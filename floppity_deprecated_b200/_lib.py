@@ -22,6 +22,7 @@ FP_E = {-1: "FP_E_BADARG", -2: "FP_E_TOOLARGE", -3: "FP_E_NOTREADY"}
 P_CTX_W, P_CTX_B, P_W0X, P_W1, P_B1, P_W2, P_B2, P_WF, P_BF, P_LU_LOWER, P_LU_UPPER, P_LU_DIAG, P_LU_BIAS = range(13)
 # fp_gemm_flags
 G_RELU_A, G_RELU_B, G_BIAS, G_ADD_CTX, G_GLU_RES, G_RELUMASK, G_ACCUM, G_ATOMIC, G_TF32X3 = 1, 2, 4, 8, 16, 32, 64, 128, 256
+G_COLSUM_A = 4096
 
 
 class NsfConfig(Structure):
@@ -93,6 +94,7 @@ SIGNATURES = {
     "fp_prof_enable": (c_int32, [c_int32]),
     "fp_prof_collect": (c_int32, [_P, _P, _P]),
     "fp_prof_collect2": (c_int32, [_P, _P, _P, _P]),
+    "fp_tc_set_debug": (c_int32, [c_int32]),
     "fp_version": (c_char_p, []),
 }
 

@@ -80,17 +80,22 @@ static int pick_split(int64_t M, int N, int64_t K) {
 }
 
 // dW[N_out, K_in] += dOut[R, N_out]^T @ Act[R, K_in]   (both operands row-major over the batch)
+// db[N_out] += colsum(dOut) rides along when `db` is given (fused into the tensor-core kernel, else its own launch)
 static int wgrad(const float* dOut, int64_t ldo, int n_out, const float* act, int64_t lda, int k_in, int64_t R,
-                 float* dW, int64_t ldw, int flags_extra, float drop_p, uint64_t seed, int drop_width, cudaStream_t s) {
+                 float* dW, int64_t ldw, int flags_extra, float drop_p, uint64_t seed, int drop_width, cudaStream_t s,
+                 float* db = nullptr) {
   fp_gemm_args g{};
   g.A = dOut; g.lda = ldo; g.a_kmajor = 0;   // logical A'[n_out, R], element (n, r) at dOut[r*ldo + n]
   g.B = act; g.ldb = lda; g.b_kmajor = 0;    // logical B'[k_in, R], element (k, r) at act[r*lda + k]
   g.C = dW; g.ldc = ldw; g.M = n_out; g.N = k_in; g.K = R;
-  g.flags = FP_G_ATOMIC | flags_extra;
+  g.flags = FP_G_ATOMIC | flags_extra | (db ? FP_G_COLSUM_A : 0);
+  g.U = db;
   if (drop_p == 0.f) {
     int r = launch_gemm_tc_tn(&g, s);
     if (r != FP_E_NOTREADY) return r;
   }
+  if (db) FP_TRY(launch_colsum(dOut, ldo, R, n_out, db, s));
+  g.flags &= ~FP_G_COLSUM_A; g.U = nullptr;
   g.split_k = pick_split(n_out, k_in, R);
   return launch_gemm(&g, drop_p, seed, drop_width, s);
 }
@@ -353,21 +358,18 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
                                prepared + L.prepM(i), ws + W.thsp(i), grads + L.gradTailDM(i), grads + L.luBias(i)));
     { float* t = dth_a; dth_a = dth_b; dth_b = t; }
     // ---- final layer
-    FP_TRY(launch_colsum(dprm, ldP, R, dP, grads + L.bf(i), s));
-    FP_TRY(wgrad(dprm, ldP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, 0.f, 0, 0, s));
+    FP_TRY(wgrad(dprm, ldP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, 0.f, 0, 0, s, grads + L.bf(i)));
     FP_TRY(dgrad_weight(L, prepared, L.tWf(i), ldP, dprm, ldP, dP, params + L.wf(i), H, H, R, dh, H, 0, nullptr, 0, 0.f, 0, 0, s));
     // ---- residual blocks, last to first
     for (int k = L.Bk - 1; k >= 0; --k) {
       const uint64_t seed = layer_seed(dropout_seed, i, k);
       FP_TRY(launch_glu_bwd(dh, ws + W.ubuf(i, k), ctx_all + L.ctxCol(i, 1 + k), L.Nctx, du,
                             dctx_all + L.ctxCol(i, 1 + k), Rc, A, H, s));
-      FP_TRY(launch_colsum(du, H, R, H, grads + L.b2(i, k), s));
       FP_TRY(wgrad(du, H, H, ws + W.tbuf(i, k), H, H, R, grads + L.w2(i, k), H,
-                   FP_G_RELU_B | (drop > 0.f ? 1024 : 0), drop, seed, H, s));
+                   FP_G_RELU_B | (drop > 0.f ? 1024 : 0), drop, seed, H, s, grads + L.b2(i, k)));
       FP_TRY(dgrad_weight(L, prepared, L.tW2(i, k), H, du, H, H, params + L.w2(i, k), H, H, R, dt, H,
                           FP_G_RELUMASK | (drop > 0.f ? 2048 : 0), ws + W.tbuf(i, k), H, drop, seed, H, s));
-      FP_TRY(launch_colsum(dt, H, R, H, grads + L.b1(i, k), s));
-      FP_TRY(wgrad(dt, H, H, ws + W.hbuf(i, k), H, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, 0.f, 0, 0, s));
+      FP_TRY(wgrad(dt, H, H, ws + W.hbuf(i, k), H, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, 0.f, 0, 0, s, grads + L.b1(i, k)));
       FP_TRY(dgrad_weight(L, prepared, L.tW1(i, k), H, dt, H, H, params + L.w1(i, k), H, H, R, dh, H,
                           FP_G_RELUMASK | FP_G_ACCUM, ws + W.hbuf(i, k), H, 0.f, 0, 0, s));
     }
@@ -380,8 +382,7 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
   if (d_theta) FP_TRY(launch_affine_bwd(dth_a, zscale, d_theta, R, D, s));
 
   // ---- context projection weights: dWctx += dctx_all^T @ ctx ; db += colsum(dctx_all)
-  FP_TRY(launch_colsum(dctx_all, L.Nctx, Rc, (int)L.Nctx, grads + L.ctx_b, s));
-  FP_TRY(wgrad(dctx_all, L.Nctx, (int)L.Nctx, ctx, L.C, L.C, Rc, grads + L.ctx_w, L.C, 0, 0.f, 0, 0, s));
+  FP_TRY(wgrad(dctx_all, L.Nctx, (int)L.Nctx, ctx, L.C, L.C, Rc, grads + L.ctx_w, L.C, 0, 0.f, 0, 0, s, grads + L.ctx_b));
   return 0;
 }
 

@@ -446,7 +446,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 // activations, so the splitter warps split BOTH (relu prologue on B for the relu'd activation operand).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const fp_gemm_args g,
-             int nkb_total, int nsplit, int vec_all) {
+             int nkb_total, int nsplit, int vec_all, int dbg) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_a = smem_u32(smem);                                  // shared-space address of the ring
@@ -539,7 +539,7 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
             umma_tf32(t_hh, a_hi, b_hi, idesc, acc);
             umma_tf32(t_x, a_lo, b_hi, idesc, acc);
-            umma_tf32(t_x, a_hi, b_lo, idesc, 1u);
+            if (!(dbg & 4)) umma_tf32(t_x, a_hi, b_lo, idesc, 1u);
           }
           umma_commit(&empty[s]);
         }
@@ -550,19 +550,30 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // splitter: raw A at +0 -> hi in place, lo at +TILE; raw B at +2*TILE -> hi in place, lo at +3*TILE
     const int tid_s = threadIdx.x - 64;
     const bool relu_b = (g.flags & FP_G_RELU_B) != 0;
+    // FP_G_COLSUM_A: the bias gradient colsum(A) rides along.  This thread's eight 16-byte chunks of the raw A tile
+    // are chunk (tid_s & 7) of k-rows (tid_s >> 3) + 16 (i & 1) of MN group i >> 1; the 32-byte-atom swizzle XORs the
+    // 32-byte chunk index with (k-row & 3), which does not depend on i, so the chunk is the same four logical
+    // columns for every i & 1 and every k-block: one float4 accumulator per MN group.
+    const bool colsum = (g.flags & FP_G_COLSUM_A) != 0;
+    float* const cs_out = g.U;
     uint32_t it = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
       int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
+      float4 cs[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) cs[q4] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1u;
         mbar_wait(&full_raw[s], ph);
         const uint32_t aA = smem_a + (uint32_t)(s * TC_STAGE_BYTES) + (uint32_t)tid_s * 16u;
-#pragma unroll 4
+        if (!(dbg & 1))
+#pragma unroll
         for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
           const uint32_t off = aA + (uint32_t)i * 2048u;
           const float4 v = lds128(off);
           float4 u = lds128(off + 2 * TC_TILE_BYTES);
+          cs[i >> 1].x += v.x; cs[i >> 1].y += v.y; cs[i >> 1].z += v.z; cs[i >> 1].w += v.w;
           const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
           sts128(off, h);
           sts128(off + TC_TILE_BYTES, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
@@ -574,6 +585,26 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ready[s]);
+      }
+      if (colsum && n0 == 0 && kb0 < kb1) {
+        // lanes l, l^10, l^20, l^30 hold the same logical columns (k-rows differing in their low two bits)
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float4 c = cs[q4];
+#pragma unroll
+          for (int sh = 10; sh <= 20; sh += 10) {
+            c.x += __shfl_xor_sync(0xffffffffu, c.x, sh); c.y += __shfl_xor_sync(0xffffffffu, c.y, sh);
+            c.z += __shfl_xor_sync(0xffffffffu, c.z, sh); c.w += __shfl_xor_sync(0xffffffffu, c.w, sh);
+          }
+          if (lane < 8) {               // k-row & 3 == 0: physical chunk == logical chunk
+            const int m = m0 + q4 * 32 + lane * 4;
+            if (vec_all && m + 3 < (int)g.M) red_add_f32x4(cs_out + m, c);
+            else {
+              const float e[4] = {c.x, c.y, c.z, c.w};
+              for (int j = 0; j < 4; ++j) if (m + j < (int)g.M) red_add_f32(cs_out + m + j, e[j]);
+            }
+          }
+        }
       }
     }
   } else {
@@ -618,7 +649,8 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int n = n0 + half * 64 + chunk * 32 + cch * 4;
         const bool vec = vec_all && (n + 3 < gN);
         const int64_t mrow = (int64_t)m0 + q * 32 + rsub;
-        if (vec && m0 + TC_BM <= gM) {            // full tile: straight-line, four rows in flight
+        if (dbg & 2) {
+        } else if (vec && m0 + TC_BM <= gM) {            // full tile: straight-line, four rows in flight
           float* cp = gC + mrow * g_ldc + n;
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
@@ -750,6 +782,7 @@ static bool get_tensor_map(const float* base, int64_t rows, int64_t cols, int64_
 }
 
 static long long* g_tc_trace = nullptr;
+static int g_tc_dbg = 0;     // debug switches of the TN kernel (fp_tc_set_debug): 1 no split, 2 no reductions, 4 two products
 
 // Launch with programmatic stream serialisation: the kernel may begin (barrier init, TMEM allocation, tensor-map
 // prefetch) while the previous kernel in the stream drains; it calls griddepcontrol.wait before touching memory.
@@ -849,7 +882,8 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
 int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   if (!tc_enabled()) return FP_E_NOTREADY;
   if (a->a_kmajor || a->b_kmajor) return FP_E_NOTREADY;
-  if ((a->flags & ~(FP_G_ATOMIC | FP_G_RELU_B)) != 0 || !(a->flags & FP_G_ATOMIC)) return FP_E_NOTREADY;
+  if ((a->flags & ~(FP_G_ATOMIC | FP_G_RELU_B | FP_G_COLSUM_A)) != 0 || !(a->flags & FP_G_ATOMIC)) return FP_E_NOTREADY;
+  if ((a->flags & FP_G_COLSUM_A) && !a->U) return FP_E_BADARG;
   if ((a->lda & 3) || (a->ldb & 3)) return FP_E_NOTREADY;
   if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return FP_E_NOTREADY;
   if (a->M < 1 || a->N < 1 || a->K < 1 || a->M > 65536) return FP_E_NOTREADY;
@@ -870,8 +904,9 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   nsplit = (nkb + kbps - 1) / kbps;                        // no empty splits
   const int grid = (int)std::min<int64_t>(tiles * nsplit, num_sms());
   int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
+  if ((a->flags & FP_G_COLSUM_A) && (reinterpret_cast<uintptr_t>(a->U) & 15)) vec_all = 0;
   ProfScope ps(TAG_GEMM_TC, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
-  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, mA, mB, *a, nkb, nsplit, vec_all));
+  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg));
   FP_LAUNCH_CHECK();
   return 0;
 }
@@ -904,6 +939,8 @@ int launch_gemm_ctx(const fp_gemm_args* a, cudaStream_t stream) { return launch_
 extern "C" {
 // debug: device buffer of >= 512 int64 receiving SM-clock stamps of CTA 0 (NULL switches tracing off)
 int fp_tc_set_trace(void* buf) { fp::g_tc_trace = reinterpret_cast<long long*>(buf); return 0; }
+// debug: ablation switches for kernel timing experiments (results are WRONG when non-zero); 0 = normal
+int fp_tc_set_debug(int32_t bits) { fp::g_tc_dbg = bits; return 0; }
 // Standalone entry: C = pro(A) * B^T (+ epilogue) on the tensor cores; B_hi/B_lo from fp_split_tf32.
 // Returns FP_E_NOTREADY when the shape/stride/flags are not supported by the tcgen05 kernel.
 int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, void* stream) {

@@ -108,7 +108,8 @@ enum fp_gemm_flags {
   FP_G_TF32X3      = 256, /* use the tcgen05 3xTF32 path when shapes allow (fp32-accurate) */
   FP_G_DROP_A      = 512, /* inverted dropout on A on load (engine-internal; needs the engine's seed) */
   FP_G_DROP_B      = 1024,
-  FP_G_DROPMASK    = 2048 /* dropout mask applied with FP_G_RELUMASK in the backward */
+  FP_G_DROPMASK    = 2048,/* dropout mask applied with FP_G_RELUMASK in the backward */
+  FP_G_COLSUM_A    = 4096 /* weight-gradient form only: U[m] += sum_k A[k,m] (the bias gradient rides along) */
 };
 typedef struct fp_gemm_args {
   const float* A; int64_t lda; int32_t a_kmajor;
@@ -129,11 +130,15 @@ int fp_gemm(const fp_gemm_args* args, void* stream);
  * anything else (the caller then uses fp_gemm).  Set FLOPPITY_TC=0 to disable the tensor-core path. */
 int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, void* stream);
 int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
-/* weight-gradient form: C[M,N] += A[K,M]^T * B[K,N] (a_kmajor = b_kmajor = 0, flags = FP_G_ATOMIC [| FP_G_RELU_B]);
- * contraction split across CTAs, partial tiles added with vector atomics.  FP_E_NOTREADY -> use fp_gemm. */
+/* weight-gradient form: C[M,N] += A[K,M]^T * B[K,N] (a_kmajor = b_kmajor = 0, flags = FP_G_ATOMIC [| FP_G_RELU_B]
+ * [| FP_G_COLSUM_A with the bias-gradient vector [M] in `U`]); contraction split across CTAs, partial tiles added
+ * with vector atomics.  FP_E_NOTREADY -> use fp_gemm (which ignores FP_G_COLSUM_A: the caller sums columns itself). */
 int fp_gemm_tc_tn(const fp_gemm_args* args, void* stream);
 /* debug: SM-clock stamps of CTA 0 of the next fp_gemm_tc launches into a device int64[512] buffer (NULL = off) */
 int fp_tc_set_trace(void* buf);
+/* debug: ablation switches for timing experiments on the weight-gradient kernel (1 skip split, 2 skip reductions,
+ * 4 two of three products); results are wrong while non-zero */
+int fp_tc_set_debug(int32_t bits);
 
 /* ---- whole-flow entry points --------------------------------------------------------------- */
 /* Derive per-step constants from the parameters (W = L*U, L, U, sum log diag U). */

@@ -303,10 +303,16 @@ def test_tcgen05_wgrad_form(R, M, N):
     args.A, args.lda, args.a_kmajor = Ad.data_ptr(), M, 0
     args.B, args.ldb, args.b_kmajor = Bd.data_ptr(), N, 0
     args.C, args.ldc, args.M, args.N, args.K = Cd.data_ptr(), N, M, N, R
-    args.flags, args.split_k = _lib.G_ATOMIC | _lib.G_RELU_B, 1
+    # the bias gradient colsum(A) rides along (FP_G_COLSUM_A, output vector in U)
+    b0 = torch.randn(M, generator=g)
+    bd = b0.clone().cuda()
+    args.flags, args.split_k = _lib.G_ATOMIC | _lib.G_RELU_B | _lib.G_COLSUM_A, 1
+    args.U = bd.data_ptr()
     rc = _lib.lib().fp_gemm_tc_tn(ctypes.byref(args), _lib.stream())
     assert rc == 0, rc
     torch.cuda.synchronize()
+    want_b = b0.double() + A.double().sum(0)
+    assert (bd.cpu().double() - want_b).abs().max().item() < 1e-5 * max(1.0, want_b.abs().max().item()) * max(1.0, (R / 1000) ** 0.5)
     err = (Cd.cpu().double() - want).abs().max().item()
     fp32_err = ((C0 + A.t() @ torch.relu(B)).double() - want).abs().max().item()
     scale = want.abs().max().item()
