@@ -95,6 +95,7 @@ SIGNATURES = {
     "fp_prof_collect": (c_int32, [_P, _P, _P]),
     "fp_prof_collect2": (c_int32, [_P, _P, _P, _P]),
     "fp_tc_set_debug": (c_int32, [c_int32]),
+    "fp_cf_set_trace": (c_int32, [_P]),
     "fp_version": (c_char_p, []),
 }
 

@@ -1,0 +1,563 @@
+// cond_fused.cu -- the whole ResidualNet conditioner of one coupling layer as ONE persistent tcgen05 kernel (hidden 128).
+//
+// Stands for nflows ResidualNet.forward (initial layer, Bk x ResidualBlock with context GLU, final layer), reached
+// from /root/reference/modules.py:63 via sbi build_nsf; upstream runs it as ~10 eager ops per block
+// (SURVEY.md 2.3 iii-iv), gemm_tc.cu runs it as 2*Bk+2 GEMM launches with every activation making a round trip
+// through HBM/L2.  Here a CTA takes a tile of 128 flow rows through the whole chain
+//     h0 = theta W0x^T + ctx0 ;  per block: t = relu(h) W1^T + b1 ; u = relu(t) W2^T + b2 ; h += u * sigmoid(ctx_k)
+//     params = h Wf^T + bf
+// with the activations never leaving the SM:
+//   * the A operand of every GEMM lives in TENSOR MEMORY (tcgen05.mma with A from TMEM): the epilogue threads own one
+//     row each, apply bias / context / GLU / relu, split the result into TF32 hi + lo (3xTF32, fp32-accurate) and
+//     write it back with tcgen05.st as the next GEMM's operand -- no shared-memory round trip, no swizzle;
+//   * the residual stream h stays in the epilogue threads' registers;
+//   * weights (pre-split hi / lo, fp_nsf_prepare) stream from L2 through a TMA ring that runs ahead across GEMM and
+//     tile boundaries;
+//   * the only global traffic is theta in, the spline parameters out and -- in training mode -- the saved activations
+//     (h_k, t_k, u_k) out, staged in shared memory and written by TMA tensor stores.
+// TMEM map (512 columns): [0,256) accumulators (hi*hi | cross terms; two 64-wide sets for the final layer so its
+// epilogue overlaps the next MMAs), [256,384) operand hi, [384,512) operand lo.
+#include "common.cuh"
+#include "prof.h"
+#include "layout.h"
+#include "tc_common.cuh"
+#include "gemm_epilogue.cuh"
+#include <stdlib.h>
+#include <algorithm>
+
+namespace fp {
+
+constexpr int CF_BM = 128;
+constexpr int CF_WSTAGES = 3;
+constexpr int CF_TILE_BYTES = 128 * 128;                // one [128 rows x 32 floats] SWIZZLE_128B box
+constexpr int CF_WSTAGE_BYTES = 2 * CF_TILE_BYTES;      // hi + lo
+constexpr int CF_SLOT_BYTES = 2 * CF_TILE_BYTES;        // staging slot: 64 columns of 128 rows
+constexpr int CF_NSLOTS = 4;                            // two per column half
+constexpr int CF_THREADS = 320;                         // TMA producer, MMA issuer, 8 epilogue warps
+constexpr int CF_MAXBK = 4;
+constexpr int CF_SB_BLOCKS = 2;                         // blocks whose biases live in shared memory
+constexpr int CF_SBIAS_BYTES = CF_SB_BLOCKS * 2 * 128 * 4;
+constexpr int CF_SMEM_BYTES = CF_WSTAGES * CF_WSTAGE_BYTES + CF_NSLOTS * CF_SLOT_BYTES + CF_SBIAS_BYTES + 256 /*barriers*/;
+constexpr uint32_t CF_T_ACC = 0, CF_T_AHI = 256, CF_T_ALO = 384;
+
+struct CondFwdMaps {
+  CUtensorMap w0h, w0l;       // W0x hi / lo   [128, D]
+  CUtensorMap wh, wl;         // blocks: rows k*258 = W1_k, k*258+129 = W2_k   [Bk*258, 128]
+  CUtensorMap wfh, wfl;       // Wf hi / lo    [dP, 128], 64-row boxes
+  CUtensorMap prm;            // spline parameters out [R, dP]
+  CUtensorMap h[CF_MAXBK + 1], t[CF_MAXBK], u[CF_MAXBK];   // saved activations out [R, 128] (training)
+};
+struct CondFwdParams {
+  const float* theta; int32_t D;
+  const float* ctx; int64_t ldg; int32_t ctx_div;     // ctx_all + column of this layer's slot 0; slot k at +128 k
+  const float* b1[CF_MAXBK]; const float* b2[CF_MAXBK]; const float* bf;
+  int64_t R; int32_t Bk; int32_t dP; int32_t training;
+  long long* trace;      // debug: SM-clock stamps of CTA 0 (fp_cf_set_trace)
+};
+
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32 (A: lane = row, one 32-bit column per k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// One column half (4 warps, 128 threads) of the epilogue group stages 64-column pieces of a [128 x *] result in its
+// own two shared-memory slots and hands them to the TMA store engine.
+struct Stager {
+  uint32_t slots;       // shared address of this half's two slots
+  uint32_t op;          // store ops issued so far by this half
+  int bar_id;           // named barrier of this half
+  bool issuer;          // the one thread that talks to the TMA engine
+  uint32_t row_off;     // this thread's row inside the tile * 128 bytes
+  uint32_t swz;         // row & 7
+  __device__ __forceinline__ uint32_t begin() {
+    if (issuer) bulk_wait_read<1>();          // the op that used this slot two ops ago has been read out
+    named_bar_sync(bar_id, 128);
+    return slots + (op & 1u) * (uint32_t)CF_SLOT_BYTES;
+  }
+  // 16 consecutive floats of this thread's row: columns [piece*16, piece*16+16) of 32-column box `box`
+  __device__ __forceinline__ void put16(uint32_t slot, int box, int piece, const float (&v)[16]) const {
+    const uint32_t base = slot + (uint32_t)box * (uint32_t)CF_TILE_BYTES + row_off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(base + ((((uint32_t)(piece * 4 + j)) ^ swz) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+  }
+  __device__ __forceinline__ void end(uint32_t slot, const CUtensorMap* map, int col0, int row0, int nbox) {
+    fence_proxy_async_smem();
+    named_bar_sync(bar_id, 128);
+    if (issuer) {
+      for (int b = 0; b < nbox; ++b) tma_store_2d(map, slot + (uint32_t)b * (uint32_t)CF_TILE_BYTES, col0 + 32 * b, row0);
+      bulk_commit();
+    }
+    ++op;
+  }
+};
+
+__device__ __forceinline__ void split16(const float (&w)[16], float (&hi)[16], float (&lo)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { hi[j] = tf32_round(w[j]); lo[j] = w[j] - hi[j]; }
+}
+
+#define CF_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && (slot) < 512) p.trace[(slot)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(CF_THREADS, 1)
+k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t cf_smem[];     // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = cf_smem;
+  const uint32_t smem_a = smem_u32(smem);
+  const uint32_t slots_a = smem_a + CF_WSTAGES * CF_WSTAGE_BYTES;
+  float* sbias = reinterpret_cast<float*>(smem + CF_WSTAGES * CF_WSTAGE_BYTES + CF_NSLOTS * CF_SLOT_BYTES);
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + CF_WSTAGES * CF_WSTAGE_BYTES + CF_NSLOTS * CF_SLOT_BYTES + CF_SBIAS_BYTES);
+  uint64_t* w_empty = w_full + CF_WSTAGES;
+  uint64_t* a_ready = w_empty + CF_WSTAGES;     // [1]
+  uint64_t* acc_full = a_ready + 1;             // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (p.R + CF_BM - 1) / CF_BM;
+  const int Bk = p.Bk;
+  const int nF = (p.dP + 63) / 64;              // 64-column units of the final layer
+  const int ks0 = (p.D + 7) / 8;                // k-steps of the initial layer (K = D <= 32)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(a_ready, 8);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w0h) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wfh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.prm) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // weights (fp_nsf_prepare), theta and the context projection come from earlier kernels in the stream
+  if ((smem_a & 1023u) != 0u) __trap();     // the swizzled tiles rely on the declared alignment
+  for (int e = threadIdx.x; e < CF_SB_BLOCKS * 256; e += CF_THREADS) {
+    const int k = e >> 8, r = e & 255;
+    sbias[e] = (k < Bk) ? ((r < 128) ? p.b1[k][r] : p.b2[k][r - 128]) : 0.f;
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ===== weight producer: the same sequence of k-blocks for every tile, running ahead through the ring =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      auto stage = [&](const CUtensorMap* mh, const CUtensorMap* ml, int col, int row, uint32_t bytes) {
+        const int s = it % CF_WSTAGES;
+        const uint32_t ph = (it / CF_WSTAGES) & 1u;
+        mbar_wait(&w_empty[s], ph ^ 1u);
+        uint8_t* sb = smem + s * CF_WSTAGE_BYTES;
+        mbar_expect_tx(&w_full[s], bytes);
+        tma_load_2d(sb, mh, col, row, &w_full[s]);
+        tma_load_2d(sb + CF_TILE_BYTES, ml, col, row, &w_full[s]);
+        ++it;
+      };
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        stage(&maps.w0h, &maps.w0l, 0, 0, 2 * CF_TILE_BYTES);
+        for (int k = 0; k < Bk; ++k)
+          for (int g = 0; g < 2; ++g)
+            for (int kb = 0; kb < 4; ++kb) stage(&maps.wh, &maps.wl, kb * 32, k * 258 + g * 129, 2 * CF_TILE_BYTES);
+        for (int j = 0; j < nF; ++j)
+          for (int kb = 0; kb < 4; ++kb) stage(&maps.wfh, &maps.wfl, kb * 32, j * 64, CF_TILE_BYTES);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc128 = make_idesc_tf32(128, 128);
+      constexpr uint32_t idesc64 = make_idesc_tf32(128, 64);
+      const uint32_t t_ahi = tmem_base + CF_T_AHI, t_alo = tmem_base + CF_T_ALO;
+      uint32_t it = 0, n_ar = 0, n_gf[2] = {0u, 0u};
+      // one k-block (ring stage) of a GEMM unit: nk k-steps of 8, operand columns from acol
+      auto kblock = [&](uint32_t d_hh, uint32_t d_x, uint32_t acol, int nk, uint32_t idesc, bool first) {
+        const int s = it % CF_WSTAGES;
+        const uint32_t ph = (it / CF_WSTAGES) & 1u;
+        mbar_wait(&w_full[s], ph);
+        tcgen05_fence_after();
+        uint8_t* sb = smem + s * CF_WSTAGE_BYTES;
+        const uint64_t b_hi = make_kmajor_desc(sb), b_lo = make_kmajor_desc(sb + CF_TILE_BYTES);
+        for (int k = 0; k < nk; ++k) {
+          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+          const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+          umma_tf32_ts(d_hh, t_ahi + acol + 8u * k, b_hi + adv, idesc, acc);
+          umma_tf32_ts(d_x, t_alo + acol + 8u * k, b_hi + adv, idesc, acc);
+          umma_tf32_ts(d_x, t_ahi + acol + 8u * k, b_lo + adv, idesc, 1u);
+        }
+        umma_commit(&w_empty[s]);
+        ++it;
+      };
+      auto wait_operand = [&]() {
+        mbar_wait(a_ready, n_ar & 1u);
+        ++n_ar;
+        tcgen05_fence_after();
+      };
+      const uint32_t d_hh = tmem_base + CF_T_ACC, d_x = d_hh + 128;
+      int ts = 0;     // trace slot (MMA: 0..255)
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        wait_operand();                                   // theta tile split into the operand columns
+        CF_TRACE(ts); ++ts;
+        kblock(d_hh, d_x, 0, ks0, idesc128, true);
+        umma_commit(&acc_full[0]);
+        CF_TRACE(ts); ++ts;
+        for (int u = 0; u < 2 * Bk; ++u) {
+          wait_operand();
+          CF_TRACE(ts); ++ts;
+          for (int kb = 0; kb < 4; ++kb) kblock(d_hh, d_x, 32u * kb, 4, idesc128, kb == 0);
+          umma_commit(&acc_full[0]);
+          CF_TRACE(ts); ++ts;
+        }
+        wait_operand();                                   // final hidden state
+        CF_TRACE(ts); ++ts;
+        for (int j = 0; j < nF; ++j) {
+          const int b = j & 1;
+          if (n_gf[b] > 0) {                              // the epilogue of the previous unit on this set has drained it
+            mbar_wait(&acc_empty[b], (n_gf[b] - 1) & 1u);
+            tcgen05_fence_after();
+          }
+          const uint32_t f_hh = tmem_base + CF_T_ACC + 128u * b, f_x = f_hh + 64;
+          for (int kb = 0; kb < 4; ++kb) kblock(f_hh, f_x, 32u * kb, 4, idesc64, kb == 0);
+          umma_commit(&acc_full[b]);
+          ++n_gf[b];
+          CF_TRACE(ts); ++ts;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..9: TMEM lane quarter q (= warp % 4), column half hf; one row per thread =====
+    // Every global operand of a phase (context / gate rows) is requested one 16-column piece ahead -- the first piece
+    // before the accumulator is even complete -- and the biases sit in shared memory, so the serial chain
+    // MMA -> read-out -> operand write-back has no exposed L2 round trips.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int hf = ew >> 2;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t t_acc = tmem_base + lane_sel + CF_T_ACC;
+    const uint32_t t_ahi = tmem_base + lane_sel + CF_T_AHI, t_alo = tmem_base + lane_sel + CF_T_ALO;
+    const bool training = p.training != 0;
+    Stager st;
+    st.slots = slots_a + (uint32_t)(2 * hf) * (uint32_t)CF_SLOT_BYTES;
+    st.op = 0;
+    st.bar_id = 1 + hf;
+    st.issuer = ((ew & 3) == 0) && lane == 0;
+    st.row_off = (uint32_t)(q * 32 + lane) * 128u;
+    st.swz = (uint32_t)(lane & 7);
+    const uint32_t cdiv = p.ctx_div <= 0 ? 0xFFFFFFFFu : (uint32_t)p.ctx_div;
+    uint32_t n_af[2] = {0u, 0u};
+    int es = 256;    // trace slot (epilogue warp 2: 256..511)
+    auto wait_acc = [&](int b) {
+      mbar_wait(&acc_full[b], n_af[b] & 1u);
+      ++n_af[b];
+      tcgen05_fence_after();
+      if (threadIdx.x == 64) { CF_TRACE(es); ++es; }
+    };
+    auto operand_done = [&]() {
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+      if (threadIdx.x == 64) { CF_TRACE(es); ++es; }
+    };
+    auto ldg16 = [](const float* src, float4 (&g)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = __ldg(reinterpret_cast<const float4*>(src + 4 * j));
+    };
+    // biases of the first CF_SB_BLOCKS blocks: [k][b1 | b2][128] in shared memory (broadcast reads)
+    const uint32_t sbias_a = smem_u32(sbias) + (uint32_t)hf * 256u;
+    float hres[4][16];      // this row's residual stream, columns hf*64 .. hf*64+63
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row0 = tile * CF_BM;
+      const int64_t m = row0 + q * 32 + lane;
+      const int64_t mc = m < p.R ? m : p.R - 1;
+      const float* ctx_row = p.ctx + (int64_t)((uint32_t)mc / cdiv) * p.ldg + hf * 64;
+      float4 aux[4], nxt[4];
+
+      {  // ---- theta tile -> operand columns [hf*16, hf*16+16)
+        float w[16], hi[16], lo[16];
+        const float* tp = p.theta + mc * p.D + hf * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (hf * 16 + 4 * j < p.D) v = __ldg(reinterpret_cast<const float4*>(tp + 4 * j));
+          w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+        }
+        ldg16(ctx_row, aux);                  // first context piece of the initial layer, ahead of its accumulator
+        split16(w, hi, lo);
+        tmem_st_16(t_ahi + hf * 16, hi);
+        tmem_st_16(t_alo + hf * 16, lo);
+        operand_done();
+      }
+
+      {  // ---- initial layer: h0 = acc + ctx slot 0
+        wait_acc(0);
+        uint32_t slot = 0;
+        if (training) slot = st.begin();
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+          float v[16], x[16], hi[16], lo[16];
+          const uint32_t col = (uint32_t)(hf * 64 + pc * 16);
+          if (pc < 3) ldg16(ctx_row + (pc + 1) * 16, nxt);
+          else ldg16(ctx_row + 128, nxt);     // first gate piece of block 0
+          tmem_ld_2x16(t_acc + col, t_acc + 128u + col, v, x);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[4 * j] += x[4 * j] + aux[j].x; v[4 * j + 1] += x[4 * j + 1] + aux[j].y;
+            v[4 * j + 2] += x[4 * j + 2] + aux[j].z; v[4 * j + 3] += x[4 * j + 3] + aux[j].w;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { hres[pc][j] = v[j]; x[j] = fmaxf(v[j], 0.f); }
+          if (training) st.put16(slot, pc >> 1, pc & 1, v);
+          split16(x, hi, lo);
+          tmem_st_16(t_ahi + col, hi);
+          tmem_st_16(t_alo + col, lo);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) aux[j] = nxt[j];
+        }
+        if (training) st.end(slot, &maps.h[0], hf * 64, (int)row0, 2);
+        operand_done();
+      }
+
+      for (int k = 0; k < Bk; ++k) {
+        const bool sb = k < CF_SB_BLOCKS;
+        {  // ---- t = acc + b1 ; operand relu(t)            (aux keeps holding the first gate piece of this block)
+          wait_acc(0);
+          uint32_t slot = 0;
+          if (training) slot = st.begin();
+          const float* bp = p.b1[k] + hf * 64;
+          const uint32_t sbp = sbias_a + (uint32_t)k * 1024u;
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            float v[16], x[16], hi[16], lo[16];
+            const uint32_t col = (uint32_t)(hf * 64 + pc * 16);
+            tmem_ld_2x16(t_acc + col, t_acc + 128u + col, v, x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 c = sb ? lds128(sbp + (uint32_t)(pc * 64 + j * 16)) : __ldg(reinterpret_cast<const float4*>(bp + pc * 16 + 4 * j));
+              v[4 * j] += x[4 * j] + c.x; v[4 * j + 1] += x[4 * j + 1] + c.y;
+              v[4 * j + 2] += x[4 * j + 2] + c.z; v[4 * j + 3] += x[4 * j + 3] + c.w;
+            }
+            if (training) st.put16(slot, pc >> 1, pc & 1, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = fmaxf(v[j], 0.f);
+            split16(x, hi, lo);
+            tmem_st_16(t_ahi + col, hi);
+            tmem_st_16(t_alo + col, lo);
+          }
+          if (training) st.end(slot, &maps.t[k], hf * 64, (int)row0, 2);
+          operand_done();
+        }
+        {  // ---- u = acc + b2 ; h += u * gate (slot 1+k of ctx_all holds sigmoid(gate), k_gate_sigmoid) ; operand relu(h)
+           //      (the final layer takes h itself)
+          wait_acc(0);
+          uint32_t slot_u = 0, slot_h = 0;
+          if (training) slot_u = st.begin();
+          const float* bp = p.b2[k] + hf * 64;
+          const uint32_t sbp = sbias_a + (uint32_t)k * 1024u + 512u;
+          const float* gp = ctx_row + 128 * (1 + k);
+          const bool last = (k == Bk - 1);
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            float v[16], x[16], hi[16], lo[16];
+            const uint32_t col = (uint32_t)(hf * 64 + pc * 16);
+            if (pc < 3) ldg16(gp + (pc + 1) * 16, nxt);
+            else if (!last) ldg16(gp + 128, nxt);       // first gate piece of the next block
+            tmem_ld_2x16(t_acc + col, t_acc + 128u + col, v, x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 c = sb ? lds128(sbp + (uint32_t)(pc * 64 + j * 16)) : __ldg(reinterpret_cast<const float4*>(bp + pc * 16 + 4 * j));
+              v[4 * j] += x[4 * j] + c.x; v[4 * j + 1] += x[4 * j + 1] + c.y;
+              v[4 * j + 2] += x[4 * j + 2] + c.z; v[4 * j + 3] += x[4 * j + 3] + c.w;
+            }
+            if (training) st.put16(slot_u, pc >> 1, pc & 1, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              hres[pc][4 * j] = fmaf(v[4 * j], aux[j].x, hres[pc][4 * j]);
+              hres[pc][4 * j + 1] = fmaf(v[4 * j + 1], aux[j].y, hres[pc][4 * j + 1]);
+              hres[pc][4 * j + 2] = fmaf(v[4 * j + 2], aux[j].z, hres[pc][4 * j + 2]);
+              hres[pc][4 * j + 3] = fmaf(v[4 * j + 3], aux[j].w, hres[pc][4 * j + 3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = last ? hres[pc][j] : fmaxf(hres[pc][j], 0.f);
+            split16(x, hi, lo);
+            tmem_st_16(t_ahi + col, hi);
+            tmem_st_16(t_alo + col, lo);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) aux[j] = nxt[j];
+          }
+          if (training) {
+            st.end(slot_u, &maps.u[k], hf * 64, (int)row0, 2);
+            slot_h = st.begin();
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) st.put16(slot_h, pc >> 1, pc & 1, hres[pc]);
+            st.end(slot_h, &maps.h[k + 1], hf * 64, (int)row0, 2);
+          }
+          operand_done();
+        }
+      }
+
+      // ---- final layer: 64-column units, accumulator sets alternate so unit j+1's MMAs overlap this read-out
+      for (int j = 0; j < nF; ++j) {
+        const int b = j & 1;
+        const int n0 = j * 64 + hf * 32;
+        float bias[2][16];
+        if (n0 + 32 <= p.dP) {                  // bias ahead of the accumulator
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 c = __ldg(reinterpret_cast<const float4*>(p.bf + n0 + pc * 16 + 4 * e));
+              bias[pc][4 * e] = c.x; bias[pc][4 * e + 1] = c.y; bias[pc][4 * e + 2] = c.z; bias[pc][4 * e + 3] = c.w;
+            }
+        } else {
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int n = n0 + pc * 16 + e;
+              bias[pc][e] = (n < p.dP) ? __ldg(p.bf + n) : 0.f;
+            }
+        }
+        wait_acc(b);
+        float o[2][16];
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {
+          float x[16];
+          const uint32_t col = (uint32_t)(128 * b + hf * 32 + pc * 16);
+          tmem_ld_2x16(t_acc + col, t_acc + 64u + col, o[pc], x);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[pc][e] += x[e] + bias[pc][e];
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
+        const uint32_t slot = st.begin();
+        st.put16(slot, 0, 0, o[0]);
+        st.put16(slot, 0, 1, o[1]);
+        st.end(slot, &maps.prm, n0, (int)row0, (n0 < p.dP) ? 1 : 0);
+        if (threadIdx.x == 64) { CF_TRACE(es); ++es; }
+      }
+    }
+    if (st.issuer) bulk_wait_all<0>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static long long* g_cf_trace = nullptr;
+
+static bool fused_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FLOPPITY_FUSED");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// Shapes the fused kernel covers (a property of the flow, identical for every layer and every pass)
+bool cond_fwd_supported(const Layout& L, const float* prepared) {
+  if (!tc_enabled() || !fused_enabled() || !prepared) return false;
+  return L.H == 128 && L.D <= 32 && (L.D & 3) == 0 && L.Bk >= 1 && L.Bk <= CF_MAXBK;
+}
+
+// Conditioner forward of layer i as one launch.  h/t/u: saved-activation buffers ([R,128] each) when training, else unused.
+// Returns FP_E_NOTREADY when the shape is outside what the fused kernel covers (the caller then runs the GEMM chain).
+int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
+                    const float* theta_i, const float* ctx_all, int64_t R, int ctx_div, float* const* h, float* const* t,
+                    float* const* u, float* prm, bool training, cudaStream_t stream) {
+  if (!cond_fwd_supported(L, prepared)) return FP_E_NOTREADY;
+  if (R < 1 || R > 2147483647LL - 256) return FP_E_TOOLARGE;
+  if ((reinterpret_cast<uintptr_t>(ctx_all) & 15) || (reinterpret_cast<uintptr_t>(theta_i) & 15)) return FP_E_BADARG;
+  const int dP = L.dP(i);
+  CondFwdMaps maps;
+  const float* hi = prepared + L.prepHi();
+  const float* lo = prepared + L.prepLo();
+  bool ok = true;
+  ok = ok && get_tensor_map(hi + L.w0x(i), 128, L.D, L.D, &maps.w0h);
+  ok = ok && get_tensor_map(lo + L.w0x(i), 128, L.D, L.D, &maps.w0l);
+  ok = ok && get_tensor_map(hi + L.w1(i, 0), (int64_t)L.Bk * 258, 128, 128, &maps.wh);
+  ok = ok && get_tensor_map(lo + L.w1(i, 0), (int64_t)L.Bk * 258, 128, 128, &maps.wl);
+  ok = ok && get_tensor_map(hi + L.wf(i), dP, 128, 128, &maps.wfh, 64);
+  ok = ok && get_tensor_map(lo + L.wf(i), dP, 128, 128, &maps.wfl, 64);
+  ok = ok && get_tensor_map(prm, R, dP, L.ldP(i), &maps.prm);
+  for (int k = 0; k <= CF_MAXBK; ++k) maps.h[k] = maps.prm;
+  for (int k = 0; k < CF_MAXBK; ++k) { maps.t[k] = maps.prm; maps.u[k] = maps.prm; }
+  if (training) {
+    for (int k = 0; k <= L.Bk && ok; ++k) ok = get_tensor_map(h[k], R, 128, 128, &maps.h[k]);
+    for (int k = 0; k < L.Bk && ok; ++k) ok = get_tensor_map(t[k], R, 128, 128, &maps.t[k]) && get_tensor_map(u[k], R, 128, 128, &maps.u[k]);
+  }
+  if (!ok) return FP_E_NOTREADY;
+  CondFwdParams p{};
+  p.theta = theta_i; p.D = L.D;
+  p.ctx = ctx_all + L.ctxCol(i, 0); p.ldg = L.Nctx; p.ctx_div = ctx_div;
+  for (int k = 0; k < L.Bk; ++k) { p.b1[k] = params + L.b1(i, k); p.b2[k] = params + L.b2(i, k); }
+  p.bf = params + L.bf(i);
+  p.R = R; p.Bk = L.Bk; p.dP = dP; p.training = training ? 1 : 0;
+  p.trace = g_cf_trace;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t tiles = (R + CF_BM - 1) / CF_BM;
+  const int grid = (int)std::min<int64_t>(tiles, num_sms());
+  const double flops = 2.0 * (double)R * ((double)L.D * 128 + (double)L.Bk * 2 * 128 * 128 + 128.0 * dP);
+  const double bytes = 4.0 * ((double)R * (L.D + dP + (training ? (3.0 * L.Bk + 1) * 128 : 0.0)) +
+                              (double)(128 * L.D + L.Bk * 2 * 128 * 128 + dP * 128) * 2);
+  ProfScope ps(TAG_GEMM_TC, flops, stream, bytes);
+  static int pdl_on = -1;
+  if (pdl_on < 0) { const char* e = getenv("FLOPPITY_PDL"); pdl_on = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid, 1, 1);
+  lc.blockDim = dim3(CF_THREADS, 1, 1);
+  lc.dynamicSmemBytes = CF_SMEM_BYTES;
+  lc.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = pdl_on ? 1 : 0;
+  FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd, maps, p));
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace fp
+
+extern "C" {
+// debug: device buffer of >= 512 int64 receiving SM-clock stamps of CTA 0 of the fused conditioner (NULL = off)
+int fp_cf_set_trace(void* buf) { fp::g_cf_trace = reinterpret_cast<long long*>(buf); return 0; }
+}

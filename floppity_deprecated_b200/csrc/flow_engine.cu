@@ -24,6 +24,9 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream);
 int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
 int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params, float* t_hi, float* t_lo, cudaStream_t stream);
 bool tc_enabled();
+int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
+                    const float* theta_i, const float* ctx_all, int64_t R, int ctx_div, float* const* h, float* const* t,
+                    float* const* u, float* prm, bool training, cudaStream_t stream);       // cond_fused.cu
 int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                      float* theta_out, float* theta_sp, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status,
                      const float* luM, const float* luPre, float pre_sign, const float* luPost,
@@ -38,7 +41,9 @@ int launch_affine_bwd(const float*, const float*, float*, int64_t, int, cudaStre
 int launch_base_logprob(const float*, const float*, float*, int64_t, int, int32_t*, cudaStream_t);
 int launch_base_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
 int launch_rows_affine(const float*, const float*, const float*, float, const float*, float*, int64_t, int, cudaStream_t);
-int launch_glu_bwd(const float*, const float*, const float*, int64_t, float*, float*, int64_t, int, int, cudaStream_t);
+int launch_glu_bwd(const float*, const float*, const float*, int64_t, float*, float*, int64_t, int, int, int, cudaStream_t);
+int launch_gate_sigmoid(float*, int64_t, int64_t, int, int, cudaStream_t);
+bool cond_fwd_supported(const Layout& L, const float* prepared);      // cond_fused.cu
 int launch_ctx_reduce(const float*, float*, int64_t, int64_t, int, int, cudaStream_t);
 int launch_colsum(const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int launch_sum(const float*, int64_t, float, float*, cudaStream_t);
@@ -144,6 +149,13 @@ static inline uint64_t layer_seed(uint64_t seed, int layer, int block) {
   return seed * 0x9E3779B97F4A7C15ull + (uint64_t)(layer * 64 + block + 1) * 0xD6E8FEB86659FD93ull;
 }
 
+// One decision per flow pass: does every layer's conditioner run as the fused kernel (cond_fused.cu)?  Dropout draws
+// masks inside the GEMM prologues, so a training pass with dropout keeps the GEMM chain.
+static bool use_fused(const fp_nsf_config* cfg, const Layout& L, const float* prepared, bool training) {
+  if (training && cfg->dropout_p > 0.f) return false;
+  return cond_fwd_supported(L, prepared);
+}
+
 // conditioner forward of layer i: theta_i [R, D] -> spline params [R, dP_i]
 // h buffers: h(b) for b = 0..Bk (may alias when not training), t(b), u(b) (NULL when not training)
 struct CondBufs {
@@ -156,9 +168,13 @@ struct CondBufs {
 static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
                                const float* theta_i,
                                const float* ctx_all, int64_t R, int ctx_div, const CondBufs& b, bool training,
-                               uint64_t seed, cudaStream_t s) {
+                               uint64_t seed, bool fused, cudaStream_t s) {
   const int H = L.H, D = L.D;
   const float drop = training ? cfg->dropout_p : 0.f;
+  if (fused) {   // hidden 128: the whole chain in one persistent tcgen05 kernel (activations stay in TMEM); the gate
+                 // slots of ctx_all already hold sigmoid(gate), so there is no falling back to the GEMM chain from here
+    return launch_cond_fwd(cfg, L, params, prepared, i, theta_i, ctx_all, R, ctx_div, b.h, b.t, b.u, b.prm, training, s);
+  }
   {  // initial layer: h0 = theta_i @ W0x^T + (ctx @ W0ctx^T + b0)   [the bracket is a column block of ctx_all]
     fp_gemm_args g = gemm_nt(theta_i, D, params + L.w0x(i), D, b.h[0], H, R, H, D, FP_G_ADD_CTX);
     g.G = ctx_all + L.ctxCol(i, 0); g.ldg = L.Nctx; g.ctx_div = ctx_div;
@@ -299,6 +315,8 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
   float* ctx_all = ws + W.ctx_all;
   float* logdet = ws + W.logdet;
   FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
+  const bool fused = use_fused(cfg, L, prepared, training != 0);
+  if (fused) FP_TRY(launch_gate_sigmoid(ctx_all, Rc, L.Nctx, L.H, L.S, s));
 
   float* th_cur = training ? ws + W.thst(0) : ws + W.th_a;
   FP_TRY(launch_affine_fwd(theta, zshift, zscale, zlogdet, th_cur, logdet, R, D, s));
@@ -318,7 +336,7 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
       b.prm = ws + W.prm;
       th_next = (th_cur == ws + W.th_a) ? ws + W.th_b : ws + W.th_a;
     }
-    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, s));
+    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, fused, s));
     FP_TRY(launch_rqs_apply(false, cfg, i & 1, th_cur, b.prm, th_next, th_sp, logdet, nullptr, R, status,
                             prepared + L.prepM(i), nullptr, 1.f, params + L.luBias(i), prepared + L.prepLogdet(i), L.ldP(i), s));
     th_cur = th_next;
@@ -340,6 +358,7 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
   const int A = (int)(R / Rc);
   const int D = L.D, H = L.H;
   const float drop = cfg->dropout_p;
+  const int sig_given = use_fused(cfg, L, prepared, true) ? 1 : 0;     // same decision as the forward pass that filled ws
 
   float* dth_a = ws + W.dth_a; float* dth_b = ws + W.dth_b;
   float* dh = ws + W.dh; float* dt = ws + W.dt; float* du = ws + W.du; float* dprm = ws + W.dprm;
@@ -364,7 +383,7 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
     for (int k = L.Bk - 1; k >= 0; --k) {
       const uint64_t seed = layer_seed(dropout_seed, i, k);
       FP_TRY(launch_glu_bwd(dh, ws + W.ubuf(i, k), ctx_all + L.ctxCol(i, 1 + k), L.Nctx, du,
-                            dctx_all + L.ctxCol(i, 1 + k), Rc, A, H, s));
+                            dctx_all + L.ctxCol(i, 1 + k), Rc, A, H, sig_given, s));
       FP_TRY(wgrad(du, H, H, ws + W.tbuf(i, k), H, H, R, grads + L.w2(i, k), H,
                    FP_G_RELU_B | (drop > 0.f ? 1024 : 0), drop, seed, H, s, grads + L.b2(i, k)));
       FP_TRY(dgrad_weight(L, prepared, L.tW2(i, k), H, du, H, H, params + L.w2(i, k), H, H, R, dt, H,
@@ -400,6 +419,8 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
   const int D = L.D;
   float* ctx_all = ws + W.ctx_all;
   FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
+  const bool fused = use_fused(cfg, L, prepared, false);
+  if (fused) FP_TRY(launch_gate_sigmoid(ctx_all, Rc, L.Nctx, L.H, L.S, s));
 
   // inverse of the last LULinear on the base noise
   float* th_cur = ws + W.th_a; float* th_next = ws + W.th_b;
@@ -409,7 +430,7 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
     for (int k = 0; k <= L.Bk; ++k) b.h[k] = ws + W.h;
     for (int k = 0; k < L.Bk; ++k) { b.t[k] = ws + W.t; b.u[k] = nullptr; }
     b.prm = ws + W.prm;
-    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, false, 0, s));
+    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, false, 0, fused, s));
     // spline inverse of layer i fused with the inverse LULinear of layer i-1
     const float* M = (i > 0) ? prepared + L.prepMinv(i - 1) : nullptr;
     const float* pre = (i > 0) ? params + L.luBias(i - 1) : nullptr;

@@ -83,13 +83,15 @@ __global__ void k_rows_affine(const float* __restrict__ x, const float* __restri
 // ---- GLU backward (nflows ResidualBlock: temps = glu(cat(temps, context_layer(ctx)))) -----------------
 // h_next = h + u*sigmoid(G).  dh is the gradient wrt h_next (and, unchanged, wrt h via the residual).
 // du = dh*sig ; dG[cr] = sum over the `A` rows sharing context row cr of dh*u*sig*(1-sig).
+// sig_given: G already holds sigmoid(gate) (the fused conditioner path applies k_gate_sigmoid to the context projection).
 __global__ void k_glu_bwd(const float* __restrict__ dh, const float* __restrict__ u, const float* __restrict__ G,
-                          int64_t ldg, float* __restrict__ du, float* __restrict__ dG, int64_t Rc, int A, int H) {
+                          int64_t ldg, float* __restrict__ du, float* __restrict__ dG, int64_t Rc, int A, int H,
+                          int sig_given) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Rc * H) return;
   int64_t cr = i / H; int j = (int)(i - cr * H);
   float g = G[cr * ldg + j];
-  float sg = 1.f / (1.f + expf(-g));
+  float sg = sig_given ? g : 1.f / (1.f + expf(-g));
   float acc = 0.f;
   for (int a = 0; a < A; ++a) {
     int64_t r = cr * A + a;
@@ -98,6 +100,18 @@ __global__ void k_glu_bwd(const float* __restrict__ dh, const float* __restrict_
     acc = fmaf(d, u[r * H + j], acc);
   }
   dG[cr * ldg + j] = acc * sg * (1.f - sg);
+}
+// in place: gate slots (every slot but the first of each layer) of the context projection [Rc, T*S*H] -> sigmoid
+__global__ void k_gate_sigmoid(float* __restrict__ ctx_all, int64_t n4, int H, int S) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    // rows are a whole number of slots, so the slot index of flat element e is simply (e / H) % S
+    const int64_t e = i * 4;
+    if (((e / H) % S) == 0) continue;
+    float4 v = reinterpret_cast<float4*>(ctx_all)[i];
+    v.x = 1.f / (1.f + expf(-v.x)); v.y = 1.f / (1.f + expf(-v.y));
+    v.z = 1.f / (1.f + expf(-v.z)); v.w = 1.f / (1.f + expf(-v.w));
+    reinterpret_cast<float4*>(ctx_all)[i] = v;
+  }
 }
 // first-layer context gradient: dG[cr, j] = sum_a dh[cr*A+a, j]
 __global__ void k_ctx_reduce(const float* __restrict__ dh, float* __restrict__ dG, int64_t ldg, int64_t Rc, int A, int H) {
@@ -452,9 +466,17 @@ int launch_rows_affine(const float* x, const float* M, const float* pre, float s
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_glu_bwd(const float* dh, const float* u, const float* G, int64_t ldg, float* du, float* dG, int64_t Rc, int A,
-                   int H, cudaStream_t s) {
+                   int H, int sig_given, cudaStream_t s) {
   ProfScope ps(TAG_OTHER, 0.0, s);
-  k_glu_bwd<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, u, G, ldg, du, dG, Rc, A, H);
+  k_glu_bwd<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, u, G, ldg, du, dG, Rc, A, H, sig_given);
+  FP_LAUNCH_CHECK(); return 0;
+}
+// requires H % 4 == 0 and a 16-byte aligned buffer
+int launch_gate_sigmoid(float* ctx_all, int64_t Rc, int64_t Nctx, int H, int S, cudaStream_t s) {
+  const int64_t n4 = Rc * Nctx / 4;
+  if (n4 <= 0) return 0;
+  ProfScope ps(TAG_OTHER, 0.0, s);
+  k_gate_sigmoid<<<(unsigned)std::min<int64_t>((n4 + 255) / 256, 16 * (int64_t)num_sms()), 256, 0, s>>>(ctx_all, n4, H, S);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_ctx_reduce(const float* dh, float* dG, int64_t ldg, int64_t Rc, int A, int H, cudaStream_t s) {

@@ -139,6 +139,8 @@ int fp_tc_set_trace(void* buf);
 /* debug: ablation switches for timing experiments on the weight-gradient kernel (1 skip split, 2 skip reductions,
  * 4 two of three products); results are wrong while non-zero */
 int fp_tc_set_debug(int32_t bits);
+/* debug: SM-clock stamps of CTA 0 of the fused conditioner kernel (cond_fused.cu) into a device int64[512] (NULL = off) */
+int fp_cf_set_trace(void* buf);
 
 /* ---- whole-flow entry points --------------------------------------------------------------- */
 /* Derive per-step constants from the parameters (W = L*U, L, U, sum log diag U). */
