@@ -15,8 +15,9 @@
 //     tile boundaries;
 //   * the only global traffic is theta in, the spline parameters out and -- in training mode -- the saved activations
 //     (h_k, t_k, u_k) out, staged in shared memory and written by TMA tensor stores.
-// TMEM map (512 columns): [0,256) accumulators (hi*hi | cross terms; two 64-wide sets for the final layer so its
-// epilogue overlaps the next MMAs), [256,384) operand hi, [384,512) operand lo.
+// TMEM map (512 columns): [0,128) hi*hi accumulator, [128,256) cross-term accumulator, [256,384) operand hi,
+// [384,512) operand lo.  (tcgen05.mma kind::tf32 reads 32 bytes of every A row per instruction, so an MMA costs
+// ~75 cycles for any N <= 128: narrower N units do not pay -- every GEMM of the chain is issued at N = 128.)
 #include "common.cuh"
 #include "prof.h"
 #include "layout.h"
@@ -43,7 +44,7 @@ constexpr uint32_t CF_T_ACC = 0, CF_T_AHI = 256, CF_T_ALO = 384;
 struct CondFwdMaps {
   CUtensorMap w0h, w0l;       // W0x hi / lo   [128, D]
   CUtensorMap wh, wl;         // blocks: rows k*258 = W1_k, k*258+129 = W2_k   [Bk*258, 128]
-  CUtensorMap wfh, wfl;       // Wf hi / lo    [dP, 128], 64-row boxes
+  CUtensorMap wfh, wfl;       // Wf hi / lo    [dP, 128]
   CUtensorMap prm;            // spline parameters out [R, dP]
   CUtensorMap h[CF_MAXBK + 1], t[CF_MAXBK], u[CF_MAXBK];   // saved activations out [R, 128] (training)
 };
@@ -81,6 +82,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
                ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -99,12 +101,31 @@ struct Stager {
     named_bar_sync(bar_id, 128);
     return slots + (op & 1u) * (uint32_t)CF_SLOT_BYTES;
   }
+  // both slots at once (a phase with two results): every earlier store of this half has been read out
+  __device__ __forceinline__ void begin2(uint32_t& s0, uint32_t& s1) {
+    if (issuer) bulk_wait_read<0>();
+    named_bar_sync(bar_id, 128);
+    s0 = slots + (op & 1u) * (uint32_t)CF_SLOT_BYTES;
+    s1 = slots + ((op + 1u) & 1u) * (uint32_t)CF_SLOT_BYTES;
+  }
   // 16 consecutive floats of this thread's row: columns [piece*16, piece*16+16) of 32-column box `box`
   __device__ __forceinline__ void put16(uint32_t slot, int box, int piece, const float (&v)[16]) const {
     const uint32_t base = slot + (uint32_t)box * (uint32_t)CF_TILE_BYTES + row_off;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       sts128(base + ((((uint32_t)(piece * 4 + j)) ^ swz) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+  }
+  // two 64-column results (both slots) in one hand-over
+  __device__ __forceinline__ void end2(uint32_t s0, const CUtensorMap* m0, uint32_t s1, const CUtensorMap* m1, int col0, int row0) {
+    fence_proxy_async_smem();
+    named_bar_sync(bar_id, 128);
+    if (issuer) {
+      for (int b = 0; b < 2; ++b) tma_store_2d(m0, s0 + (uint32_t)b * (uint32_t)CF_TILE_BYTES, col0 + 32 * b, row0);
+      bulk_commit();
+      for (int b = 0; b < 2; ++b) tma_store_2d(m1, s1 + (uint32_t)b * (uint32_t)CF_TILE_BYTES, col0 + 32 * b, row0);
+      bulk_commit();
+    }
+    op += 2;
   }
   __device__ __forceinline__ void end(uint32_t slot, const CUtensorMap* map, int col0, int row0, int nbox) {
     fence_proxy_async_smem();
@@ -142,7 +163,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (p.R + CF_BM - 1) / CF_BM;
   const int Bk = p.Bk;
-  const int nF = (p.dP + 63) / 64;              // 64-column units of the final layer
+  const int nF = (p.dP + 127) / 128;            // 128-column units of the final layer
   const int ks0 = (p.D + 7) / 8;                // k-steps of the initial layer (K = D <= 32)
 
   if (threadIdx.x == 0) {
@@ -189,16 +210,16 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
           for (int g = 0; g < 2; ++g)
             for (int kb = 0; kb < 4; ++kb) stage(&maps.wh, &maps.wl, kb * 32, k * 258 + g * 129, 2 * CF_TILE_BYTES);
         for (int j = 0; j < nF; ++j)
-          for (int kb = 0; kb < 4; ++kb) stage(&maps.wfh, &maps.wfl, kb * 32, j * 64, CF_TILE_BYTES);
+          for (int kb = 0; kb < 4; ++kb) stage(&maps.wfh, &maps.wfl, kb * 32, j * 128, 2 * CF_TILE_BYTES);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc128 = make_idesc_tf32(128, 128);
-      constexpr uint32_t idesc64 = make_idesc_tf32(128, 64);
       const uint32_t t_ahi = tmem_base + CF_T_AHI, t_alo = tmem_base + CF_T_ALO;
-      uint32_t it = 0, n_ar = 0, n_gf[2] = {0u, 0u};
+      uint32_t it = 0, n_ar = 0, n_ae = 0;
+      int pend = 0;          // final-layer units whose read-out has not been awaited yet
       // one k-block (ring stage) of a GEMM unit: nk k-steps of 8, operand columns from acol
       auto kblock = [&](uint32_t d_hh, uint32_t d_x, uint32_t acol, int nk, uint32_t idesc, bool first) {
         const int s = it % CF_WSTAGES;
@@ -222,10 +243,17 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         ++n_ar;
         tcgen05_fence_after();
       };
+      auto wait_drained = [&]() {
+        mbar_wait(&acc_empty[0], n_ae & 1u);
+        ++n_ae;
+        --pend;
+        tcgen05_fence_after();
+      };
       const uint32_t d_hh = tmem_base + CF_T_ACC, d_x = d_hh + 128;
       int ts = 0;     // trace slot (MMA: 0..255)
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         wait_operand();                                   // theta tile split into the operand columns
+        while (pend > 0) wait_drained();                  // (already true by program order: keeps the phase count in step)
         CF_TRACE(ts); ++ts;
         kblock(d_hh, d_x, 0, ks0, idesc128, true);
         umma_commit(&acc_full[0]);
@@ -240,15 +268,10 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         wait_operand();                                   // final hidden state
         CF_TRACE(ts); ++ts;
         for (int j = 0; j < nF; ++j) {
-          const int b = j & 1;
-          if (n_gf[b] > 0) {                              // the epilogue of the previous unit on this set has drained it
-            mbar_wait(&acc_empty[b], (n_gf[b] - 1) & 1u);
-            tcgen05_fence_after();
-          }
-          const uint32_t f_hh = tmem_base + CF_T_ACC + 128u * b, f_x = f_hh + 64;
-          for (int kb = 0; kb < 4; ++kb) kblock(f_hh, f_x, 32u * kb, 4, idesc64, kb == 0);
-          umma_commit(&acc_full[b]);
-          ++n_gf[b];
+          if (pend > 0) wait_drained();                   // the read-out of the previous unit has drained the accumulators
+          for (int kb = 0; kb < 4; ++kb) kblock(d_hh, d_x, 32u * kb, 4, idesc128, kb == 0);
+          umma_commit(&acc_full[0]);
+          ++pend;
           CF_TRACE(ts); ++ts;
         }
       }
@@ -313,6 +336,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
           w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
         }
         ldg16(ctx_row, aux);                  // first context piece of the initial layer, ahead of its accumulator
+        prefetch_l1(ctx_row + 32);
         split16(w, hi, lo);
         tmem_st_16(t_ahi + hf * 16, hi);
         tmem_st_16(t_alo + hf * 16, lo);
@@ -320,9 +344,9 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
       }
 
       {  // ---- initial layer: h0 = acc + ctx slot 0
-        wait_acc(0);
         uint32_t slot = 0;
-        if (training) slot = st.begin();
+        if (training) slot = st.begin();      // slot hand-shake while the MMAs run; the store itself after the hand-over
+        wait_acc(0);
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) {
           float v[16], x[16], hi[16], lo[16];
@@ -344,16 +368,18 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) aux[j] = nxt[j];
         }
-        if (training) st.end(slot, &maps.h[0], hf * 64, (int)row0, 2);
         operand_done();
+        if (training) st.end(slot, &maps.h[0], hf * 64, (int)row0, 2);
+        prefetch_l1(ctx_row + 128);           // gate rows of block 0 (used two phases from now)
+        prefetch_l1(ctx_row + 128 + 32);
       }
 
       for (int k = 0; k < Bk; ++k) {
         const bool sb = k < CF_SB_BLOCKS;
         {  // ---- t = acc + b1 ; operand relu(t)            (aux keeps holding the first gate piece of this block)
-          wait_acc(0);
           uint32_t slot = 0;
           if (training) slot = st.begin();
+          wait_acc(0);
           const float* bp = p.b1[k] + hf * 64;
           const uint32_t sbp = sbias_a + (uint32_t)k * 1024u;
 #pragma unroll
@@ -374,14 +400,14 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
             tmem_st_16(t_ahi + col, hi);
             tmem_st_16(t_alo + col, lo);
           }
-          if (training) st.end(slot, &maps.t[k], hf * 64, (int)row0, 2);
           operand_done();
+          if (training) st.end(slot, &maps.t[k], hf * 64, (int)row0, 2);
         }
         {  // ---- u = acc + b2 ; h += u * gate (slot 1+k of ctx_all holds sigmoid(gate), k_gate_sigmoid) ; operand relu(h)
            //      (the final layer takes h itself)
-          wait_acc(0);
           uint32_t slot_u = 0, slot_h = 0;
-          if (training) slot_u = st.begin();
+          if (training) st.begin2(slot_u, slot_h);
+          wait_acc(0);
           const float* bp = p.b2[k] + hf * 64;
           const uint32_t sbp = sbias_a + (uint32_t)k * 1024u + 512u;
           const float* gp = ctx_row + 128 * (1 + k);
@@ -415,56 +441,55 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) aux[j] = nxt[j];
           }
+          operand_done();
           if (training) {
-            st.end(slot_u, &maps.u[k], hf * 64, (int)row0, 2);
-            slot_h = st.begin();
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) st.put16(slot_h, pc >> 1, pc & 1, hres[pc]);
-            st.end(slot_h, &maps.h[k + 1], hf * 64, (int)row0, 2);
+            st.end2(slot_u, &maps.u[k], slot_h, &maps.h[k + 1], hf * 64, (int)row0);
           }
-          operand_done();
+          if (!last) { prefetch_l1(gp + 128); prefetch_l1(gp + 128 + 32); }    // gate rows of the next block
         }
       }
 
-      // ---- final layer: 64-column units, accumulator sets alternate so unit j+1's MMAs overlap this read-out
+      // ---- final layer: 128-column units.  The residual registers are dead by now, so a unit's 64 columns are drained
+      //      into registers at once and the accumulators handed back: bias, staging and the TMA store of unit j run
+      //      under the MMAs of unit j+1.
       for (int j = 0; j < nF; ++j) {
-        const int b = j & 1;
-        const int n0 = j * 64 + hf * 32;
-        float bias[2][16];
-        if (n0 + 32 <= p.dP) {                  // bias ahead of the accumulator
+        wait_acc(0);
+        float o[4][16];
 #pragma unroll
-          for (int pc = 0; pc < 2; ++pc)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 c = __ldg(reinterpret_cast<const float4*>(p.bf + n0 + pc * 16 + 4 * e));
-              bias[pc][4 * e] = c.x; bias[pc][4 * e + 1] = c.y; bias[pc][4 * e + 2] = c.z; bias[pc][4 * e + 3] = c.w;
-            }
-        } else {
-#pragma unroll
-          for (int pc = 0; pc < 2; ++pc)
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int n = n0 + pc * 16 + e;
-              bias[pc][e] = (n < p.dP) ? __ldg(p.bf + n) : 0.f;
-            }
-        }
-        wait_acc(b);
-        float o[2][16];
-#pragma unroll
-        for (int pc = 0; pc < 2; ++pc) {
+        for (int pc = 0; pc < 4; ++pc) {
           float x[16];
-          const uint32_t col = (uint32_t)(128 * b + hf * 32 + pc * 16);
-          tmem_ld_2x16(t_acc + col, t_acc + 64u + col, o[pc], x);
+          const uint32_t col = (uint32_t)(hf * 64 + pc * 16);
+          tmem_ld_2x16(t_acc + col, t_acc + 128u + col, o[pc], x);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) o[pc][e] += x[e] + bias[pc][e];
+          for (int e = 0; e < 16; ++e) o[pc][e] += x[e];
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[b]);
+        if (lane == 0) mbar_arrive(&acc_empty[0]);
+        const int n0 = j * 128 + hf * 64;
+        if (n0 + 64 <= p.dP) {
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 c = __ldg(reinterpret_cast<const float4*>(p.bf + n0 + pc * 16 + 4 * e));
+              o[pc][4 * e] += c.x; o[pc][4 * e + 1] += c.y; o[pc][4 * e + 2] += c.z; o[pc][4 * e + 3] += c.w;
+            }
+        } else {
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int n = n0 + pc * 16 + e;
+              o[pc][e] += (n < p.dP) ? __ldg(p.bf + n) : 0.f;
+            }
+        }
         const uint32_t slot = st.begin();
-        st.put16(slot, 0, 0, o[0]);
-        st.put16(slot, 0, 1, o[1]);
-        st.end(slot, &maps.prm, n0, (int)row0, (n0 < p.dP) ? 1 : 0);
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) st.put16(slot, pc >> 1, pc & 1, o[pc]);
+        st.end(slot, &maps.prm, n0, (int)row0, (n0 < p.dP ? 1 : 0) + (n0 + 32 < p.dP ? 1 : 0));
         if (threadIdx.x == 64) { CF_TRACE(es); ++es; }
       }
     }
@@ -509,8 +534,8 @@ int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* para
   ok = ok && get_tensor_map(lo + L.w0x(i), 128, L.D, L.D, &maps.w0l);
   ok = ok && get_tensor_map(hi + L.w1(i, 0), (int64_t)L.Bk * 258, 128, 128, &maps.wh);
   ok = ok && get_tensor_map(lo + L.w1(i, 0), (int64_t)L.Bk * 258, 128, 128, &maps.wl);
-  ok = ok && get_tensor_map(hi + L.wf(i), dP, 128, 128, &maps.wfh, 64);
-  ok = ok && get_tensor_map(lo + L.wf(i), dP, 128, 128, &maps.wfl, 64);
+  ok = ok && get_tensor_map(hi + L.wf(i), dP, 128, 128, &maps.wfh);
+  ok = ok && get_tensor_map(lo + L.wf(i), dP, 128, 128, &maps.wfl);
   ok = ok && get_tensor_map(prm, R, dP, L.ldP(i), &maps.prm);
   for (int k = 0; k <= CF_MAXBK; ++k) maps.h[k] = maps.prm;
   for (int k = 0; k < CF_MAXBK; ++k) { maps.t[k] = maps.prm; maps.u[k] = maps.prm; }
