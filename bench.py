@@ -34,11 +34,14 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4"])
-    ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (rows of (theta, x) pairs)")
+    ap.add_argument("--batch", type=int, default=9472,
+                    help="per-GPU batch (rows of (theta, x) pairs).  Default 9472 = 148 SMs x 64: with atoms 10 a step is "
+                         "94 720 flow rows = 740 row tiles of 128 = exactly 5 per SM, so the persistent kernels run whole "
+                         "waves (4096 leaves 2.16 tiles per SM: 3 waves of work for 2.16 waves of rows)")
     ap.add_argument("--loss", default="atomic", choices=["atomic", "mle"],
                     help="atomic = SNPE-C APT loss with `atoms` contrastive proposals (subsystem 3); mle = the branch "
                          "the reference actually takes (force_first_round_loss=True, floppity.py:220)")
-    ap.add_argument("--rows", type=int, default=16384, help="resident dataset rows per GPU")
+    ap.add_argument("--rows", type=int, default=65536, help="resident dataset rows per GPU (c2: 50k pairs/round -> 65 536)")
     ap.add_argument("--ref-batch", type=int, default=256, help="bounded per-step sample for the CPU arm")
     ap.add_argument("--graph", type=int, default=0, help="replay the optimiser step from a CUDA graph")
     ap.add_argument("--no-extras", action="store_true")

@@ -319,6 +319,15 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// Stage geometry of the weight-gradient kernel.  (Measured: 16-row stages in a six-deep ring are SLOWER than 32-row
+// stages in a three-deep one -- 15.1 vs 14.2 us for [40960 x 128]^T [40960 x 128] -- twice the TMA requests and barrier
+// hand-offs outweigh the extra loads in flight; gpurun_out/tn_ablate*.log.)
+constexpr int TN_BK = 32, TN_STAGES = 3;
+constexpr int TN_TILE_BYTES = TC_BM * TN_BK * 4;           // 8 KB: 16 batch rows x 128 columns
+constexpr int TN_STAGE_BYTES = 4 * TN_TILE_BYTES;          // A(raw->hi), A_lo, B(raw->hi), B_lo
+static_assert(TN_STAGES * TN_STAGE_BYTES == TC_STAGES * TC_STAGE_BYTES, "the TN ring reuses the NT kernel's shared-memory budget");
+static_assert(3 * TN_STAGES * 8 + 2 * 2 * 8 + 8 <= 256, "barrier block");
+
 // ---------------------------------------------------------------------------------------------------------
 // TN variant (weight gradients): C[M,N] += sum_r A[r,M] * B[r,N], both operands row-major over the batch index r
 // (MN-major for the tensor core), contraction over r split across CTAs, partial tiles added with vector atomics.
@@ -330,11 +339,11 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_a = smem_u32(smem);                                  // shared-space address of the ring
-  const uint32_t cs_a = smem_a + TC_STAGES * TC_STAGE_BYTES;              // epilogue staging slabs
-  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES);
-  uint64_t* ready = full_raw + TC_STAGES;
-  uint64_t* empty = ready + TC_STAGES;
-  uint64_t* acc_full = empty + TC_STAGES;      // [2]
+  const uint32_t cs_a = smem_a + TN_STAGES * TN_STAGE_BYTES;              // epilogue staging slabs
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem + TN_STAGES * TN_STAGE_BYTES + TC_CS_BYTES);
+  uint64_t* ready = full_raw + TN_STAGES;
+  uint64_t* empty = ready + TN_STAGES;
+  uint64_t* acc_full = empty + TN_STAGES;      // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -344,10 +353,10 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const int tiles_m = (int)((g.M + TC_BM - 1) / TC_BM);
   const int64_t n_items = (int64_t)tiles_m * tiles_n * nsplit;
   const int kb_per_split = (nkb_total + nsplit - 1) / nsplit;
-  constexpr uint32_t GROUP_BYTES = TC_BK * 128;   // one 32-float MN group: TC_BK k-rows x 128 B
+  constexpr uint32_t GROUP_BYTES = TN_BK * 128;   // one 32-float MN group: TN_BK k-rows x 128 B
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TN_STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -377,15 +386,15 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
         int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (it / TC_STAGES) & 1u;
+          const int s = it % TN_STAGES;
+          const uint32_t ph = (it / TN_STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          uint8_t* sb = smem + s * TC_STAGE_BYTES;
-          mbar_expect_tx(&full_raw[s], 2 * TC_TILE_BYTES);
+          uint8_t* sb = smem + s * TN_STAGE_BYTES;
+          mbar_expect_tx(&full_raw[s], 2 * TN_TILE_BYTES);
 #pragma unroll
           for (int gidx = 0; gidx < 4; ++gidx) {     // four 32-float MN groups per operand
-            tma_load_2d(sb + gidx * GROUP_BYTES, &mapA, m0 + gidx * 32, kb * TC_BK, &full_raw[s]);
-            tma_load_2d(sb + 2 * TC_TILE_BYTES + gidx * GROUP_BYTES, &mapB, n0 + gidx * 32, kb * TC_BK, &full_raw[s]);
+            tma_load_2d(sb + gidx * GROUP_BYTES, &mapA, m0 + gidx * 32, kb * TN_BK, &full_raw[s]);
+            tma_load_2d(sb + 2 * TN_TILE_BYTES + gidx * GROUP_BYTES, &mapB, n0 + gidx * 32, kb * TN_BK, &full_raw[s]);
           }
         }
       }
@@ -404,18 +413,18 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256);
         const uint32_t t_x = t_hh + 128;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (it / TC_STAGES) & 1u;
+          const int s = it % TN_STAGES;
+          const uint32_t ph = (it / TN_STAGES) & 1u;
           mbar_wait(&ready[s], ph);
           tcgen05_fence_after();
-          uint8_t* sb = smem + s * TC_STAGE_BYTES;
+          uint8_t* sb = smem + s * TN_STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
+          for (int k = 0; k < TN_BK / 8; ++k) {
             const uint32_t koff = (uint32_t)k * 1024u;             // 8 k-rows of 128 B
             const uint64_t a_hi = make_mnmajor_desc(sb + koff, GROUP_BYTES);
-            const uint64_t a_lo = make_mnmajor_desc(sb + TC_TILE_BYTES + koff, GROUP_BYTES);
-            const uint64_t b_hi = make_mnmajor_desc(sb + 2 * TC_TILE_BYTES + koff, GROUP_BYTES);
-            const uint64_t b_lo = make_mnmajor_desc(sb + 3 * TC_TILE_BYTES + koff, GROUP_BYTES);
+            const uint64_t a_lo = make_mnmajor_desc(sb + TN_TILE_BYTES + koff, GROUP_BYTES);
+            const uint64_t b_hi = make_mnmajor_desc(sb + 2 * TN_TILE_BYTES + koff, GROUP_BYTES);
+            const uint64_t b_lo = make_mnmajor_desc(sb + 3 * TN_TILE_BYTES + koff, GROUP_BYTES);
             const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
             umma_tf32(t_hh, a_hi, b_hi, idesc, acc);
             umma_tf32(t_x, a_lo, b_hi, idesc, acc);
@@ -431,7 +440,7 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int tid_s = threadIdx.x - 64;
     const bool relu_b = (g.flags & FP_G_RELU_B) != 0;
     // FP_G_COLSUM_A: the bias gradient colsum(A) rides along.  This thread's eight 16-byte chunks of the raw A tile
-    // are chunk (tid_s & 7) of k-rows (tid_s >> 3) + 16 (i & 1) of MN group i >> 1; the 32-byte-atom swizzle XORs the
+    // are chunk (tid_s & 7) of k-row (tid_s >> 3) (+ 16 per further pass over the same group) of successive MN groups; the 32-byte-atom swizzle XORs the
     // 32-byte chunk index with (k-row & 3), which does not depend on i, so the chunk is the same four logical
     // columns for every i & 1 and every k-block: one float4 accumulator per MN group.
     const bool colsum = (g.flags & FP_G_COLSUM_A) != 0;
@@ -443,24 +452,25 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) cs[q4] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1u;
+        const int s = it % TN_STAGES;
+        const uint32_t ph = (it / TN_STAGES) & 1u;
         mbar_wait(&full_raw[s], ph);
-        const uint32_t aA = smem_a + (uint32_t)(s * TC_STAGE_BYTES) + (uint32_t)tid_s * 16u;
+        const uint32_t aA = smem_a + (uint32_t)(s * TN_STAGE_BYTES) + (uint32_t)tid_s * 16u;
         if (!(dbg & 1))
 #pragma unroll
-        for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) {
+        for (int i = 0; i < TN_TILE_BYTES / 16 / 128; ++i) {
           const uint32_t off = aA + (uint32_t)i * 2048u;
           const float4 v = lds128(off);
-          float4 u = lds128(off + 2 * TC_TILE_BYTES);
-          cs[i >> 1].x += v.x; cs[i >> 1].y += v.y; cs[i >> 1].z += v.z; cs[i >> 1].w += v.w;
+          float4 u = lds128(off + 2 * TN_TILE_BYTES);
+          constexpr int IPG = (int)(GROUP_BYTES / 2048u);      // iterations per 32-float MN group
+          cs[i / IPG].x += v.x; cs[i / IPG].y += v.y; cs[i / IPG].z += v.z; cs[i / IPG].w += v.w;
           const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
           sts128(off, h);
-          sts128(off + TC_TILE_BYTES, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+          sts128(off + TN_TILE_BYTES, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
           if (relu_b) { u.x = fmaxf(u.x, 0.f); u.y = fmaxf(u.y, 0.f); u.z = fmaxf(u.z, 0.f); u.w = fmaxf(u.w, 0.f); }
           const float4 hb = make_float4(tf32_round(u.x), tf32_round(u.y), tf32_round(u.z), tf32_round(u.w));
-          sts128(off + 2 * TC_TILE_BYTES, hb);
-          sts128(off + 3 * TC_TILE_BYTES, make_float4(u.x - hb.x, u.y - hb.y, u.z - hb.z, u.w - hb.w));
+          sts128(off + 2 * TN_TILE_BYTES, hb);
+          sts128(off + 3 * TN_TILE_BYTES, make_float4(u.x - hb.x, u.y - hb.y, u.z - hb.z, u.w - hb.w));
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -767,18 +777,19 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return FP_E_NOTREADY;
   if (a->M < 1 || a->N < 1 || a->K < 1 || a->M > 65536) return FP_E_NOTREADY;
   CUtensorMap mA, mB;
-  if (!get_tensor_map(a->A, a->K, a->M, a->lda, &mA, TC_BK, true)) return FP_E_NOTREADY;   // [R rows, M cols]
-  if (!get_tensor_map(a->B, a->K, a->N, a->ldb, &mB, TC_BK, true)) return FP_E_NOTREADY;   // [R rows, N cols]
+  if (!get_tensor_map(a->A, a->K, a->M, a->lda, &mA, TN_BK, true)) return FP_E_NOTREADY;   // [R rows, M cols]
+  if (!get_tensor_map(a->B, a->K, a->N, a->ldb, &mB, TN_BK, true)) return FP_E_NOTREADY;   // [R rows, N cols]
   static bool attr_set = false;
   if (!attr_set) {
     FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  const int nkb = (int)((a->K + TC_BK - 1) / TC_BK);
+  const int nkb = (int)((a->K + TN_BK - 1) / TN_BK);
   const int64_t tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + TC_BN - 1) / TC_BN);
   int nsplit = (int)std::max<int64_t>(1, (num_sms() + tiles - 1) / tiles);
-  nsplit = std::min(nsplit, std::max(1, nkb / 4));         // at least 4 k-blocks (128 batch rows) per split
-  nsplit = std::max(nsplit, (nkb + TC_KCHUNK_BLOCKS - 1) / TC_KCHUNK_BLOCKS);   // bound the truncating accumulation chain
+  nsplit = std::min(nsplit, std::max(1, nkb * TN_BK / 128));   // at least 128 batch rows per split
+  constexpr int kchunk = TC_KCHUNK_BLOCKS * TC_BK / TN_BK;  // bound the truncating accumulation chain (1024 batch rows)
+  nsplit = std::max(nsplit, (nkb + kchunk - 1) / kchunk);
   const int kbps = (nkb + nsplit - 1) / nsplit;
   nsplit = (nkb + kbps - 1) / kbps;                        // no empty splits
   const int grid = (int)std::min<int64_t>(tiles * nsplit, num_sms());

@@ -18,9 +18,9 @@ tail -2 "${OUT}"/bench_*.err | tail -30
 # ncu: launch list of one step + full capture of the dominant GEMM (same command ran plain right before)
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras"
 $CMD > "${OUT}/plain.log" 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 700 --csv --log-file "${OUT}/launches.csv" $CMD > "${OUT}/ncu_list.log" 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 900 -c 450 --csv --log-file "${OUT}/launches.csv" $CMD > "${OUT}/ncu_list.log" 2>&1
 echo "ncu list rc=$?"
 $CMD > "${OUT}/plain2.log" 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc_nt -s 200 -c 3 -o "${OUT}/prof_gemm_tc" $CMD > "${OUT}/ncu_full.log" 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_cond_fwd|k_gemm_tc_tn|k_rqs" -s 60 -c 8 -o "${OUT}/prof_top" $CMD > "${OUT}/ncu_full.log" 2>&1
 echo "ncu full rc=$?"
 ls -la "${OUT}"
