@@ -11,10 +11,10 @@ from . import _lib
 from .flow import NSFFlow, build_nsf, posterior_nn
 from .inference import BoxUniform, DirectPosterior, SNPE_C
 from .density_estimator import NSFDensityEstimator
-from . import utils, synthetic, dist
+from . import utils, synthetic, dist, retrieval
 
 __all__ = ["NSFFlow", "build_nsf", "posterior_nn", "BoxUniform", "DirectPosterior", "SNPE_C",
-           "NSFDensityEstimator", "utils", "synthetic", "dist", "build"]
+           "NSFDensityEstimator", "utils", "synthetic", "dist", "retrieval", "build"]
 
 
 def build(verbose: bool = False) -> str:

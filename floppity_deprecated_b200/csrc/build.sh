@@ -6,7 +6,7 @@ OUT="${HERE}/../libfloppity_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr)
 OBJS=()
-for f in rqs_kernels gemm_simt gemm_tc cond_fused misc_kernels flow_engine prof; do
+for f in rqs_kernels gemm_simt gemm_tc cond_fused misc_kernels retrieval_kernels flow_engine prof; do
   "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/${f}.o" 2> "${HERE}/${f}.ptxas.log" || { cat "${HERE}/${f}.ptxas.log"; exit 1; }
   OBJS+=("${HERE}/${f}.o")
 done

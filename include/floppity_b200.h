@@ -203,6 +203,20 @@ int fp_standardize(const float* x, const float* mean, const float* std, float* o
 /* out[i] = scale*sum(x) accumulated into out[0] */
 int fp_sum(const float* x, int64_t n, float scale, float* out, void* stream);
 /* BoxUniform support test: inside[r] = all(low <= theta[r] <= high) (uint8) */
+/* ---- data-side neighbours of the flow ---------------------------------------------
+ * Noise augmentation + scaling of simulated spectra into fp32 context rows: /root/reference/floppityFUN.py:383-428
+ * (`preprocess`: np.repeat(spec, naug) + noise*randn, then rm_mean / sigma_res_scale, then the fitted StandardScaler
+ * or the PCA centring as (v - shift) / scale).  spec [n_spec, C] fp64, z [n_spec*naug, C] fp32 standard-normal draw,
+ * noise / obs [C] fp64, shift / scale [C (+1 when mode 1)] fp64 or NULL, out [n_spec*naug, ldo] fp32.
+ * mode 0 plain, 1 remove the row mean and append it as column C (floppityFUN.py:229-244), 2 residuals
+ * (v - obs) / noise (floppityFUN.py:196-204). */
+int fp_preprocess_rows(const double* spec, const float* z, const double* noise, const double* obs, const double* shift,
+                       const double* scale, float* out, int64_t n_spec, int32_t C, int32_t naug, int32_t mode,
+                       int64_t ldo, void* stream);
+/* Row-wise Gaussian log-likelihood of model spectra x [rows, C] against the observation (floppityFUN.py:24-28, the
+ * inner loop of IS / evidence, floppityFUN.py:30-91): out[i] = sum_j -log(sqrt(2 pi) err_j) - (obs_j - x_ij)^2 / (2 err_j^2) */
+int fp_gauss_loglik(const double* obs, const double* err, const double* x, double* out, int64_t rows, int32_t C, void* stream);
+
 int fp_within_box(const float* theta, const float* low, const float* high, uint8_t* inside, int64_t R, int32_t D, void* stream);
 
 /* ---- launch accounting (bench.py: gpu_launches and the live roofline numbers) -----------------------
