@@ -33,9 +33,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     import floppity_deprecated_b200 as fb
     from floppity_deprecated_b200 import synthetic, dist as fdist
 
@@ -47,6 +44,12 @@ def main():
     inf = fb.SNPE_C(prior, density_estimator=builder, device=str(dev))
     inf.append_simulations(torch.tensor(theta), torch.tensor(x))
     net = inf.train(training_batch_size=1024, max_num_epochs=args.epochs, stop_after_epochs=args.epochs, seed=0)
+    # The SAME trained flow at every N (so accepted-samples/s are comparable: the acceptance rate is a property of the
+    # model): every rank trains the identical single-process job above, then the group is formed and rank 0's weights win.
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        dist.broadcast(net._flat.data, src=0)
     post = inf.build_posterior(net).set_default_x(torch.tensor(x[:1]))
     post.max_sampling_batch_size = args.chunk
     val_lp = inf._summary["validation_log_probs"][-1]
@@ -70,6 +73,7 @@ def main():
         return float(ms.item()), out
 
     post.sample((10000,))      # warm-up (also fills the workspace caches)
+    acc_rate = post.leakage_correction(torch.tensor(x[:1]), num_rejection_samples=200000)
     for e in range(4, args.max_exp + 1):
         n = 10 ** e
         lo, hi = fdist.shard_rows(n)
@@ -86,7 +90,14 @@ def main():
                 acc = s
             return acc
 
-        ms_s, last = timed(draw)
+        if os.environ.get("SWEEP_PROFILE") and e == args.max_exp and rank == 0:
+            import cProfile, pstats
+            pr = cProfile.Profile(); pr.enable()
+            ms_s, last = timed(draw)
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(18)
+        else:
+            ms_s, last = timed(draw)
         th = last[: min(last.shape[0], args.chunk)].contiguous()
 
         def lps():
@@ -103,6 +114,7 @@ def main():
             print(json.dumps({"config": args.config, "n": n, "n_gpus": world, "samples_per_s": n / (ms_s * 1e-3),
                               "sample_ms": ms_s, "log_prob_per_s": n / (ms_l * 1e-3), "log_prob_ms": ms_l,
                               "trained_epochs": args.epochs, "val_log_prob": val_lp,
+                              "acceptance_rate": acc_rate, "raw_draws_per_s": n / max(acc_rate, 1e-9) / (ms_s * 1e-3),
                               "mean_log_prob_of_draws": float(lp.mean().item()), "chunk": args.chunk}), flush=True)
     if world > 1:
         dist.destroy_process_group()
