@@ -172,6 +172,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly ONE line (rank 0's JSON): library chatter such as NCCL's version banner goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -382,7 +386,10 @@ def main():
             "kernel_classes": classes, "final_loss": losses[-1] if losses else None,
         }
         line.update(out_extra)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
