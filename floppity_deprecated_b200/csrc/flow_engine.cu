@@ -405,6 +405,20 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
   return 0;
 }
 
+// d_ctx[Rc, C] = dctx_all[Rc, Nctx] @ Wctx[Nctx, C]: the gradient wrt the (embedded) context rows, for an embedding
+// net trained jointly in front of the flow (sbi FCEmbedding, /root/reference/modules.py:21-45).  Reads the context-
+// projection gradient the backward pass left in the workspace.
+int fp_nsf_ctx_backward(const fp_nsf_config* cfg, const float* params, int64_t R, int64_t Rc, const float* workspace,
+                        float* d_ctx, void* stream) {
+  FP_TRY(check_cfg(cfg));
+  if (Rc <= 0) return 0;
+  if (R % Rc != 0 || !d_ctx) return FP_E_BADARG;
+  Layout L(cfg);
+  Workspace W(L, R, Rc, true);
+  fp_gemm_args g = dgrad_args(workspace + W.dctx_all, L.Nctx, (int)L.Nctx, params + L.ctx_w, L.C, L.C, Rc, d_ctx, L.C, 0);
+  return launch_gemm(&g, 0.f, 0, 0, (cudaStream_t)stream);
+}
+
 int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* prepared, const float* z, const float* ctx,
                   int64_t R, int64_t Rc, const float* zshift, const float* zscale, float* theta_out, float* workspace,
                   int32_t* status, void* stream) {

@@ -76,6 +76,16 @@ k_gauss_loglik(const double* __restrict__ obs, const double* __restrict__ err, c
   }
 }
 
+// relu forward / backward for the embedding net's output layer (every other relu of the net is a GEMM prologue / mask)
+__global__ void k_relu(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = fmaxf(x[i], 0.f);
+}
+__global__ void k_relu_bwd(const float* __restrict__ d, const float* __restrict__ z, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = z[i] > 0.f ? d[i] : 0.f;
+}
+
 }  // namespace fp
 
 using namespace fp;
@@ -102,6 +112,21 @@ int fp_gauss_loglik(const double* obs, const double* err, const double* x, doubl
   ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   const unsigned grid = (unsigned)std::min<int64_t>(rows, 16 * (int64_t)num_sms());
   k_gauss_loglik<<<grid, 128, 0, (cudaStream_t)stream>>>(obs, err, x, out, rows, C);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fp_relu(const float* x, float* out, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
+  k_relu<<<(unsigned)std::min<int64_t>((n + 255) / 256, 8 * (int64_t)num_sms()), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+int fp_relu_bwd(const float* d, const float* z, float* out, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
+  k_relu_bwd<<<(unsigned)std::min<int64_t>((n + 255) / 256, 8 * (int64_t)num_sms()), 256, 0, (cudaStream_t)stream>>>(d, z, out, n);
   FP_LAUNCH_CHECK();
   return 0;
 }

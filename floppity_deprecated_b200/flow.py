@@ -445,8 +445,13 @@ def build_nsf(batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score
               use_batch_norm: bool = False, generator: Optional[torch.Generator] = None, **kwargs) -> NSFFlow:
     """sbi ``build_nsf`` (sbi naming: ``batch_x`` is theta, ``batch_y`` the spectrum).  Statistics for the two
     z-scorings come from the given batches exactly as upstream (unbiased std, clamp 1e-14 / 1e-7)."""
+    from .embedding import EmbeddedNSF, FCEmbedding
+    emb = None
     if embedding_net is not None and not isinstance(embedding_net, nn.Identity):
-        raise NotImplementedError("embedding nets are SURVEY.md row N1 (next); the default nn.Identity() is supported")
+        if not isinstance(embedding_net, FCEmbedding):
+            raise NotImplementedError("only nn.Identity() and floppity_deprecated_b200.embedding.FCEmbedding (modules.py:25, "
+                                      "-embedding_type FC) are implemented; the CNN / multi embeddings are not")
+        emb = embedding_net
     if use_batch_norm:
         raise NotImplementedError("use_batch_norm=True is not on the FlopPITy path")
     batch_x = torch.as_tensor(batch_x, dtype=torch.float32)
@@ -461,6 +466,16 @@ def build_nsf(batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score
         shift, scale = -t_mean / t_std, 1 / t_std
     if zy:
         mean, std = _zscore_stats(batch_y.reshape(batch_y.shape[0], -1).cpu(), 1e-7)
+    if emb is not None:
+        # sbi: Flow(..., embedding_net=Sequential(Standardize(y), embedding)); the flow's context is the embedding output
+        if emb.input_dim != C:
+            raise ValueError(f"embedding net expects {emb.input_dim} input features, the observations have {C}")
+        flow = NSFFlow(D, emb.output_dim, hidden_features=hidden_features, num_transforms=num_transforms,
+                       num_bins=num_bins, num_blocks=num_blocks, dropout_probability=dropout_probability,
+                       tail_bound=tail_bound, theta_shift=shift, theta_scale=scale, z_score_theta=zx, z_score_x=False,
+                       generator=generator)
+        import copy
+        return EmbeddedNSF(flow, copy.deepcopy(emb), mean, std)
     return NSFFlow(D, C, hidden_features=hidden_features, num_transforms=num_transforms, num_bins=num_bins,
                    num_blocks=num_blocks, dropout_probability=dropout_probability, tail_bound=tail_bound,
                    theta_shift=shift, theta_scale=scale, x_mean=mean, x_std=std, z_score_theta=zx, z_score_x=zy,

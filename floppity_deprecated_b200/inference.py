@@ -74,6 +74,12 @@ class _TrainEngine:
 
     def __init__(self, net: NSFFlow, prior: BoxUniform, batch: int, atomic: bool, num_atoms: int, combined: bool,
                  lr: float, clip_max_norm: Optional[float], use_graph: bool = False):
+        # an embedding net in front of the flow (modules.py:21-45, -embedding FC) is trained jointly: its forward runs
+        # before the flow's, its backward after, and both parameter sets share one clip norm and one Adam step count
+        self.emb = getattr(net, "embedding", None)
+        self.x_dim = net.C                           # width of the (standardised) observation rows
+        if self.emb is not None:
+            net = net.flow
         self.net, self.B = net, int(batch)
         dev = net._flat.device
         self.dev = dev
@@ -94,7 +100,13 @@ class _TrainEngine:
         self.logp = torch.empty(self.R, **f32)
         self.d_logp = torch.full((self.R,), -1.0 / self.B, **f32)
         self.theta_b = torch.empty(self.B, net.D, **f32)
-        self.x_b = torch.empty(self.B, net.C, **f32)
+        self.x_b = torch.empty(self.B, self.x_dim, **f32)
+        if self.emb is not None:
+            self.emb_grads = torch.zeros(self.emb.param_count, **f32)
+            self.emb_m = torch.zeros(self.emb.param_count, **f32)
+            self.emb_v = torch.zeros(self.emb.param_count, **f32)
+            self.d_ctx = torch.empty(self.B, net.C, **f32)
+            self._emb_saved = None
         self.mask_b = torch.zeros(self.B, **f32)
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -109,14 +121,14 @@ class _TrainEngine:
         self.seed = 0
         self.world = fdist.rank_world()[1]
         self.graph = None
-        self.use_graph = bool(use_graph) and self.world == 1 and net.cfg["dropout_p"] == 0.0
+        self.use_graph = bool(use_graph) and self.world == 1 and net.cfg["dropout_p"] == 0.0 and self.emb is None
         self.launches_per_step = 0
 
     # -- pieces -------------------------------------------------------------------------------------------
     def _gather(self, theta_all, x_all, masks_all):
         L, s = _lib.lib(), _lib.stream()
         _lib.check(L.fp_gather_rows(_lib.ptr(theta_all), _lib.ptr(self.idx), _lib.ptr(self.theta_b), self.B, self.net.D, s), "gather theta")
-        _lib.check(L.fp_gather_rows(_lib.ptr(x_all), _lib.ptr(self.idx), _lib.ptr(self.x_b), self.B, self.net.C, s), "gather x")
+        _lib.check(L.fp_gather_rows(_lib.ptr(x_all), _lib.ptr(self.idx), _lib.ptr(self.x_b), self.B, self.x_dim, s), "gather x")
         if masks_all is not None:
             _lib.check(L.fp_gather_rows(_lib.ptr(masks_all), _lib.ptr(self.idx), _lib.ptr(self.mask_b), self.B, 1, s), "gather masks")
 
@@ -136,8 +148,13 @@ class _TrainEngine:
             theta = self.atom_rows
         else:
             theta = self.theta_b
+        ctx = self.x_b
+        if self.emb is not None:
+            ctx, zs = self.emb.forward_raw(self.x_b, keep=training)
+            self._emb_saved = (ctx, zs)
+        self._ctx = ctx
         _lib.check(L.fp_nsf_logprob_forward(
-            c, _lib.ptr(net._flat), _lib.ptr(self.prepared), _lib.ptr(theta), _lib.ptr(self.x_b), self.R, self.B,
+            c, _lib.ptr(net._flat), _lib.ptr(self.prepared), _lib.ptr(theta), _lib.ptr(ctx), self.R, self.B,
             _lib.ptr(net._theta_shift), _lib.ptr(net._theta_scale), self.zlogdet, _lib.ptr(self.logp), _lib.ptr(self.ws),
             1, self.seed if drop_on else 0, _lib.ptr(self.status), s), "logprob forward")
         if self.atomic:
@@ -162,19 +179,33 @@ class _TrainEngine:
         self.grads.zero_()
         self.sumsq.zero_()
         _lib.check(L.fp_nsf_logprob_backward(
-            c, _lib.ptr(net._flat), _lib.ptr(self.prepared), _lib.ptr(self.x_b), self.R, self.B,
+            c, _lib.ptr(net._flat), _lib.ptr(self.prepared), _lib.ptr(self._ctx), self.R, self.B,
             _lib.ptr(net._theta_scale), _lib.ptr(self.d_logp), _lib.ptr(self.grads), None, _lib.ptr(self.ws),
             self.seed if c.dropout_p > 0 else 0, s), "logprob backward")
         _lib.check(L.fp_nsf_finish_grads(c, _lib.ptr(net._flat), _lib.ptr(self.prepared), _lib.ptr(self.grads), s), "finish grads")
+        if self.emb is not None:
+            self.emb_grads.zero_()
+            _lib.check(L.fp_nsf_ctx_backward(c, _lib.ptr(net._flat), self.R, self.B, _lib.ptr(self.ws), _lib.ptr(self.d_ctx), s),
+                       "ctx backward")
+            self.emb.backward_raw(self.x_b, self._emb_saved[1], self.d_ctx, self.emb_grads)
         scale = 1.0
         if self.world > 1:
             fdist.allreduce_sum_(self.grads[:n])
+            if self.emb is not None:
+                fdist.allreduce_sum_(self.emb_grads)
             scale = 1.0 / self.world
+        # clip_grad_norm_ over ALL parameters (flow + embedding): both buffers feed one sum of squares
         _lib.check(L.fp_grad_sumsq(_lib.ptr(self.grads), n, _lib.ptr(self.sumsq), s), "sumsq")
+        if self.emb is not None:
+            _lib.check(L.fp_grad_sumsq(_lib.ptr(self.emb_grads), self.emb.param_count, _lib.ptr(self.sumsq), s), "sumsq emb")
         self.step_dev += 1
         _lib.check(L.fp_adam_step(_lib.ptr(net._flat), _lib.ptr(self.grads), _lib.ptr(self.m), _lib.ptr(self.v), n,
                                   self.lr, 0.9, 0.999, 1e-8, _lib.ptr(self.step_dev), self.clip, scale,
                                   _lib.ptr(self.sumsq), s), "adam")
+        if self.emb is not None:
+            _lib.check(L.fp_adam_step(_lib.ptr(self.emb._flat), _lib.ptr(self.emb_grads), _lib.ptr(self.emb_m),
+                                      _lib.ptr(self.emb_v), self.emb.param_count, self.lr, 0.9, 0.999, 1e-8,
+                                      _lib.ptr(self.step_dev), self.clip, scale, _lib.ptr(self.sumsq), s), "adam emb")
 
     # -- public -------------------------------------------------------------------------------------------
     def _step_body(self, theta_all, x_all, masks_all):
@@ -327,6 +358,8 @@ class SNPE_C:
             self._neural_net = self._build_neural_net(theta[train_idx], x[train_idx]).to(dev)
             if world > 1:
                 fdist.broadcast_(self._neural_net._flat.data)
+                if getattr(self._neural_net, "embedding", None) is not None:
+                    fdist.broadcast_(self._neural_net.embedding._flat.data)
         net = self._neural_net
         net.train()
 

@@ -162,6 +162,10 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
                             const float* ctx, int64_t R, int64_t Rc, const float* zscale,
                             const float* d_logp, float* grads, float* d_theta, float* workspace,
                             uint64_t dropout_seed, void* stream);
+/* d_ctx [Rc, C] = gradient wrt the context rows (for an embedding net trained jointly in front of the flow: sbi
+ * FCEmbedding built at /root/reference/modules.py:21-45).  Call after fp_nsf_logprob_backward with the same workspace. */
+int fp_nsf_ctx_backward(const fp_nsf_config* cfg, const float* params, int64_t R, int64_t Rc, const float* workspace,
+                        float* d_ctx, void* stream);
 /* Fold d(W=L*U) etc. accumulated by the backward into the LU parameter gradients and zero the
  * structural zeros of W0X. Call once after all backward passes of a step. */
 int fp_nsf_finish_grads(const fp_nsf_config* cfg, const float* params, const float* prepared,
@@ -216,6 +220,10 @@ int fp_preprocess_rows(const double* spec, const float* z, const double* noise, 
 /* Row-wise Gaussian log-likelihood of model spectra x [rows, C] against the observation (floppityFUN.py:24-28, the
  * inner loop of IS / evidence, floppityFUN.py:30-91): out[i] = sum_j -log(sqrt(2 pi) err_j) - (obs_j - x_ij)^2 / (2 err_j^2) */
 int fp_gauss_loglik(const double* obs, const double* err, const double* x, double* out, int64_t rows, int32_t C, void* stream);
+
+/* out = max(x, 0) ; out = d * (z > 0): the output relu of the embedding net (its inner relus are GEMM prologues / masks) */
+int fp_relu(const float* x, float* out, int64_t n, void* stream);
+int fp_relu_bwd(const float* d, const float* z, float* out, int64_t n, void* stream);
 
 int fp_within_box(const float* theta, const float* low, const float* high, uint8_t* inside, int64_t R, int32_t D, void* stream);
 

@@ -513,6 +513,25 @@ def standardizing_net(batch_t: Tensor, min_std: float = 1e-7) -> Standardize:
     return Standardize(t_mean, t_std)
 
 
+class FCEmbedding(nn.Module):
+    """[UPSTREAM-RECALL sbi 0.22 ``sbi.neural_nets.embedding_nets.FCEmbedding``] as FlopPITy builds it at
+    /root/reference/modules.py:25 (``FCEmbedding(input_dim=nwvl, num_hiddens=256, num_layers=4, output_dim=embed_size)``):
+    Linear(input, hidden)+ReLU, (num_layers-2) x [Linear(hidden, hidden)+ReLU], Linear(hidden, output)+ReLU."""
+
+    def __init__(self, input_dim: int, output_dim: int = 20, num_layers: int = 2, num_hiddens: int = 50):
+        super().__init__()
+        layers = [nn.Linear(input_dim, num_hiddens), nn.ReLU()]
+        for _ in range(num_layers - 2):
+            layers.append(nn.Linear(num_hiddens, num_hiddens))
+            layers.append(nn.ReLU())
+        layers.append(nn.Linear(num_hiddens, output_dim))
+        layers.append(nn.ReLU())
+        self.net = nn.Sequential(*layers)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.net(x)
+
+
 def build_nsf(batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score_y="independent",
               hidden_features=50, num_transforms=5, num_bins=10, embedding_net: nn.Module = None,
               tail_bound=3.0, hidden_layers_spline_context=1, num_blocks=2, dropout_probability=0.0,
