@@ -90,6 +90,7 @@ SIGNATURES = {
     "fp_standardize": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P]),
     "fp_sum": (c_int32, [_P, c_int64, c_float, _P, _P]),
     "fp_within_box": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P]),
+    "fp_compact_inside": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int64, _P]),
     "fp_preprocess_rows": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int64, _P]),
     "fp_gauss_loglik": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P]),
     "fp_relu": (c_int32, [_P, _P, c_int64, _P]),

@@ -427,6 +427,27 @@ __global__ void k_within_box(const float* __restrict__ theta, const float* __res
   inside[r] = ok ? 1 : 0;
 }
 
+// Rejection step of accept_reject_sample (sbi.samplers.rejection, reached from floppity.py:252): rows inside the prior
+// box are appended to `out` behind a device counter -- one warp-aggregated atomic per 32 candidates -- until `cap`
+// rows are stored.  The order of accepted rows is not the candidate order (they are i.i.d. draws).
+__global__ void k_compact_inside(const float* __restrict__ theta, const float* __restrict__ low, const float* __restrict__ high,
+                                 float* __restrict__ out, unsigned long long* __restrict__ counter, int64_t R, int D,
+                                 int64_t cap) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = r < R;
+  if (ok) for (int f = 0; f < D; ++f) { const float v = theta[r * D + f]; ok &= (v >= low[f]) && (v <= high[f]); }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (!ok) return;
+  const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+  if (pos >= cap) return;
+  for (int f = 0; f < D; ++f) out[pos * D + f] = theta[r * D + f];
+}
+
 // ---- launch wrappers used by the engine ----------------------------------------------------------------------
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
@@ -575,6 +596,15 @@ int fp_within_box(const float* theta, const float* low, const float* high, uint8
   if (R <= 0) return 0;
   ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_within_box<<<nblk(R, 256), 256, 0, (cudaStream_t)stream>>>(theta, low, high, inside, R, D);
+  FP_LAUNCH_CHECK(); return 0;
+}
+int fp_compact_inside(const float* theta, const float* low, const float* high, float* out, uint64_t* counter, int64_t R,
+                      int32_t D, int64_t cap, void* stream) {
+  if (R <= 0) return 0;
+  if (D < 1 || cap < 0 || !counter) return FP_E_BADARG;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
+  k_compact_inside<<<nblk(R, 256), 256, 0, (cudaStream_t)stream>>>(theta, low, high, out,
+                                                                   reinterpret_cast<unsigned long long*>(counter), R, D, cap);
   FP_LAUNCH_CHECK(); return 0;
 }
 const char* fp_version(void) { return "floppity_b200 0.1 (sm_100a)"; }

@@ -16,11 +16,19 @@
 #include "rqs_math.cuh"
 #include "prof.h"
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace fp {
 
-constexpr int RQS_STAGES = 2;
+constexpr int RQS_MAX_STAGES = 2;
+// ring depth of the spline kernels (1 or 2), FLOPPITY_RQS_STAGES: with one stage a CTA holds half the shared memory, so
+// twice as many CTAs (and rows in flight through the arithmetic) fit an SM and other CTAs' loads cover a CTA's wait
+static int rqs_stages() {
+  static int n = 0;
+  if (n == 0) { const char* e = getenv("FLOPPITY_RQS_STAGES"); n = (e && e[0] == '2') ? 2 : ((e && e[0] == '1') ? 1 : 2); }
+  return n;
+}
 
 struct RqsArgs {
   const float* theta_in;
@@ -31,7 +39,7 @@ struct RqsArgs {
   int32_t* bin_idx;     // optional
   int32_t* status;      // optional
   int64_t R;
-  int D, d_tr, parity, rows;
+  int D, d_tr, parity, rows, stages;
   int ldp;              // row stride of params in floats (>= d_tr*P; padded to a multiple of 4 by the engine)
   RqsConsts c;
   const float* luM;     // optional [D, D]
@@ -45,14 +53,14 @@ struct RqsArgs {
 //   [ params: rows*d_tr*P floats | theta rows: rows*D floats | logdet: rows floats ]
 // The transformed values overwrite the theta rows in place; nothing is read from global by the SM's load path.
 struct RqsSmem {
-  float* stage[RQS_STAGES];
+  float* stage[RQS_MAX_STAGES];
   float* ladbuf;
   float* luM;
   uint64_t* bars;
   int stage_floats, th_off, ld_off;
 };
 
-__device__ __forceinline__ RqsSmem carve(unsigned char* base, int tile_floats, int rows, int D, int d_tr, bool lu) {
+__device__ __forceinline__ RqsSmem carve(unsigned char* base, int tile_floats, int rows, int D, int d_tr, bool lu, int RQS_STAGES) {
   RqsSmem s;
   s.th_off = tile_floats;                       // rows % 4 == 0 -> every region starts 16-byte aligned
   s.ld_off = tile_floats + rows * D;
@@ -67,6 +75,7 @@ __device__ __forceinline__ RqsSmem carve(unsigned char* base, int tile_floats, i
 }
 
 static size_t rqs_smem_bytes(int tile_floats, int rows, int D, int d_tr, bool lu) {
+  const int RQS_STAGES = rqs_stages();
   size_t f = (size_t)RQS_STAGES * (tile_floats + rows * D + rows) + (size_t)rows * d_tr + (lu ? (size_t)D * D : 0);
   return f * 4 + 8 + RQS_STAGES * 8 + 16;
 }
@@ -109,7 +118,8 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
   const int row_floats = a.ldp;
   const int tile_floats = a.rows * row_floats;
   const bool lu = a.luM != nullptr;
-  RqsSmem s = carve(smem_raw, tile_floats, a.rows, a.D, a.d_tr, lu);
+  const int RQS_STAGES = a.stages;
+  RqsSmem s = carve(smem_raw, tile_floats, a.rows, a.D, a.d_tr, lu, RQS_STAGES);
   const int64_t ntiles = (a.R + a.rows - 1) / a.rows;
   const int D = a.D, d_tr = a.d_tr;
   const float inv_dtr = 1.f / (float)d_tr, inv_D = 1.f / (float)D;
@@ -208,7 +218,7 @@ struct RqsBwdArgs {
   float* d_params;           // [R, d_tr, P]
   float* d_theta_in;         // [R, D]
   int64_t R;
-  int D, d_tr, parity, rows;
+  int D, d_tr, parity, rows, stages;
   int ldp;                   // row stride of params / d_params in floats
   RqsConsts c;
   // optional fused LULinear backward (y = M x + b after the spline): d_theta_out is then the gradient wrt y
@@ -223,7 +233,8 @@ __global__ void __launch_bounds__(512) k_rqs_backward(RqsBwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int row_floats = a.ldp;
   const int tile_floats = a.rows * row_floats;
-  float* stage[RQS_STAGES];
+  const int RQS_STAGES = a.stages;
+  float* stage[RQS_MAX_STAGES];
   {
     float* f = reinterpret_cast<float*>(smem_raw);
     for (int i = 0; i < RQS_STAGES; ++i) { stage[i] = f; f += tile_floats; }
@@ -372,7 +383,9 @@ RqsConsts make_rqs_consts(const fp_nsf_config* cfg) {
 // rows per tile: multiple of 4 (keeps every full tile 16-byte granular for the bulk copy), sized to ~20 KB per
 // stage so that 4-5 CTAs stay resident per SM (the kernels are issue-bound: occupancy hides the MUFU/LDS latency)
 static int pick_rows(int row_floats, int d_tr) {
-  int rows = (20 * 1024) / (row_floats * 4);
+  static int kb = 0;
+  if (kb == 0) { const char* e = getenv("FLOPPITY_RQS_TILE_KB"); kb = e ? atoi(e) : 20; if (kb < 2 || kb > 96) kb = 20; }
+  int rows = (kb * 1024) / (row_floats * 4);
   rows = rows / 4 * 4;
   if (rows < 4) rows = 4;
   if (rows > 128) rows = 128;
@@ -404,6 +417,7 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
   a.ldp = ldp > 0 ? ldp : a.d_tr * a.c.P;
   int row_floats = a.ldp;
   a.rows = pick_rows(row_floats, a.d_tr);
+  a.stages = rqs_stages();
   int threads = pick_threads(a.rows, a.d_tr);
   size_t smem = rqs_smem_bytes(a.rows * row_floats, a.rows, a.D, a.d_tr, luM != nullptr);
   void (*kern)(RqsArgs);
@@ -446,6 +460,8 @@ int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta
   a.ldp = ldp > 0 ? ldp : a.d_tr * a.c.P;
   int row_floats = a.ldp;
   a.rows = pick_rows(row_floats, a.d_tr);
+  a.stages = rqs_stages();
+  const int RQS_STAGES = a.stages;
   int threads = pick_threads(a.rows, a.d_tr);
   size_t smem = (size_t)RQS_STAGES * a.rows * row_floats * 4 + 8 + RQS_STAGES * 8 + 16;
   smem += ((size_t)2 * a.D * a.D + a.D + (size_t)3 * a.rows * a.D) * 4;      // LU scratch (see the kernel)

@@ -481,22 +481,30 @@ class DirectPosterior:
         net = self.posterior_estimator
         net.eval()
         ctx_std = net._standardize(x)
-        accepted, num_remaining, num_total = [], num_samples, 0
+        dev = net._flat.device
+        out = torch.empty(num_samples, net.D, dtype=torch.float32, device=dev)
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)        # accepted so far (device side)
+        low, high = self._box(dev)
+        num_remaining, num_total, num_accepted = num_samples, 0, 0
         bs = min(num_samples, max_sampling_batch_size)
         acceptance_rate = 1.0
         warned = False
         while num_remaining > 0:
-            cand, inside = self._draw(bs, ctx_std)
-            keep = cand[inside.bool()]
-            accepted.append(keep)
-            num_remaining -= keep.shape[0]
+            z = torch.randn(bs, net.D, device=dev, dtype=torch.float32)
+            cand = net.inverse_rows(z, ctx_std)
+            # in-support rows are appended to `out` on the device; the only host round trip per batch is the count
+            _lib.check(_lib.lib().fp_compact_inside(_lib.ptr(cand), _lib.ptr(low), _lib.ptr(high), _lib.ptr(out),
+                                                    _lib.ptr(counter), bs, net.D, num_samples, _lib.stream()),
+                       "fp_compact_inside")
+            num_accepted = int(counter.item())
             num_total += bs
-            acceptance_rate = (num_samples - num_remaining) / num_total
+            num_remaining = num_samples - num_accepted
+            acceptance_rate = num_accepted / num_total
             if not warned and num_total > 1000 and acceptance_rate < 0.01:
                 warnings.warn(f"Only {acceptance_rate:.3%} proposal samples are accepted; the posterior leaks out of the prior.")
                 warned = True
             bs = min(max_sampling_batch_size, max(int(1.5 * num_remaining / max(acceptance_rate, 1e-12)), 100))
-        return torch.cat(accepted)[:num_samples], acceptance_rate
+        return out, acceptance_rate
 
     def sample(self, sample_shape=torch.Size(), x=None, max_sampling_batch_size: Optional[int] = None,
                sample_with=None, show_progress_bars: bool = False) -> Tensor:

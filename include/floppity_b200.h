@@ -230,6 +230,10 @@ int fp_within_box(const float* theta, const float* low, const float* high, uint8
 /* ---- launch accounting (bench.py: gpu_launches and the live roofline numbers) -----------------------
  * classes: 0 SIMT GEMM (work = flops), 1 tcgen05 GEMM (flops), 2 spline fwd, 3 spline inverse, 4 spline
  * backward (work = algorithmic bytes), 5 everything else. */
+/* Rejection step of accept_reject_sample: append the rows of theta [R, D] that lie inside [low, high] to out (row
+ * capacity `cap`) behind the device counter *counter (rows accepted so far, also counts rows beyond cap). */
+int fp_compact_inside(const float* theta, const float* low, const float* high, float* out, uint64_t* counter, int64_t R,
+                      int32_t D, int64_t cap, void* stream);
 int64_t fp_launch_count(void);
 int fp_prof_enable(int32_t on);
 int fp_prof_collect(double* ms /*[6]*/, int64_t* launches /*[6]*/, double* work /*[6]*/);

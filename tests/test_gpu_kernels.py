@@ -403,3 +403,38 @@ def test_small_utilities():
     inside = torch.empty(100, dtype=torch.uint8, device="cuda")
     _lib.check(lib.fp_within_box(_lib.ptr(src_d), _lib.ptr(low_d), _lib.ptr(high_d), _lib.ptr(inside), 100, 37, _lib.stream()), "w")
     assert torch.equal(inside.cpu().bool(), ((src >= low) & (src <= high)).all(-1))
+
+
+@pytest.mark.gpu
+def test_compact_inside_is_the_rejection_step():
+    """fp_compact_inside == keep the rows inside the prior box (sbi accept_reject_sample, floppity.py:252): same SET of
+    rows as a boolean mask, appended behind a device counter, capacity respected, counter keeps counting."""
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    R, D = 100_003, 7
+    theta = (torch.randn(R, D, generator=g) * 1.6).cuda()
+    low, high = torch.full((D,), -3.0).cuda(), torch.full((D,), 3.0).cuda()
+    low[2], high[4] = -1.0, 0.5
+    mask = ((theta >= low) & (theta <= high)).all(1)
+    want = theta[mask]
+    for cap in (R, 1000, 0):
+        out = torch.full((max(cap, 1), D), float("nan")).cuda()
+        counter = torch.zeros(1, dtype=torch.int64).cuda()
+        # two calls append behind each other
+        half = R // 2
+        assert lib.fp_compact_inside(theta.data_ptr(), low.data_ptr(), high.data_ptr(), out.data_ptr(), counter.data_ptr(),
+                                     half, D, cap, _lib.stream()) == 0
+        assert lib.fp_compact_inside(theta[half:].data_ptr(), low.data_ptr(), high.data_ptr(), out.data_ptr(),
+                                     counter.data_ptr(), R - half, D, cap, _lib.stream()) == 0
+        torch.cuda.synchronize()
+        assert int(counter.item()) == want.shape[0]
+        n = min(cap, want.shape[0])
+        got = out[:n]
+        assert torch.isfinite(got).all()
+        if cap >= want.shape[0]:
+            import numpy as np
+            canon = lambda t: np.unique(t.cpu().numpy(), axis=0)        # lexicographically sorted rows
+            a, b = canon(got), canon(want)
+            assert a.shape == b.shape == tuple(want.shape) and np.array_equal(a, b)
+        else:
+            assert bool((((got >= low) & (got <= high)).all(1)).all())
