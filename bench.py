@@ -311,6 +311,15 @@ def main():
         roof = {"bound": "hbm", "achieved": ach, "peak": PK["hbm"], "unit": "GB/s", "frac": ach / PK["hbm"], "traffic": None,
                 "kernel": CLASS_NAMES[dom], "peak_source": PK["source"]}
 
+    # measured DRAM traffic of the dominant class's main kernel (one ncu --set full capture, profiles/traffic.json)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(roof["kernel"])
+        if tr:
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_note"] = f"{tr['kernel']}: algorithmic {tr['algorithmic_bytes_per_launch']} B per launch; {tr['source']}"
+    except Exception:
+        pass
+
     # ---- extras: posterior sampling / log_prob throughput (sharded per GPU, no collective), MLE-mode training
     if not args.no_extras:
         net.eval()
