@@ -438,6 +438,10 @@ class DirectPosterior:
         self.prior = prior
         self.max_sampling_batch_size = int(max_sampling_batch_size)
         self._x: Optional[Tensor] = None
+        # Drop-in fidelity: FlopPITy's default is -device cpu (floppity.py:30) and its helpers call .numpy() on what
+        # log_prob returns (floppityFUN.py:37-39).  The work always runs on CUDA; a posterior built for 'cpu' hands its
+        # RESULTS back on the CPU, any other / no device keeps them on the GPU.
+        self._return_device = torch.device("cpu") if (device is not None and str(device) == "cpu") else None
         self._leakage_cache = {}
         self._purpose = "direct posterior (B200 NSF)"
 
@@ -513,7 +517,8 @@ class DirectPosterior:
         x = self._x_or_default(x)
         mx = self.max_sampling_batch_size if max_sampling_batch_size is None else int(max_sampling_batch_size)
         samples, _ = self._accept_reject(num_samples, x, mx)
-        return samples.reshape(*torch.Size(sample_shape), -1)
+        samples = samples.reshape(*torch.Size(sample_shape), -1)
+        return samples if self._return_device is None else samples.to(self._return_device)
 
     def sample_sharded(self, num_samples: int, x=None, gather: bool = False) -> Tensor:
         """Embarrassingly parallel sampling: this rank draws its contiguous share of ``num_samples``."""
@@ -549,7 +554,7 @@ class DirectPosterior:
             if norm_posterior:
                 acc = self.leakage_correction(x, **(leakage_correction_params or {}))
                 lp = lp - float(np.log(acc))
-        return lp
+        return lp if self._return_device is None else lp.to(self._return_device)
 
     def log_prob_sharded(self, theta, x=None, norm_posterior: bool = False, gather: bool = False) -> Tensor:
         theta = torch.as_tensor(theta)
@@ -564,8 +569,8 @@ class DirectPosterior:
         Uses the kernels' input-gradient path (d log q / d theta)."""
         x = self._x_or_default(x)
         dev = self.posterior_estimator._flat.device
-        init = self.sample((num_init_samples,), x=x) if isinstance(init_method, str) else torch.as_tensor(init_method).to(dev)
-        lp0 = self.log_prob(init, x=x, norm_posterior=False)
+        init = (self.sample((num_init_samples,), x=x) if isinstance(init_method, str) else torch.as_tensor(init_method)).to(dev)
+        lp0 = self.log_prob(init, x=x, norm_posterior=False).to(dev)
         top = init[torch.argsort(lp0, descending=True)[:num_to_optimize]].clone()
         low, high = self._box(dev)
         theta = top.clone().requires_grad_(True)
@@ -582,11 +587,11 @@ class DirectPosterior:
                 with torch.no_grad():
                     theta.data = torch.minimum(torch.maximum(theta.data, low), high)
                     if it % save_best_every == 0 or it == num_iter - 1:
-                        cur = self.log_prob(theta.detach(), x=x, norm_posterior=False)
+                        cur = self.log_prob(theta.detach(), x=x, norm_posterior=False).to(dev)
                         j = int(torch.argmax(cur))
                         if cur[j] > best_lp:
                             best, best_lp = theta.detach()[j].clone(), cur[j]
         finally:
             self.posterior_estimator._flat.requires_grad_(was)
-        self._map = best
-        return best
+        self._map = best if self._return_device is None else best.to(self._return_device)
+        return self._map

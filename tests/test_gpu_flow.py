@@ -282,3 +282,29 @@ def test_fused_conditioner_training_gradients_many_tiles():
     for k, p in onet.named_parameters():
         worst = max(worst, float((got[k].cpu() - p.grad).abs().max()) / max(float(p.grad.abs().max()), 1e-4))
     assert worst < 2e-3, worst
+
+
+def test_cpu_device_request_gets_cpu_results():
+    """FlopPITy's default is -device cpu (floppity.py:30) and its helpers call .numpy() on log_prob's result
+    (floppityFUN.py:37-39): a posterior built for 'cpu' computes on the GPU but hands results back on the CPU."""
+    import warnings
+    theta, x, _, _ = synthetic.make_dataset("c1", 1024)
+    prior = fb.BoxUniform(-3 * torch.ones(10), 3 * torch.ones(10), device="cpu")
+    inf = fb.SNPE_C(prior, density_estimator=fb.posterior_nn(model="nsf", hidden_features=50, num_transforms=3, num_bins=8),
+                    device="cpu")
+    inf.append_simulations(torch.tensor(theta), torch.tensor(x))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        est = inf.train(training_batch_size=256, max_num_epochs=2, stop_after_epochs=2, seed=0)
+    post = inf.build_posterior(est).set_default_x(torch.tensor(x[:1]))
+    s = post.sample((100,))
+    assert not s.is_cuda and s.shape == (100, 10)
+    P = post.log_prob(torch.tensor(theta[:50]), x=x[:1])
+    pi = prior.log_prob(torch.tensor(theta[:50]))
+    _ = -(P - pi).detach().numpy()                          # the expression of floppityFUN.py:37
+    m = post.map(num_iter=5, num_to_optimize=10, num_init_samples=50)
+    assert not m.is_cuda and m.shape == (10,)
+    from floppity_deprecated_b200 import retrieval as RT
+    spec = np.abs(x[:50].astype(np.float64)) + 1.0
+    w, eff = RT.IS(post, spec[0], np.full(spec.shape[1], 0.1), spec, theta[:50])
+    assert w.shape == (50,) and 0.0 < eff <= 1.0
