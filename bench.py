@@ -348,6 +348,18 @@ def main():
             eng2.step(batches[i], theta_dev, x_dev, masks_dev)
         ms2 = timed(lambda i: eng2.step(batches[i % 8], theta_dev, x_dev, masks_dev), K)
         out_extra["train_pairs_per_s_" + ("mle" if atomic else "atomic")] = world * B * K / (ms2 * 1e-3)
+        if atomic:
+            # the same MLE loss at the row count the atomic step works on (B x atoms flow rows): the launch-bound small
+            # step above is a property of the batch size, not of the loss
+            Bb = B * cfg.atoms
+            del eng2
+            eng3 = _TrainEngine(net, prior, Bb, False, cfg.atoms, True, 5e-4, 5.0, use_graph=False)
+            big = [torch.randint(0, args.rows, (Bb,), device=dev, generator=g) for _ in range(2)]
+            for i in range(3):
+                eng3.step(big[i % 2], theta_dev, x_dev, masks_dev)
+            ms3 = timed(lambda i: eng3.step(big[i % 2], theta_dev, x_dev, masks_dev), max(K // 2, 2))
+            out_extra["train_pairs_per_s_mle_batch_x_atoms"] = world * Bb * max(K // 2, 2) / (ms3 * 1e-3)
+            del eng3
 
     # ---- CPU baseline beside it (rank 0, N == 1 only): the oracle on the host cores, bounded sample
     cpu_base = None
