@@ -308,3 +308,21 @@ def test_cpu_device_request_gets_cpu_results():
     spec = np.abs(x[:50].astype(np.float64)) + 1.0
     w, eff = RT.IS(post, spec[0], np.full(spec.shape[1], 0.1), spec, theta[:50])
     assert w.shape == (50,) and 0.0 < eff <= 1.0
+
+
+def test_example_retrieval_round_loop(tmp_path):
+    """examples/synthetic_retrieval.py = floppity.py's round loop on the synthetic forward model: preprocess on the GPU,
+    MLE round then (force_first_round_loss=0) atomic rounds, IS evidence, pickled checkpoints, MAP."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("synthetic_retrieval", os.path.join(os.path.dirname(__file__), "..", "examples", "synthetic_retrieval.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--config", "c1", "--rounds", "2", "--samples", "1024", "--naug", "2", "--patience", "2", "--batch", "256",
+                    "--npew", "500", "--force-first-round-loss", "0", "--out", str(tmp_path)])
+    assert len(out["samples"]) == 2 and out["samples"][0].shape == (500, 10)
+    assert np.isfinite(out["MAP"]).all() and len(out["logZs"]) == 1 and np.isfinite(out["logZs"][0][0])
+    for f in ("posteriors.pt", "inference.p", "samples.p", "xscaler.p", "pca.p", "map_params.npy"):
+        assert os.path.exists(tmp_path / f), f
+    posts = torch.load(tmp_path / "posteriors.pt", weights_only=False)          # modules.py:74 (-resume)
+    assert posts[-1].sample((10,)).shape == (10, 10)
