@@ -5,7 +5,7 @@
 // (SURVEY.md 2.3 iii-iv), gemm_tc.cu runs it as 2*Bk+2 GEMM launches with every activation making a round trip
 // through HBM/L2.  Here a CTA takes a tile of 128 flow rows through the whole chain
 //     h0 = theta W0x^T + ctx0 ;  per block: t = relu(h) W1^T + b1 ; u = relu(t) W2^T + b2 ; h += u * sigmoid(ctx_k)
-//     params = h Wf^T + bf
+//     params = h Wf^T + bf            (sigmoid(ctx_k) arrives precomputed, once per context row: k_gate_sigmoid)
 // with the activations never leaving the SM:
 //   * the A operand of every GEMM lives in TENSOR MEMORY (tcgen05.mma with A from TMEM): the epilogue threads own one
 //     row each, apply bias / context / GLU / relu, split the result into TF32 hi + lo (3xTF32, fp32-accurate) and

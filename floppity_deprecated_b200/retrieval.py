@@ -20,14 +20,12 @@ from __future__ import annotations
 
 import os
 import pickle
-from typing import Optional, Tuple
+from typing import Optional
 
 import numpy as np
 import torch
 
 from . import _lib
-
-_SQRT_2PI = 2.5066282746310002
 
 
 class Normalizer:
