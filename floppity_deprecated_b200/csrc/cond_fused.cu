@@ -164,7 +164,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
   const int64_t n_tiles = (p.R + CF_BM - 1) / CF_BM;
   const int Bk = p.Bk;
   const int nF = (p.dP + 127) / 128;            // 128-column units of the final layer
-  const int ks0 = (p.D + 7) / 8;                // k-steps of the initial layer (K = D <= 32)
+  const int nkb0 = (p.D + 31) / 32;             // k-blocks of the initial layer (K = D <= 64)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -205,7 +205,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         ++it;
       };
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        stage(&maps.w0h, &maps.w0l, 0, 0, 2 * CF_TILE_BYTES);
+        for (int kb = 0; kb < nkb0; ++kb) stage(&maps.w0h, &maps.w0l, kb * 32, 0, 2 * CF_TILE_BYTES);
         for (int k = 0; k < Bk; ++k)
           for (int g = 0; g < 2; ++g)
             for (int kb = 0; kb < 4; ++kb) stage(&maps.wh, &maps.wl, kb * 32, k * 258 + g * 129, 2 * CF_TILE_BYTES);
@@ -255,7 +255,8 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         wait_operand();                                   // theta tile split into the operand columns
         while (pend > 0) wait_drained();                  // (already true by program order: keeps the phase count in step)
         CF_TRACE(ts); ++ts;
-        kblock(d_hh, d_x, 0, ks0, idesc128, true);
+        for (int kb = 0; kb < nkb0; ++kb)
+          kblock(d_hh, d_x, 32u * kb, min(4, (p.D - 32 * kb + 7) / 8), idesc128, kb == 0);
         umma_commit(&acc_full[0]);
         CF_TRACE(ts); ++ts;
         for (int u = 0; u < 2 * Bk; ++u) {
@@ -326,20 +327,24 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
       const float* ctx_row = p.ctx + (int64_t)((uint32_t)mc / cdiv) * p.ldg + hf * 64;
       float4 aux[4], nxt[4];
 
-      {  // ---- theta tile -> operand columns [hf*16, hf*16+16)
-        float w[16], hi[16], lo[16];
-        const float* tp = p.theta + mc * p.D + hf * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (hf * 16 + 4 * j < p.D) v = __ldg(reinterpret_cast<const float4*>(tp + 4 * j));
-          w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
-        }
+      {  // ---- theta tile -> operand columns: this thread's half of the 32 (D <= 32) or 64 (D <= 64) padded columns
+        const int npc = nkb0;                 // 16-column pieces per thread: 1 or 2
         ldg16(ctx_row, aux);                  // first context piece of the initial layer, ahead of its accumulator
         prefetch_l1(ctx_row + 32);
-        split16(w, hi, lo);
-        tmem_st_16(t_ahi + hf * 16, hi);
-        tmem_st_16(t_alo + hf * 16, lo);
+        for (int pc = 0; pc < npc; ++pc) {
+          float w[16], hi[16], lo[16];
+          const int c0 = hf * 16 * npc + pc * 16;
+          const float* tp = p.theta + mc * p.D + c0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + 4 * j < p.D) v = __ldg(reinterpret_cast<const float4*>(tp + 4 * j));
+            w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+          }
+          split16(w, hi, lo);
+          tmem_st_16(t_ahi + c0, hi);
+          tmem_st_16(t_alo + c0, lo);
+        }
         operand_done();
       }
 
@@ -514,7 +519,7 @@ static bool fused_enabled() {
 // Shapes the fused kernel covers (a property of the flow, identical for every layer and every pass)
 bool cond_fwd_supported(const Layout& L, const float* prepared) {
   if (!tc_enabled() || !fused_enabled() || !prepared) return false;
-  return L.H == 128 && L.D <= 32 && (L.D & 3) == 0 && L.Bk >= 1 && L.Bk <= CF_MAXBK;
+  return L.H == 128 && L.D <= 64 && (L.D & 3) == 0 && L.Bk >= 1 && L.Bk <= CF_MAXBK;
 }
 
 // Conditioner forward of layer i as one launch.  h/t/u: saved-activation buffers ([R,128] each) when training, else unused.

@@ -210,7 +210,7 @@ def test_map_moves_uphill():
     prior = fb.BoxUniform(-3 * torch.ones(10), 3 * torch.ones(10), device="cuda")
     post = fb.DirectPosterior(net, prior).set_default_x(x[:1])
     init = post.sample((200,))
-    m = post.map(num_iter=20, num_to_optimize=20, num_init_samples=200)
+    m = post.map(num_iter=20, num_to_optimize=20, init_method=init)      # same starting population as the comparison
     assert post.log_prob(m[None], norm_posterior=False).item() >= post.log_prob(init, norm_posterior=False).max().item() - 1e-3
 
 
@@ -218,20 +218,20 @@ def test_map_moves_uphill():
 # The fused conditioner kernel (cond_fused.cu, hidden 128) on MANY row tiles: ragged last tile, CTAs walking several
 # tiles, every context-sharing pattern (one row per flow row, A atoms per context row, one context row for all).
 # ---------------------------------------------------------------------------------------------------------------------
-def _c2_pair(seed=11):
-    cfg = synthetic.CONFIGS["c2"]
+def _c2_pair(seed=11, name="c2", C=None, T=None):
+    cfg = synthetic.CONFIGS[name]
     g = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
     theta = torch.rand(2048, cfg.D, generator=g) * 6 - 3
-    x = torch.randn(2048, cfg.C, generator=g)
-    hp = dict(hidden_features=cfg.hidden, num_transforms=cfg.transforms, num_bins=cfg.bins, num_blocks=cfg.blocks)
+    x = torch.randn(2048, C or cfg.C, generator=g)
+    hp = dict(hidden_features=cfg.hidden, num_transforms=T or cfg.transforms, num_bins=cfg.bins, num_blocks=cfg.blocks)
     onet = O.build_nsf(theta, x, **hp)
     O.randomize_lu(onet, g, 0.05)
     with torch.no_grad():
         for c in O.coupling_layers(onet):
             for blk in c.transform_net.blocks:
                 blk.linear_layers[1].weight.add_(0.03 * torch.randn(blk.linear_layers[1].weight.shape, generator=g))
-    net = fb.NSFFlow(cfg.D, cfg.C, **hp)
+    net = fb.NSFFlow(cfg.D, C or cfg.C, **hp)
     net.load_state_dict(onet.state_dict())
     return onet.eval(), net.cuda().eval(), theta, x
 
@@ -326,3 +326,17 @@ def test_example_retrieval_round_loop(tmp_path):
         assert os.path.exists(tmp_path / f), f
     posts = torch.load(tmp_path / "posteriors.pt", weights_only=False)          # modules.py:74 (-resume)
     assert posts[-1].sample((10,)).shape == (10, 10)
+
+
+def test_fused_conditioner_forty_parameters():
+    """c4 shapes on the fused kernel: 40 parameters -> the initial layer's contraction spans two k-blocks (D <= 64)."""
+    onet, net, theta, x = _c2_pair(13, "c4", C=96, T=4)
+    with torch.no_grad():
+        got = net.log_prob(theta[:700].cuda(), x[:70].cuda()).cpu().numpy()           # 10 atoms per context row
+        want = onet.log_prob(theta[:700], x[:70].repeat_interleave(10, dim=0)).numpy()
+    assert rel_err(got, want).max() < TOL, rel_err(got, want).max()
+    z = torch.randn(300, 40, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        s = net.sample(300, context=x[:1].cuda(), noise=z.cuda())[0].cpu().numpy()
+        ws = onet.sample(300, context=x[:1], noise=z)[0].numpy()
+    assert rel_err(s, ws).max() < TOL
