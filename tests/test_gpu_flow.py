@@ -340,3 +340,40 @@ def test_fused_conditioner_forty_parameters():
         s = net.sample(300, context=x[:1].cuda(), noise=z.cuda())[0].cpu().numpy()
         ws = onet.sample(300, context=x[:1], noise=z)[0].numpy()
     assert rel_err(s, ws).max() < TOL
+
+
+@pytest.mark.parametrize("D,Bk,K,A", [(22, 3, 10, 1), (8, 1, 8, 4), (64, 4, 5, 1), (36, 2, 16, 7)])
+def test_fused_conditioner_other_shapes(D, Bk, K, A):
+    """Block counts beyond the two whose biases sit in shared memory, a single block, the widest supported flow (64
+    parameters), odd numbers of spline parameters per row (TMA stores clip at d_tr * (3K-1)), atoms that do not divide 128."""
+    g = torch.Generator().manual_seed(100 + D)
+    torch.manual_seed(100 + D)
+    C, R = 24, 7 * 128 * A // A + 3 * A                      # several tiles, ragged
+    Rc = R // A
+    R = Rc * A
+    theta = torch.rand(1024, D, generator=g) * 6 - 3
+    x = torch.randn(1024, C, generator=g)
+    hp = dict(hidden_features=128, num_transforms=2, num_bins=K, num_blocks=Bk)
+    onet = O.build_nsf(theta, x, **hp)
+    O.randomize_lu(onet, g, 0.05)
+    with torch.no_grad():
+        for c in O.coupling_layers(onet):
+            for blk in c.transform_net.blocks:
+                blk.linear_layers[1].weight.add_(0.03 * torch.randn(blk.linear_layers[1].weight.shape, generator=g))
+    net = fb.NSFFlow(D, C, **hp)
+    net.load_state_dict(onet.state_dict())
+    net, onet = net.cuda().eval(), onet.eval()
+    th = theta[:R] if R <= 1024 else theta.repeat(2, 1)[:R]
+    with torch.no_grad():
+        got = net.log_prob(th.cuda(), x[:Rc].cuda()).cpu().numpy()
+        want = onet.log_prob(th, x[:Rc].repeat_interleave(A, dim=0)).numpy()
+    assert rel_err(got, want).max() < TOL, rel_err(got, want).max()
+    # training-mode forward + backward through the same kernel (saved activations via TMA stores)
+    th_g = th[:256].cuda().requires_grad_(True)
+    net.train()
+    lp = net.log_prob(th_g, x[:256].cuda())
+    lp.sum().backward()
+    tho = th[:256].clone().requires_grad_(True)
+    onet.train()
+    onet.log_prob(tho, x[:256]).sum().backward()
+    assert rel_err(th_g.grad.cpu().numpy(), tho.grad.numpy()).max() < 2e-3
