@@ -377,3 +377,40 @@ def test_fused_conditioner_other_shapes(D, Bk, K, A):
     onet.train()
     onet.log_prob(tho, x[:256]).sum().backward()
     assert rel_err(th_g.grad.cpu().numpy(), tho.grad.numpy()).max() < 2e-3
+
+
+def test_wide_conditioner_gemm_chain_hidden_512():
+    """c3-style conditioner (hidden 512, 4 blocks, 16 bins): the per-layer tcgen05 GEMM chain (the fused kernel covers
+    hidden 128 only) -- log_prob, samples and a training step's gradients against the oracle."""
+    from floppity_deprecated_b200.inference import _TrainEngine
+    g = torch.Generator().manual_seed(77)
+    torch.manual_seed(77)
+    D, C = 30, 96
+    theta = torch.rand(640, D, generator=g) * 6 - 3
+    x = torch.randn(640, C, generator=g)
+    hp = dict(hidden_features=512, num_transforms=3, num_bins=16, num_blocks=4)
+    onet = O.build_nsf(theta, x, **hp)
+    O.randomize_lu(onet, g, 0.04)
+    net = fb.NSFFlow(D, C, **hp)
+    net.load_state_dict(onet.state_dict())
+    net, onet = net.cuda().eval(), onet.eval()
+    with torch.no_grad():
+        got = net.log_prob(theta[:300].cuda(), x[:300].cuda()).cpu().numpy()
+        want = onet.log_prob(theta[:300], x[:300]).numpy()
+    assert rel_err(got, want).max() < TOL, rel_err(got, want).max()
+    z = torch.randn(200, D, generator=g)
+    with torch.no_grad():
+        s = net.sample(200, context=x[:1].cuda(), noise=z.cuda())[0].cpu().numpy()
+        ws = onet.sample(200, context=x[:1], noise=z)[0].numpy()
+    assert rel_err(s, ws).max() < TOL
+    net.train(); onet.train()
+    B = 256
+    prior = fb.BoxUniform(-3 * torch.ones(D), 3 * torch.ones(D), device="cuda")
+    eng = _TrainEngine(net, prior, B, False, 10, True, 5e-4, 5.0)
+    eng.step_on_batch(theta[:B].cuda(), net._standardize(x[:B].cuda()))
+    (-onet.log_prob(theta[:B], x[:B]).mean()).backward()
+    got_g = net.unpack(eng.grads[: net.param_count])
+    worst = 0.0
+    for k, p in onet.named_parameters():
+        worst = max(worst, float((got_g[k].cpu() - p.grad).abs().max()) / max(float(p.grad.abs().max()), 1e-4))
+    assert worst < 2e-3, worst
