@@ -76,6 +76,24 @@ __device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float (&v)[16])
         "r"(__float_as_uint(v[15]))
       : "memory");
 }
+// same with fp16 operands (two k per 32-bit TMEM column, K = 16 per instruction)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// instruction descriptor for kind::f16: D = f32, A = B = f16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -138,15 +156,33 @@ struct Stager {
   }
 };
 
-__device__ __forceinline__ void split16(const float (&w)[16], float (&hi)[16], float (&lo)[16]) {
+// 16 operand values of this thread's row, K columns kcol .. kcol+15: split into the two operand parts and written to
+// tensor memory.  TF32: one 32-bit column per k (hi | lo regions).  FP16: two k per column, residual scaled by 2^11.
+template <bool F16>
+__device__ __forceinline__ void put_operand16(uint32_t t_hi, uint32_t t_lo, uint32_t kcol, const float (&w)[16]) {
+  if (F16) {
+    uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) { hi[j] = tf32_round(w[j]); lo[j] = w[j] - hi[j]; }
+    for (int j = 0; j < 8; ++j) split_f16x2(w[2 * j], w[2 * j + 1], hi[j], lo[j]);
+    tmem_st_8(t_hi + (kcol >> 1), hi);
+    tmem_st_8(t_lo + (kcol >> 1), lo);
+  } else {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { hi[j] = tf32_round(w[j]); lo[j] = w[j] - hi[j]; }
+    tmem_st_16(t_hi + kcol, hi);
+    tmem_st_16(t_lo + kcol, lo);
+  }
 }
 
 #define CF_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && (slot) < 512) p.trace[(slot)] = clock64(); } while (0)
 
+template <bool F16>
 __global__ void __launch_bounds__(CF_THREADS, 1)
 k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
+  constexpr int KB_COLS = F16 ? 64 : 32;        // contraction columns per weight stage (one 128-byte swizzle row)
+  constexpr int NKB = 128 / KB_COLS;            // stages per hidden-128 contraction
+  constexpr float XS = F16 ? FP16_LO_UNSCALE : 1.f;   // the cross-term accumulator carries the 2^11 of the fp16 residual
   extern __shared__ __align__(1024) uint8_t cf_smem[];     // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = cf_smem;
   const uint32_t smem_a = smem_u32(smem);
@@ -164,7 +200,8 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
   const int64_t n_tiles = (p.R + CF_BM - 1) / CF_BM;
   const int Bk = p.Bk;
   const int nF = (p.dP + 127) / 128;            // 128-column units of the final layer
-  const int nkb0 = (p.D + 31) / 32;             // k-blocks of the initial layer (K = D <= 64)
+  const int nkb0 = F16 ? 1 : (p.D + 31) / 32;   // weight stages of the initial layer (K = D <= 64)
+  const int npc0 = (p.D + 31) / 32;             // 16-column theta pieces per thread (1 or 2)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CF_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -205,18 +242,18 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         ++it;
       };
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < nkb0; ++kb) stage(&maps.w0h, &maps.w0l, kb * 32, 0, 2 * CF_TILE_BYTES);
+        for (int kb = 0; kb < nkb0; ++kb) stage(&maps.w0h, &maps.w0l, kb * KB_COLS, 0, 2 * CF_TILE_BYTES);
         for (int k = 0; k < Bk; ++k)
           for (int g = 0; g < 2; ++g)
-            for (int kb = 0; kb < 4; ++kb) stage(&maps.wh, &maps.wl, kb * 32, k * 258 + g * 129, 2 * CF_TILE_BYTES);
+            for (int kb = 0; kb < NKB; ++kb) stage(&maps.wh, &maps.wl, kb * KB_COLS, F16 ? (2 * k + g) * 128 : k * 258 + g * 129, 2 * CF_TILE_BYTES);
         for (int j = 0; j < nF; ++j)
-          for (int kb = 0; kb < 4; ++kb) stage(&maps.wfh, &maps.wfl, kb * 32, j * 128, 2 * CF_TILE_BYTES);
+          for (int kb = 0; kb < NKB; ++kb) stage(&maps.wfh, &maps.wfl, kb * KB_COLS, j * 128, 2 * CF_TILE_BYTES);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc128 = make_idesc_tf32(128, 128);
+      constexpr uint32_t idesc128 = F16 ? make_idesc_f16(128, 128) : make_idesc_tf32(128, 128);
       const uint32_t t_ahi = tmem_base + CF_T_AHI, t_alo = tmem_base + CF_T_ALO;
       uint32_t it = 0, n_ar = 0, n_ae = 0;
       int pend = 0;          // final-layer units whose read-out has not been awaited yet
@@ -231,9 +268,16 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         for (int k = 0; k < nk; ++k) {
           const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
           const uint32_t acc = (!first || k > 0) ? 1u : 0u;
-          umma_tf32_ts(d_hh, t_ahi + acol + 8u * k, b_hi + adv, idesc, acc);
-          umma_tf32_ts(d_x, t_alo + acol + 8u * k, b_hi + adv, idesc, acc);
-          umma_tf32_ts(d_x, t_ahi + acol + 8u * k, b_lo + adv, idesc, 1u);
+          // one k-step = 32 bytes of every operand row: 8 tf32 or 16 fp16 contraction indices = 8 operand columns
+          if (F16) {
+            umma_f16_ts(d_hh, t_ahi + acol + 8u * k, b_hi + adv, idesc, acc);
+            umma_f16_ts(d_x, t_alo + acol + 8u * k, b_hi + adv, idesc, acc);
+            umma_f16_ts(d_x, t_ahi + acol + 8u * k, b_lo + adv, idesc, 1u);
+          } else {
+            umma_tf32_ts(d_hh, t_ahi + acol + 8u * k, b_hi + adv, idesc, acc);
+            umma_tf32_ts(d_x, t_alo + acol + 8u * k, b_hi + adv, idesc, acc);
+            umma_tf32_ts(d_x, t_ahi + acol + 8u * k, b_lo + adv, idesc, 1u);
+          }
         }
         umma_commit(&w_empty[s]);
         ++it;
@@ -256,13 +300,13 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         while (pend > 0) wait_drained();                  // (already true by program order: keeps the phase count in step)
         CF_TRACE(ts); ++ts;
         for (int kb = 0; kb < nkb0; ++kb)
-          kblock(d_hh, d_x, 32u * kb, min(4, (p.D - 32 * kb + 7) / 8), idesc128, kb == 0);
+          kblock(d_hh, d_x, 32u * kb, F16 ? (p.D + 15) / 16 : min(4, (p.D - 32 * kb + 7) / 8), idesc128, kb == 0);
         umma_commit(&acc_full[0]);
         CF_TRACE(ts); ++ts;
         for (int u = 0; u < 2 * Bk; ++u) {
           wait_operand();
           CF_TRACE(ts); ++ts;
-          for (int kb = 0; kb < 4; ++kb) kblock(d_hh, d_x, 32u * kb, 4, idesc128, kb == 0);
+          for (int kb = 0; kb < NKB; ++kb) kblock(d_hh, d_x, 32u * kb, 4, idesc128, kb == 0);
           umma_commit(&acc_full[0]);
           CF_TRACE(ts); ++ts;
         }
@@ -270,7 +314,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         CF_TRACE(ts); ++ts;
         for (int j = 0; j < nF; ++j) {
           if (pend > 0) wait_drained();                   // the read-out of the previous unit has drained the accumulators
-          for (int kb = 0; kb < 4; ++kb) kblock(d_hh, d_x, 32u * kb, 4, idesc128, kb == 0);
+          for (int kb = 0; kb < NKB; ++kb) kblock(d_hh, d_x, 32u * kb, 4, idesc128, kb == 0);
           umma_commit(&acc_full[0]);
           ++pend;
           CF_TRACE(ts); ++ts;
@@ -328,11 +372,11 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
       float4 aux[4], nxt[4];
 
       {  // ---- theta tile -> operand columns: this thread's half of the 32 (D <= 32) or 64 (D <= 64) padded columns
-        const int npc = nkb0;                 // 16-column pieces per thread: 1 or 2
+        const int npc = npc0;                 // 16-column pieces per thread: 1 or 2
         ldg16(ctx_row, aux);                  // first context piece of the initial layer, ahead of its accumulator
         prefetch_l1(ctx_row + 32);
         for (int pc = 0; pc < npc; ++pc) {
-          float w[16], hi[16], lo[16];
+          float w[16];
           const int c0 = hf * 16 * npc + pc * 16;
           const float* tp = p.theta + mc * p.D + c0;
 #pragma unroll
@@ -341,9 +385,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
             if (c0 + 4 * j < p.D) v = __ldg(reinterpret_cast<const float4*>(tp + 4 * j));
             w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
           }
-          split16(w, hi, lo);
-          tmem_st_16(t_ahi + c0, hi);
-          tmem_st_16(t_alo + c0, lo);
+          put_operand16<F16>(t_ahi, t_alo, (uint32_t)c0, w);
         }
         operand_done();
       }
@@ -354,22 +396,20 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         wait_acc(0);
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) {
-          float v[16], x[16], hi[16], lo[16];
+          float v[16], x[16];
           const uint32_t col = (uint32_t)(hf * 64 + pc * 16);
           if (pc < 3) ldg16(ctx_row + (pc + 1) * 16, nxt);
           else ldg16(ctx_row + 128, nxt);     // first gate piece of block 0
           tmem_ld_2x16(t_acc + col, t_acc + 128u + col, v, x);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            v[4 * j] += x[4 * j] + aux[j].x; v[4 * j + 1] += x[4 * j + 1] + aux[j].y;
-            v[4 * j + 2] += x[4 * j + 2] + aux[j].z; v[4 * j + 3] += x[4 * j + 3] + aux[j].w;
+            v[4 * j] += XS * x[4 * j] + aux[j].x; v[4 * j + 1] += XS * x[4 * j + 1] + aux[j].y;
+            v[4 * j + 2] += XS * x[4 * j + 2] + aux[j].z; v[4 * j + 3] += XS * x[4 * j + 3] + aux[j].w;
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) { hres[pc][j] = v[j]; x[j] = fmaxf(v[j], 0.f); }
           if (training) st.put16(slot, pc >> 1, pc & 1, v);
-          split16(x, hi, lo);
-          tmem_st_16(t_ahi + col, hi);
-          tmem_st_16(t_alo + col, lo);
+          put_operand16<F16>(t_ahi, t_alo, col, x);
 #pragma unroll
           for (int j = 0; j < 4; ++j) aux[j] = nxt[j];
         }
@@ -389,21 +429,19 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
           const uint32_t sbp = sbias_a + (uint32_t)k * 1024u;
 #pragma unroll
           for (int pc = 0; pc < 4; ++pc) {
-            float v[16], x[16], hi[16], lo[16];
+            float v[16], x[16];
             const uint32_t col = (uint32_t)(hf * 64 + pc * 16);
             tmem_ld_2x16(t_acc + col, t_acc + 128u + col, v, x);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 c = sb ? lds128(sbp + (uint32_t)(pc * 64 + j * 16)) : __ldg(reinterpret_cast<const float4*>(bp + pc * 16 + 4 * j));
-              v[4 * j] += x[4 * j] + c.x; v[4 * j + 1] += x[4 * j + 1] + c.y;
-              v[4 * j + 2] += x[4 * j + 2] + c.z; v[4 * j + 3] += x[4 * j + 3] + c.w;
+              v[4 * j] += XS * x[4 * j] + c.x; v[4 * j + 1] += XS * x[4 * j + 1] + c.y;
+              v[4 * j + 2] += XS * x[4 * j + 2] + c.z; v[4 * j + 3] += XS * x[4 * j + 3] + c.w;
             }
             if (training) st.put16(slot, pc >> 1, pc & 1, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = fmaxf(v[j], 0.f);
-            split16(x, hi, lo);
-            tmem_st_16(t_ahi + col, hi);
-            tmem_st_16(t_alo + col, lo);
+            put_operand16<F16>(t_ahi, t_alo, col, x);
           }
           operand_done();
           if (training) st.end(slot, &maps.t[k], hf * 64, (int)row0, 2);
@@ -419,7 +457,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
           const bool last = (k == Bk - 1);
 #pragma unroll
           for (int pc = 0; pc < 4; ++pc) {
-            float v[16], x[16], hi[16], lo[16];
+            float v[16], x[16];
             const uint32_t col = (uint32_t)(hf * 64 + pc * 16);
             if (pc < 3) ldg16(gp + (pc + 1) * 16, nxt);
             else if (!last) ldg16(gp + 128, nxt);       // first gate piece of the next block
@@ -427,8 +465,8 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 c = sb ? lds128(sbp + (uint32_t)(pc * 64 + j * 16)) : __ldg(reinterpret_cast<const float4*>(bp + pc * 16 + 4 * j));
-              v[4 * j] += x[4 * j] + c.x; v[4 * j + 1] += x[4 * j + 1] + c.y;
-              v[4 * j + 2] += x[4 * j + 2] + c.z; v[4 * j + 3] += x[4 * j + 3] + c.w;
+              v[4 * j] += XS * x[4 * j] + c.x; v[4 * j + 1] += XS * x[4 * j + 1] + c.y;
+              v[4 * j + 2] += XS * x[4 * j + 2] + c.z; v[4 * j + 3] += XS * x[4 * j + 3] + c.w;
             }
             if (training) st.put16(slot_u, pc >> 1, pc & 1, v);
 #pragma unroll
@@ -440,9 +478,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = last ? hres[pc][j] : fmaxf(hres[pc][j], 0.f);
-            split16(x, hi, lo);
-            tmem_st_16(t_ahi + col, hi);
-            tmem_st_16(t_alo + col, lo);
+            put_operand16<F16>(t_ahi, t_alo, col, x);
 #pragma unroll
             for (int j = 0; j < 4; ++j) aux[j] = nxt[j];
           }
@@ -468,7 +504,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
           const uint32_t col = (uint32_t)(hf * 64 + pc * 16);
           tmem_ld_2x16(t_acc + col, t_acc + 128u + col, o[pc], x);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) o[pc][e] += x[e];
+          for (int e = 0; e < 16; ++e) o[pc][e] += XS * x[e];
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -516,6 +552,59 @@ static bool fused_enabled() {
   return on == 1;
 }
 
+// Operand format of the fused kernel: 3xFP16 (default) or 3xTF32 (FLOPPITY_FUSED_FP16=0).  Both carry 22 mantissa bits
+// through three tensor-core products; fp16 operands take half the tensor-core time, half the TMEM columns and half
+// the weight bytes.  fp16's exponent range (6e-5 .. 65504 before precision degrades / saturates) covers what flows through
+// a conditioner's forward pass -- z-scored parameters, O(1..10) activations, O(1) weights; the gradient GEMMs, whose
+// operands span many more orders of magnitude, stay on 3xTF32.
+bool cond_fused_f16() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FLOPPITY_FUSED_FP16");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// fp16 hi / scaled-residual copies of one layer's matrices in the fused kernel's own layout (layout.h f16*)
+__global__ void k_prep_f16(const float* __restrict__ params, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, fp_nsf_config cfg) {
+  const Layout L(&cfg);
+  const int i = blockIdx.y;
+  const int H = L.H, D = L.D, dP = L.dP(i);
+  const int64_t nW = (int64_t)2 * L.Bk * H * H, nF = L.f16WfRows(i) * H, n = L.f16LayerHalves(i);
+  const int64_t base = L.f16LayerOff(i);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (e < nW) {
+      const int m = (int)(e / ((int64_t)H * H));
+      const int64_t r = e - (int64_t)m * H * H;
+      v = params[((m & 1) ? L.w2(i, m >> 1) : L.w1(i, m >> 1)) + r];
+    } else if (e < nW + nF) {
+      const int64_t r = e - nW;
+      v = (r / H < dP) ? params[L.wf(i) + r] : 0.f;
+    } else {
+      const int64_t r = e - nW - nF;
+      const int row = (int)(r / 64), col = (int)(r % 64);
+      v = (col < D) ? params[L.w0x(i) + (int64_t)row * D + col] : 0.f;
+    }
+    uint32_t h2, l2;
+    split_f16x2(v, 0.f, h2, l2);
+    hi[base + e] = (uint16_t)(h2 & 0xffffu);
+    lo[base + e] = (uint16_t)(l2 & 0xffffu);
+  }
+}
+bool cond_fwd_supported(const Layout& L, const float* prepared);
+int launch_cond_prepare(const fp_nsf_config* cfg, const float* params, float* prepared, cudaStream_t stream) {
+  Layout L(cfg);
+  if (!cond_fused_f16() || !cond_fwd_supported(L, prepared)) return 0;
+  ProfScope ps(TAG_OTHER, 0.0, stream);
+  dim3 grid(64, L.T);
+  k_prep_f16<<<grid, 256, 0, stream>>>(params, reinterpret_cast<uint16_t*>(prepared + L.prepF16Hi()),
+                                       reinterpret_cast<uint16_t*>(prepared + L.prepF16Lo()), *cfg);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
 // Shapes the fused kernel covers (a property of the flow, identical for every layer and every pass)
 bool cond_fwd_supported(const Layout& L, const float* prepared) {
   if (!tc_enabled() || !fused_enabled() || !prepared) return false;
@@ -532,15 +621,27 @@ int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* para
   if ((reinterpret_cast<uintptr_t>(ctx_all) & 15) || (reinterpret_cast<uintptr_t>(theta_i) & 15)) return FP_E_BADARG;
   const int dP = L.dP(i);
   CondFwdMaps maps;
-  const float* hi = prepared + L.prepHi();
-  const float* lo = prepared + L.prepLo();
+  const bool f16 = cond_fused_f16();
   bool ok = true;
-  ok = ok && get_tensor_map(hi + L.w0x(i), 128, L.D, L.D, &maps.w0h);
-  ok = ok && get_tensor_map(lo + L.w0x(i), 128, L.D, L.D, &maps.w0l);
-  ok = ok && get_tensor_map(hi + L.w1(i, 0), (int64_t)L.Bk * 258, 128, 128, &maps.wh);
-  ok = ok && get_tensor_map(lo + L.w1(i, 0), (int64_t)L.Bk * 258, 128, 128, &maps.wl);
-  ok = ok && get_tensor_map(hi + L.wf(i), dP, 128, 128, &maps.wfh);
-  ok = ok && get_tensor_map(lo + L.wf(i), dP, 128, 128, &maps.wfl);
+  if (f16) {
+    const uint16_t* hi = reinterpret_cast<const uint16_t*>(prepared + L.prepF16Hi());
+    const uint16_t* lo = reinterpret_cast<const uint16_t*>(prepared + L.prepF16Lo());
+    ok = ok && get_tensor_map_f16(hi + L.f16W0(i), 128, 64, 64, &maps.w0h);
+    ok = ok && get_tensor_map_f16(lo + L.f16W0(i), 128, 64, 64, &maps.w0l);
+    ok = ok && get_tensor_map_f16(hi + L.f16W(i, 0, 0), (int64_t)2 * L.Bk * 128, 128, 128, &maps.wh);
+    ok = ok && get_tensor_map_f16(lo + L.f16W(i, 0, 0), (int64_t)2 * L.Bk * 128, 128, 128, &maps.wl);
+    ok = ok && get_tensor_map_f16(hi + L.f16Wf(i), dP, 128, 128, &maps.wfh);
+    ok = ok && get_tensor_map_f16(lo + L.f16Wf(i), dP, 128, 128, &maps.wfl);
+  } else {
+    const float* hi = prepared + L.prepHi();
+    const float* lo = prepared + L.prepLo();
+    ok = ok && get_tensor_map(hi + L.w0x(i), 128, L.D, L.D, &maps.w0h);
+    ok = ok && get_tensor_map(lo + L.w0x(i), 128, L.D, L.D, &maps.w0l);
+    ok = ok && get_tensor_map(hi + L.w1(i, 0), (int64_t)L.Bk * 258, 128, 128, &maps.wh);
+    ok = ok && get_tensor_map(lo + L.w1(i, 0), (int64_t)L.Bk * 258, 128, 128, &maps.wl);
+    ok = ok && get_tensor_map(hi + L.wf(i), dP, 128, 128, &maps.wfh);
+    ok = ok && get_tensor_map(lo + L.wf(i), dP, 128, 128, &maps.wfl);
+  }
   ok = ok && get_tensor_map(prm, R, dP, L.ldP(i), &maps.prm);
   for (int k = 0; k <= CF_MAXBK; ++k) maps.h[k] = maps.prm;
   for (int k = 0; k < CF_MAXBK; ++k) { maps.t[k] = maps.prm; maps.u[k] = maps.prm; }
@@ -559,7 +660,8 @@ int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* para
 
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
     attr_set = true;
   }
   const int64_t tiles = (R + CF_BM - 1) / CF_BM;
@@ -580,7 +682,8 @@ int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* para
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = pdl_on ? 1 : 0;
-  FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd, maps, p));
+  if (f16) FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd<true>, maps, p));
+  else FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd<false>, maps, p));
   FP_LAUNCH_CHECK();
   return 0;
 }

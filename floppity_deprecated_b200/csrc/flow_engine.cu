@@ -44,6 +44,7 @@ int launch_rows_affine(const float*, const float*, const float*, float, const fl
 int launch_glu_bwd(const float*, const float*, const float*, int64_t, float*, float*, int64_t, int, int, int, cudaStream_t);
 int launch_gate_sigmoid(float*, int64_t, int64_t, int, int, cudaStream_t);
 bool cond_fwd_supported(const Layout& L, const float* prepared);      // cond_fused.cu
+int launch_cond_prepare(const fp_nsf_config* cfg, const float* params, float* prepared, cudaStream_t stream);
 int launch_ctx_reduce(const float*, float*, int64_t, int64_t, int, int, cudaStream_t);
 int launch_colsum(const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int launch_sum(const float*, int64_t, float, float*, cudaStream_t);
@@ -285,6 +286,7 @@ int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepare
     Layout L(cfg);
     FP_TRY(launch_split_tf32(params, prepared + L.prepHi(), prepared + L.prepLo(), L.total(), (cudaStream_t)stream));
     FP_TRY(launch_transpose_split_weights(cfg, params, prepared + L.prepTHi(), prepared + L.prepTLo(), (cudaStream_t)stream));
+    FP_TRY(launch_cond_prepare(cfg, params, prepared, (cudaStream_t)stream));     // fp16 operand copies for the fused conditioner
   }
   return 0;
 }

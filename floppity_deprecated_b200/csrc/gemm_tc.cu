@@ -670,6 +670,32 @@ bool get_tensor_map(const float* base, int64_t rows, int64_t cols, int64_t ld, C
   return true;
 }
 
+// 2-D fp16 row-major [rows, cols] with leading dimension ld (halves); box = 64 columns x box_rows rows, SWIZZLE_128B
+bool get_tensor_map_f16(const void* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out, int box_rows) {
+  typedef std::tuple<const void*, int64_t, int64_t, int64_t, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  Key key(base, rows, cols, ld, box_rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
+
 static long long* g_tc_trace = nullptr;
 static int g_tc_dbg = 0;     // debug switches of the TN kernel (fp_tc_set_debug): 1 no split, 2 no reductions, 4 two products
 

@@ -89,7 +89,19 @@ struct Layout {
   FP_LHD int64_t tTotal() const { return (tLayerOff(T) + 31) & ~int64_t(31); }
   FP_LHD int64_t prepTHi() const { return prepLo() + ((total() + 31) & ~int64_t(31)); }
   FP_LHD int64_t prepTLo() const { return prepTHi() + tTotal(); }
-  FP_LHD int64_t prepAll() const { return prepTLo() + tTotal(); }
+  // fused conditioner in 3xFP16 mode (cond_fused.cu): per layer, fp16 hi and scaled-residual lo copies of
+  //   [ W1_0 | W2_0 | W1_1 | ... (2*Bk matrices of H x H) | Wf (dP rows padded to a multiple of 8, H columns) | W0x (H x 64) ]
+  // (units below: halves; the regions are addressed as float offsets into `prepared`, two halves per float)
+  FP_LHD int64_t f16WfRows(int i) const { return (dP(i) + 7) & ~7; }
+  FP_LHD int64_t f16LayerHalves(int i) const { return (int64_t)2 * Bk * H * H + f16WfRows(i) * H + (int64_t)H * 64; }
+  FP_LHD int64_t f16LayerOff(int i) const { int64_t o = 0; for (int l = 0; l < i; ++l) o += f16LayerHalves(l); return o; }   // halves
+  FP_LHD int64_t f16W(int i, int k, int g) const { return f16LayerOff(i) + (int64_t)(2 * k + g) * H * H; }
+  FP_LHD int64_t f16Wf(int i) const { return f16LayerOff(i) + (int64_t)2 * Bk * H * H; }
+  FP_LHD int64_t f16W0(int i) const { return f16Wf(i) + f16WfRows(i) * H; }
+  FP_LHD int64_t f16Floats() const { return ((f16LayerOff(T) / 2) + 63) & ~int64_t(63); }
+  FP_LHD int64_t prepF16Hi() const { return ((prepTLo() + tTotal()) + 63) & ~int64_t(63); }
+  FP_LHD int64_t prepF16Lo() const { return prepF16Hi() + f16Floats(); }
+  FP_LHD int64_t prepAll() const { return prepF16Lo() + f16Floats(); }
 };
 
 // workspace carve; identical arithmetic in forward and backward so saved activations are found again

@@ -132,6 +132,29 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 
 // dimension ld (floats); box = 32 columns x box_rows rows, SWIZZLE_128B (atom32: SWIZZLE_128B_ATOM_32B)
 bool get_tensor_map(const float* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out, int box_rows = 128,
                     bool atom32 = false);
+bool get_tensor_map_f16(const void* base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out, int box_rows = 128);
 bool tc_enabled();
+
+// fp16 hi + scaled fp16 residual of an fp32 value ("3xFP16": 11 + 11 mantissa bits; the residual is carried at 2^11
+// so it stays in fp16's normal range, and the products that contain it are scaled back by 2^-11 when the two
+// accumulators are combined).  Saturating conversions: |x| beyond fp16's range clamps instead of becoming inf.
+constexpr float FP16_LO_SCALE = 2048.f, FP16_LO_UNSCALE = 1.f / 2048.f;
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float upper, float lower) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+  return d;
+}
+__device__ __forceinline__ float f16_bits_to_float(uint32_t h16) {
+  float f;
+  asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.f32.f16 %0, t;\n\t}" : "=f"(f) : "r"(h16));
+  return f;
+}
+// two consecutive values -> packed {hi(b) : hi(a)} and {lo'(b) : lo'(a)} (lower k in the low half)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = cvt_f16x2_sat(b, a);
+  const float ra = (a - f16_bits_to_float(hi2 & 0xffffu)) * FP16_LO_SCALE;
+  const float rb = (b - f16_bits_to_float(hi2 >> 16)) * FP16_LO_SCALE;
+  lo2 = cvt_f16x2_sat(rb, ra);
+}
 
 }  // namespace fp
