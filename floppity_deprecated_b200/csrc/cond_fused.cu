@@ -364,31 +364,37 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
     const uint32_t sbias_a = smem_u32(sbias) + (uint32_t)hf * 256u;
     float hres[4][16];      // this row's residual stream, columns hf*64 .. hf*64+63
 
+    const float* ctx_row = nullptr;
+    float4 aux[4], nxt[4];
+    // theta tile -> operand columns: this thread's half of the 32 (D <= 32) or 64 (D <= 64) padded columns; also points
+    // ctx_row at the tile's context row and requests its first piece.  Runs for the first tile before the loop and for
+    // every further tile right after the previous tile's last accumulator has been drained (all MMAs that read the old
+    // operand are complete by then), so the next tile's first GEMM overlaps the previous tile's last store.
+    auto theta_operand = [&](int64_t tile) {
+      const int64_t m = tile * CF_BM + q * 32 + lane;
+      const int64_t mc = m < p.R ? m : p.R - 1;
+      ctx_row = p.ctx + (int64_t)((uint32_t)mc / cdiv) * p.ldg + hf * 64;
+      const int npc = npc0;                   // 16-column pieces per thread: 1 or 2
+      ldg16(ctx_row, aux);                    // first context piece of the initial layer, ahead of its accumulator
+      prefetch_l1(ctx_row + 32);
+      for (int pc = 0; pc < npc; ++pc) {
+        float w[16];
+        const int c0 = hf * 16 * npc + pc * 16;
+        const float* tp = p.theta + mc * p.D + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c0 + 4 * j < p.D) v = __ldg(reinterpret_cast<const float4*>(tp + 4 * j));
+          w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+        }
+        put_operand16<F16>(t_ahi, t_alo, (uint32_t)c0, w);
+      }
+      operand_done();
+    };
+    if ((int64_t)blockIdx.x < n_tiles) theta_operand(blockIdx.x);
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t row0 = tile * CF_BM;
-      const int64_t m = row0 + q * 32 + lane;
-      const int64_t mc = m < p.R ? m : p.R - 1;
-      const float* ctx_row = p.ctx + (int64_t)((uint32_t)mc / cdiv) * p.ldg + hf * 64;
-      float4 aux[4], nxt[4];
-
-      {  // ---- theta tile -> operand columns: this thread's half of the 32 (D <= 32) or 64 (D <= 64) padded columns
-        const int npc = npc0;                 // 16-column pieces per thread: 1 or 2
-        ldg16(ctx_row, aux);                  // first context piece of the initial layer, ahead of its accumulator
-        prefetch_l1(ctx_row + 32);
-        for (int pc = 0; pc < npc; ++pc) {
-          float w[16];
-          const int c0 = hf * 16 * npc + pc * 16;
-          const float* tp = p.theta + mc * p.D + c0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c0 + 4 * j < p.D) v = __ldg(reinterpret_cast<const float4*>(tp + 4 * j));
-            w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
-          }
-          put_operand16<F16>(t_ahi, t_alo, (uint32_t)c0, w);
-        }
-        operand_done();
-      }
 
       {  // ---- initial layer: h0 = acc + ctx slot 0
         uint32_t slot = 0;
@@ -509,6 +515,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[0]);
+        if (j == nF - 1 && tile + (int64_t)gridDim.x < n_tiles) theta_operand(tile + gridDim.x);
         const int n0 = j * 128 + hf * 64;
         if (n0 + 64 <= p.dP) {
 #pragma unroll
