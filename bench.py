@@ -399,7 +399,8 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: SNPE-C NSF T{cfg.transforms} K{cfg.bins} H{cfg.hidden} Bk{cfg.blocks}, "
-                                   f"{cfg.D} params / {cfg.C} bins, atoms {cfg.atoms} (BASELINE.json configs[1])",
+                                   f"{cfg.D} params / {cfg.C} bins, atoms {cfg.atoms} "
+                                   f"(BASELINE.json configs[{['c1', 'c2', 'c3', 'c4'].index(args.config)}])",
                        "loss": args.loss, "per_gpu_batch": B, "global_batch": B * world, "flow_rows_per_step": eng.R * world,
                        "resident_rows_per_gpu": args.rows, "parallelism": f"dp{world}",
                        "l2": f"no flush: per-step activation workspace {ws_gb:.2f} GB >> 126 MB L2"},
