@@ -68,7 +68,7 @@ __device__ __forceinline__ RqsSmem carve(unsigned char* base, int tile_floats, i
   float* f = reinterpret_cast<float*>(base);
   for (int i = 0; i < RQS_STAGES; ++i) { s.stage[i] = f; f += s.stage_floats; }
   s.ladbuf = f; f += rows * d_tr;
-  s.luM = f; if (lu) f += D * D;
+  s.luM = f; if (lu) f += D * D + D;           // M^T, then the (signed) pre-bias
   uintptr_t p = (reinterpret_cast<uintptr_t>(f) + 7) & ~uintptr_t(7);
   s.bars = reinterpret_cast<uint64_t*>(p);
   return s;
@@ -76,7 +76,7 @@ __device__ __forceinline__ RqsSmem carve(unsigned char* base, int tile_floats, i
 
 static size_t rqs_smem_bytes(int tile_floats, int rows, int D, int d_tr, bool lu) {
   const int RQS_STAGES = rqs_stages();
-  size_t f = (size_t)RQS_STAGES * (tile_floats + rows * D + rows) + (size_t)rows * d_tr + (lu ? (size_t)D * D : 0);
+  size_t f = (size_t)RQS_STAGES * (tile_floats + rows * D + rows) + (size_t)rows * d_tr + (lu ? (size_t)D * D + D : 0);
   return f * 4 + 8 + RQS_STAGES * 8 + 16;
 }
 
@@ -128,7 +128,12 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
     for (int i = 0; i < RQS_STAGES; ++i) mbar_init(&s.bars[i], 1);
     mbar_fence_init();
   }
-  if (lu) for (int i = threadIdx.x; i < D * D; i += blockDim.x) s.luM[i] = a.luM[i];
+  // M is kept TRANSPOSED in shared memory: in phase 2 consecutive threads own consecutive output features f of a row,
+  // so for a fixed k they read consecutive words M^T[k][f] (conflict-free) while x[k] is a broadcast; with the
+  // row-major copy the stride between threads was D words (4-way bank conflicts at D = 40)
+  if (lu) for (int i = threadIdx.x; i < D * D; i += blockDim.x) s.luM[(i % D) * D + i / D] = a.luM[i];
+  float* const spre = s.luM + D * D;
+  if (lu) for (int i = threadIdx.x; i < D; i += blockDim.x) spre[i] = a.luPre ? a.pre_sign * a.luPre[i] : 0.f;
   const float lu_ld = a.lu_logdet ? *a.lu_logdet : 0.f;
   __syncthreads();
 
@@ -184,12 +189,12 @@ __global__ void __launch_bounds__(512) k_rqs_apply(RqsArgs a) {
       if (a.theta_sp) a.theta_sp[r0 * D + i] = v;
       if (lu) {
         const float* xr = rowbuf + row * D;
-        const float* m = s.luM + f * D;
+        const float* m = s.luM + f;              // column f of M^T = row f of M
         float acc = 0.f;
         if (a.luPre) {
-          for (int k = 0; k < D; ++k) acc = fmaf(m[k], xr[k] + a.pre_sign * a.luPre[k], acc);
+          for (int k = 0; k < D; ++k) acc = fmaf(m[k * D], xr[k] + spre[k], acc);
         } else {
-          for (int k = 0; k < D; ++k) acc = fmaf(m[k], xr[k], acc);
+          for (int k = 0; k < D; ++k) acc = fmaf(m[k * D], xr[k], acc);
         }
         v = acc + (a.luPost ? a.luPost[f] : 0.f);
       }
