@@ -54,6 +54,7 @@ struct CondFwdParams {
   const float* b1[CF_MAXBK]; const float* b2[CF_MAXBK]; const float* bf;
   int64_t R; int32_t Bk; int32_t dP; int32_t training;
   long long* trace;      // debug: SM-clock stamps of CTA 0 (fp_cf_set_trace)
+  int32_t* status;       // optional status words; [2] counts operand pieces beyond fp16's range (3xFP16 mode)
 };
 
 // D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32 (A: lane = row, one 32-bit column per k)
@@ -159,8 +160,15 @@ struct Stager {
 // 16 operand values of this thread's row, K columns kcol .. kcol+15: split into the two operand parts and written to
 // tensor memory.  TF32: one 32-bit column per k (hi | lo regions).  FP16: two k per column, residual scaled by 2^11.
 template <bool F16>
-__device__ __forceinline__ void put_operand16(uint32_t t_hi, uint32_t t_lo, uint32_t kcol, const float (&w)[16]) {
+__device__ __forceinline__ void put_operand16(uint32_t t_hi, uint32_t t_lo, uint32_t kcol, const float (&w)[16],
+                                              int32_t* status) {
   if (F16) {
+    // the conversions saturate at +-65504: count pieces that reach the edge of fp16's range so the host can say so
+    // (z-scored inputs and O(1..10) activations never do; the host then re-runs with FLOPPITY_FUSED_FP16=0)
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fabsf(w[j]));
+    if (mx > 6.0e4f && status) atomicAdd(status + 2, 1);
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) split_f16x2(w[2 * j], w[2 * j + 1], hi[j], lo[j]);
@@ -387,7 +395,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
           if (c0 + 4 * j < p.D) v = __ldg(reinterpret_cast<const float4*>(tp + 4 * j));
           w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
         }
-        put_operand16<F16>(t_ahi, t_alo, (uint32_t)c0, w);
+        put_operand16<F16>(t_ahi, t_alo, (uint32_t)c0, w, p.status);
       }
       operand_done();
     };
@@ -415,7 +423,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) { hres[pc][j] = v[j]; x[j] = fmaxf(v[j], 0.f); }
           if (training) st.put16(slot, pc >> 1, pc & 1, v);
-          put_operand16<F16>(t_ahi, t_alo, col, x);
+          put_operand16<F16>(t_ahi, t_alo, col, x, p.status);
 #pragma unroll
           for (int j = 0; j < 4; ++j) aux[j] = nxt[j];
         }
@@ -447,7 +455,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
             if (training) st.put16(slot, pc >> 1, pc & 1, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = fmaxf(v[j], 0.f);
-            put_operand16<F16>(t_ahi, t_alo, col, x);
+            put_operand16<F16>(t_ahi, t_alo, col, x, p.status);
           }
           operand_done();
           if (training) st.end(slot, &maps.t[k], hf * 64, (int)row0, 2);
@@ -484,7 +492,7 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = last ? hres[pc][j] : fmaxf(hres[pc][j], 0.f);
-            put_operand16<F16>(t_ahi, t_alo, col, x);
+            put_operand16<F16>(t_ahi, t_alo, col, x, p.status);
 #pragma unroll
             for (int j = 0; j < 4; ++j) aux[j] = nxt[j];
           }
@@ -622,7 +630,7 @@ bool cond_fwd_supported(const Layout& L, const float* prepared) {
 // Returns FP_E_NOTREADY when the shape is outside what the fused kernel covers (the caller then runs the GEMM chain).
 int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
                     const float* theta_i, const float* ctx_all, int64_t R, int ctx_div, float* const* h, float* const* t,
-                    float* const* u, float* prm, bool training, cudaStream_t stream) {
+                    float* const* u, float* prm, bool training, int32_t* status, cudaStream_t stream) {
   if (!cond_fwd_supported(L, prepared)) return FP_E_NOTREADY;
   if (R < 1 || R > 2147483647LL - 256) return FP_E_TOOLARGE;
   if ((reinterpret_cast<uintptr_t>(ctx_all) & 15) || (reinterpret_cast<uintptr_t>(theta_i) & 15)) return FP_E_BADARG;
@@ -664,6 +672,7 @@ int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* para
   p.bf = params + L.bf(i);
   p.R = R; p.Bk = L.Bk; p.dP = dP; p.training = training ? 1 : 0;
   p.trace = g_cf_trace;
+  p.status = status;
 
   static bool attr_set = false;
   if (!attr_set) {

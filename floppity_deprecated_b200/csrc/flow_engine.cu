@@ -26,7 +26,7 @@ int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params
 bool tc_enabled();
 int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
                     const float* theta_i, const float* ctx_all, int64_t R, int ctx_div, float* const* h, float* const* t,
-                    float* const* u, float* prm, bool training, cudaStream_t stream);       // cond_fused.cu
+                    float* const* u, float* prm, bool training, int32_t* status, cudaStream_t stream);       // cond_fused.cu
 int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                      float* theta_out, float* theta_sp, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status,
                      const float* luM, const float* luPre, float pre_sign, const float* luPost,
@@ -169,12 +169,12 @@ struct CondBufs {
 static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
                                const float* theta_i,
                                const float* ctx_all, int64_t R, int ctx_div, const CondBufs& b, bool training,
-                               uint64_t seed, bool fused, cudaStream_t s) {
+                               uint64_t seed, bool fused, int32_t* status, cudaStream_t s) {
   const int H = L.H, D = L.D;
   const float drop = training ? cfg->dropout_p : 0.f;
   if (fused) {   // hidden 128: the whole chain in one persistent tcgen05 kernel (activations stay in TMEM); the gate
                  // slots of ctx_all already hold sigmoid(gate), so there is no falling back to the GEMM chain from here
-    return launch_cond_fwd(cfg, L, params, prepared, i, theta_i, ctx_all, R, ctx_div, b.h, b.t, b.u, b.prm, training, s);
+    return launch_cond_fwd(cfg, L, params, prepared, i, theta_i, ctx_all, R, ctx_div, b.h, b.t, b.u, b.prm, training, status, s);
   }
   {  // initial layer: h0 = theta_i @ W0x^T + (ctx @ W0ctx^T + b0)   [the bracket is a column block of ctx_all]
     fp_gemm_args g = gemm_nt(theta_i, D, params + L.w0x(i), D, b.h[0], H, R, H, D, FP_G_ADD_CTX);
@@ -338,7 +338,7 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
       b.prm = ws + W.prm;
       th_next = (th_cur == ws + W.th_a) ? ws + W.th_b : ws + W.th_a;
     }
-    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, fused, s));
+    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, fused, status, s));
     FP_TRY(launch_rqs_apply(false, cfg, i & 1, th_cur, b.prm, th_next, th_sp, logdet, nullptr, R, status,
                             prepared + L.prepM(i), nullptr, 1.f, params + L.luBias(i), prepared + L.prepLogdet(i), L.ldP(i), s));
     th_cur = th_next;
@@ -446,7 +446,7 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
     for (int k = 0; k <= L.Bk; ++k) b.h[k] = ws + W.h;
     for (int k = 0; k < L.Bk; ++k) { b.t[k] = ws + W.t; b.u[k] = nullptr; }
     b.prm = ws + W.prm;
-    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, false, 0, fused, s));
+    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, false, 0, fused, status, s));
     // spline inverse of layer i fused with the inverse LULinear of layer i-1
     const float* M = (i > 0) ? prepared + L.prepMinv(i - 1) : nullptr;
     const float* pre = (i > 0) ? params + L.luBias(i - 1) : nullptr;

@@ -68,6 +68,14 @@ class BoxUniform:
         return self.low + torch.rand(shape, device=self.low.device) * (self.high - self.low)
 
 
+def _check_fp16_range(st) -> None:
+    if len(st) > 2 and st[2]:
+        raise FloatingPointError(
+            f"{st[2]} operand pieces of the fused conditioner reached the edge of fp16's range (|value| > 6e4): the 3xFP16 "
+            "operand format does not cover this flow's activations -- set FLOPPITY_FUSED_FP16=0 (3xTF32 operands) and "
+            "check that the observations are z-scored")
+
+
 # ---------------------------------------------------------------------------------------------------------
 class _TrainEngine:
     """One optimiser step of ``PosteriorEstimator.train`` as a fixed kernel sequence on preallocated buffers."""
@@ -255,6 +263,7 @@ class _TrainEngine:
 
     def check_status(self):
         st = self.status.tolist()
+        _check_fp16_range(st)
         if st[0] or st[1]:
             raise AssertionError(f"non-finite log-probs or atoms outside the prior: {st[0]}, negative spline discriminants: {st[1]}")
 
@@ -488,6 +497,7 @@ class DirectPosterior:
         dev = net._flat.device
         out = torch.empty(num_samples, net.D, dtype=torch.float32, device=dev)
         counter = torch.zeros(1, dtype=torch.int64, device=dev)        # accepted so far (device side)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
         low, high = self._box(dev)
         num_remaining, num_total, num_accepted = num_samples, 0, 0
         bs = min(num_samples, max_sampling_batch_size)
@@ -495,12 +505,16 @@ class DirectPosterior:
         warned = False
         while num_remaining > 0:
             z = torch.randn(bs, net.D, device=dev, dtype=torch.float32)
-            cand = net.inverse_rows(z, ctx_std)
+            cand = net.inverse_rows(z, ctx_std, status)
             # in-support rows are appended to `out` on the device; the only host round trip per batch is the count
             _lib.check(_lib.lib().fp_compact_inside(_lib.ptr(cand), _lib.ptr(low), _lib.ptr(high), _lib.ptr(out),
                                                     _lib.ptr(counter), bs, net.D, num_samples, _lib.stream()),
                        "fp_compact_inside")
             num_accepted = int(counter.item())
+            st = status.tolist()                      # (the count above already synchronised)
+            _check_fp16_range(st)
+            if st[0]:
+                raise AssertionError(f"the flow produced {st[0]} non-finite samples")
             num_total += bs
             num_remaining = num_samples - num_accepted
             acceptance_rate = num_accepted / num_total

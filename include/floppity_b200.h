@@ -16,7 +16,8 @@
  *   - nothing is allocated or freed here; kernels are enqueued on `stream` (a cudaStream_t
  *     passed as void*) and the call returns without synchronising;
  *   - return value: 0 = ok, >0 = cudaError_t of a failed launch, <0 = FP_E_* below;
- *   - `status` words are device int32[4]: {n_nonfinite, n_negative_discriminant, 0, 0},
+ *   - `status` words are device int32[4]: {n_nonfinite, n_negative_discriminant, n_fp16_range (operand pieces of the
+ *     fused conditioner that reached the edge of fp16's range in 3xFP16 mode; re-run with FLOPPITY_FUSED_FP16=0), 0},
  *     accumulated with atomics so the Python wrapper can raise like upstream's
  *     assert_all_finite / `assert (discriminant >= 0).all()`.
  */

@@ -414,3 +414,28 @@ def test_wide_conditioner_gemm_chain_hidden_512():
     for k, p in onet.named_parameters():
         worst = max(worst, float((got_g[k].cpu() - p.grad).abs().max()) / max(float(p.grad.abs().max()), 1e-4))
     assert worst < 2e-3, worst
+
+
+def test_fp16_operand_range_guard():
+    """The fused conditioner's 3xFP16 operands saturate beyond +-65504: a flow whose activations get there is reported
+    through the status word (FloatingPointError naming the FLOPPITY_FUSED_FP16=0 switch), never silently wrong."""
+    import os
+    from floppity_deprecated_b200 import _lib
+    from floppity_deprecated_b200.inference import _TrainEngine
+    if os.environ.get("FLOPPITY_FUSED_FP16", "1") == "0" or os.environ.get("FLOPPITY_FUSED", "1") == "0":
+        pytest.skip("3xFP16 fused conditioner switched off")
+    torch.manual_seed(0)
+    D, C = 8, 16
+    theta, x = torch.rand(512, D) * 6 - 3, torch.randn(512, C)
+    net = fb.build_nsf(theta, x, hidden_features=128, num_transforms=2, num_bins=6, num_blocks=1).cuda()
+    prior = fb.BoxUniform(-3 * torch.ones(D), 3 * torch.ones(D), device="cuda")
+    post = fb.DirectPosterior(net, prior).set_default_x(x[:1])
+    assert post.sample((64,)).shape == (64, D)                           # a sane flow: no complaint
+    with torch.no_grad():
+        net.view(0, _lib.P_CTX_B, 0).fill_(3.0e5)                        # h0 = 3e5 everywhere: outside fp16
+    with pytest.raises(FloatingPointError, match="FLOPPITY_FUSED_FP16=0"):
+        post.sample((64,))
+    eng = _TrainEngine(net.train(), prior, 128, False, 10, True, 5e-4, 5.0)
+    eng.step_on_batch(theta[:128].cuda(), net._standardize(x[:128].cuda()))
+    with pytest.raises(FloatingPointError):
+        eng.check_status()
