@@ -521,7 +521,10 @@ class DirectPosterior:
             if not warned and num_total > 1000 and acceptance_rate < 0.01:
                 warnings.warn(f"Only {acceptance_rate:.3%} proposal samples are accepted; the posterior leaks out of the prior.")
                 warned = True
-            bs = min(max_sampling_batch_size, max(int(1.5 * num_remaining / max(acceptance_rate, 1e-12)), 100))
+            # upstream over-draws the remainder by 1.5x; the draws are i.i.d., so the factor only trades wasted draws
+            # against an extra (small) round: 1.1x once the remainder is large enough for the binomial noise not to matter
+            over = 1.1 if num_remaining > 20_000 else 1.5
+            bs = min(max_sampling_batch_size, max(int(over * num_remaining / max(acceptance_rate, 1e-12)), 100))
         return out, acceptance_rate
 
     def sample(self, sample_shape=torch.Size(), x=None, max_sampling_batch_size: Optional[int] = None,
