@@ -22,7 +22,7 @@ FP_E = {-1: "FP_E_BADARG", -2: "FP_E_TOOLARGE", -3: "FP_E_NOTREADY"}
 P_CTX_W, P_CTX_B, P_W0X, P_W1, P_B1, P_W2, P_B2, P_WF, P_BF, P_LU_LOWER, P_LU_UPPER, P_LU_DIAG, P_LU_BIAS = range(13)
 # fp_gemm_flags
 G_RELU_A, G_RELU_B, G_BIAS, G_ADD_CTX, G_GLU_RES, G_RELUMASK, G_ACCUM, G_ATOMIC, G_TF32X3 = 1, 2, 4, 8, 16, 32, 64, 128, 256
-G_COLSUM_A = 4096
+G_COLSUM_A, G_DROP_OUT = 4096, 8192
 
 
 class NsfConfig(Structure):
@@ -51,7 +51,7 @@ class GemmArgs(Structure):
                 ("Rsd", c_void_p), ("ldr", c_int64),
                 ("U", c_void_p), ("ldu", c_int64),
                 ("Msk", c_void_p), ("ldm", c_int64),
-                ("split_k", c_int32)]
+                ("split_k", c_int32), ("mask_scale", c_float), ("drop_p", c_float), ("drop_seed", c_uint64)]
 
 
 _CFG = POINTER(NsfConfig)
@@ -74,6 +74,9 @@ SIGNATURES = {
     "fp_split_tf32": (c_int32, [_P, _P, _P, c_int64, _P]),
     "fp_gemm_tc_tn": (c_int32, [POINTER(GemmArgs), _P]),
     "fp_tc_set_trace": (c_int32, [_P]),
+    "fp_dropout_mask": (c_int32, [_P, c_int64, c_int32, c_float, c_uint64, _P]),
+    "fp_dropout_layer_seed": (c_uint64, [c_uint64, c_int32, c_int32]),
+    "fp_set_mode": (c_int32, [c_int32, c_int32, c_int32, c_int32]),
     "fp_nsf_prepare": (c_int32, [_CFG, _P, _P, _P]),
     "fp_nsf_logprob_forward": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, _P, _P, c_int32,
                                          c_uint64, _P, _P]),

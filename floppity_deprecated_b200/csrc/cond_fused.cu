@@ -55,6 +55,8 @@ struct CondFwdParams {
   int64_t R; int32_t Bk; int32_t dP; int32_t training;
   long long* trace;      // debug: SM-clock stamps of CTA 0 (fp_cf_set_trace)
   int32_t* status;       // optional status words; [2] counts operand pieces beyond fp16's range (3xFP16 mode)
+  DropKey dk[CF_MAXBK];  // dropout mask keys of the blocks (training with dropout_p > 0; nflows ResidualBlock.dropout)
+  int32_t drop_on;
 };
 
 // D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32 (A: lane = row, one 32-bit column per k)
@@ -185,7 +187,7 @@ __device__ __forceinline__ void put_operand16(uint32_t t_hi, uint32_t t_lo, uint
 
 #define CF_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && (slot) < 512) p.trace[(slot)] = clock64(); } while (0)
 
-template <bool F16>
+template <bool F16, bool DROP>
 __global__ void __launch_bounds__(CF_THREADS, 1)
 k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
   constexpr int KB_COLS = F16 ? 64 : 32;        // contraction columns per weight stage (one 128-byte swizzle row)
@@ -452,6 +454,19 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
               v[4 * j] += XS * x[4 * j] + c.x; v[4 * j + 1] += XS * x[4 * j + 1] + c.y;
               v[4 * j + 2] += XS * x[4 * j + 2] + c.z; v[4 * j + 3] += XS * x[4 * j + 3] + c.w;
             }
+            if (DROP) {
+              // t' = dropout(t): element (row, col) of the [R, 128] activation, pairs of columns share one hash word
+              // (gemm_epilogue.cuh drop_word); what is saved and what feeds the next GEMM both come from t'
+              const uint64_t w0 = ((uint64_t)(row0 + q * 32 + lane) * 128u + col) >> 1;
+              const float ds = p.dk[k].scale;
+              const uint32_t thr = p.dk[k].thr;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t w = drop_word(p.dk[k], w0 + (uint64_t)j);
+                v[2 * j] = (w & 0xffffu) >= thr ? v[2 * j] * ds : 0.f;
+                v[2 * j + 1] = (w >> 16) >= thr ? v[2 * j + 1] * ds : 0.f;
+              }
+            }
             if (training) st.put16(slot, pc >> 1, pc & 1, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = fmaxf(v[j], 0.f);
@@ -558,28 +573,14 @@ k_cond_fwd(const __grid_constant__ CondFwdMaps maps, const CondFwdParams p) {
 
 static long long* g_cf_trace = nullptr;
 
-static bool fused_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("FLOPPITY_FUSED");
-    on = (e && e[0] == '0') ? 0 : 1;
-  }
-  return on == 1;
-}
-
-// Operand format of the fused kernel: 3xFP16 (default) or 3xTF32 (FLOPPITY_FUSED_FP16=0).  Both carry 22 mantissa bits
-// through three tensor-core products; fp16 operands take half the tensor-core time, half the TMEM columns and half
-// the weight bytes.  fp16's exponent range (6e-5 .. 65504 before precision degrades / saturates) covers what flows through
-// a conditioner's forward pass -- z-scored parameters, O(1..10) activations, O(1) weights; the gradient GEMMs, whose
-// operands span many more orders of magnitude, stay on 3xTF32.
-bool cond_fused_f16() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("FLOPPITY_FUSED_FP16");
-    on = (e && e[0] == '0') ? 0 : 1;
-  }
-  return on == 1;
-}
+bool fused_enabled();      // flow_engine.cu (fp_set_mode)
+uint64_t layer_seed(uint64_t seed, int layer, int block);
+// Operand format of the fused kernel: 3xFP16 (default) or 3xTF32 (FLOPPITY_FUSED_FP16=0 / fp_set_mode).  Both carry 22
+// mantissa bits through three tensor-core products; fp16 operands take half the tensor-core time, half the TMEM columns
+// and half the weight bytes.  fp16's exponent range (6e-5 .. 65504 before precision degrades / saturates) covers what
+// flows through a conditioner's forward pass -- z-scored parameters, O(1..10) activations, O(1) weights; the gradient
+// GEMMs, whose operands span many more orders of magnitude, stay on 3xTF32.
+bool cond_fused_f16();
 
 // fp16 hi / scaled-residual copies of one layer's matrices in the fused kernel's own layout (layout.h f16*)
 __global__ void k_prep_f16(const float* __restrict__ params, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, fp_nsf_config cfg) {
@@ -630,7 +631,8 @@ bool cond_fwd_supported(const Layout& L, const float* prepared) {
 // Returns FP_E_NOTREADY when the shape is outside what the fused kernel covers (the caller then runs the GEMM chain).
 int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
                     const float* theta_i, const float* ctx_all, int64_t R, int ctx_div, float* const* h, float* const* t,
-                    float* const* u, float* prm, bool training, int32_t* status, cudaStream_t stream) {
+                    float* const* u, float* prm, bool training, float drop_p, uint64_t drop_seed, int32_t* status,
+                    cudaStream_t stream) {
   if (!cond_fwd_supported(L, prepared)) return FP_E_NOTREADY;
   if (R < 1 || R > 2147483647LL - 256) return FP_E_TOOLARGE;
   if ((reinterpret_cast<uintptr_t>(ctx_all) & 15) || (reinterpret_cast<uintptr_t>(theta_i) & 15)) return FP_E_BADARG;
@@ -673,11 +675,15 @@ int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* para
   p.R = R; p.Bk = L.Bk; p.dP = dP; p.training = training ? 1 : 0;
   p.trace = g_cf_trace;
   p.status = status;
+  p.drop_on = (training && drop_p > 0.f) ? 1 : 0;
+  for (int k = 0; k < L.Bk; ++k) p.dk[k] = make_drop_key(layer_seed(drop_seed, i, k), drop_p);
 
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
-    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_cond_fwd<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
     attr_set = true;
   }
   const int64_t tiles = (R + CF_BM - 1) / CF_BM;
@@ -698,8 +704,13 @@ int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* para
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = pdl_on ? 1 : 0;
-  if (f16) FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd<true>, maps, p));
-  else FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd<false>, maps, p));
+  if (p.drop_on) {
+    if (f16) FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd<true, true>, maps, p));
+    else FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd<false, true>, maps, p));
+  } else {
+    if (f16) FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd<true, false>, maps, p));
+    else FP_CUDA_OK(cudaLaunchKernelEx(&lc, k_cond_fwd<false, false>, maps, p));
+  }
   FP_LAUNCH_CHECK();
   return 0;
 }

@@ -14,11 +14,12 @@
 #include "layout.h"
 #include "prof.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace fp {
 
 // from the other translation units
-int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int drop_width, cudaStream_t stream);
+int launch_gemm(const fp_gemm_args* a, cudaStream_t stream);
 int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, cudaStream_t stream);   // gemm_tc.cu
 int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream);
 int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
@@ -26,7 +27,8 @@ int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params
 bool tc_enabled();
 int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
                     const float* theta_i, const float* ctx_all, int64_t R, int ctx_div, float* const* h, float* const* t,
-                    float* const* u, float* prm, bool training, int32_t* status, cudaStream_t stream);       // cond_fused.cu
+                    float* const* u, float* prm, bool training, float drop_p, uint64_t drop_seed, int32_t* status,
+                    cudaStream_t stream);       // cond_fused.cu
 int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const float* theta_in, const float* params,
                      float* theta_out, float* theta_sp, float* logdet, int32_t* bin_idx, int64_t R, int32_t* status,
                      const float* luM, const float* luPre, float pre_sign, const float* luPost,
@@ -50,6 +52,21 @@ int launch_colsum(const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int launch_sum(const float*, int64_t, float, float*, cudaStream_t);
 __global__ void k_lu_prepare(const float*, float*, fp_nsf_config);
 __global__ void k_lu_finish(const float*, const float*, float*, fp_nsf_config);
+
+// ---- run-time switches of the conditioner paths (fp_set_mode; the environment gives the initial values) ----
+static int g_mode[4] = {-1, -1, -1, -1};     // tc, fused, fused_fp16, smallh
+static const char* const g_mode_env[4] = {"FLOPPITY_TC", "FLOPPITY_FUSED", "FLOPPITY_FUSED_FP16", "FLOPPITY_SMALLH"};
+static bool mode_on(int i) {
+  if (g_mode[i] < 0) {
+    const char* e = getenv(g_mode_env[i]);
+    g_mode[i] = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_mode[i] == 1;
+}
+bool tc_enabled() { return mode_on(0); }
+bool fused_enabled() { return mode_on(1); }
+bool cond_fused_f16() { return mode_on(2); }
+bool smallh_enabled() { return mode_on(3); }
 
 #define FP_TRY(expr)            \
   do {                          \
@@ -88,22 +105,21 @@ static int pick_split(int64_t M, int N, int64_t K) {
 // dW[N_out, K_in] += dOut[R, N_out]^T @ Act[R, K_in]   (both operands row-major over the batch)
 // db[N_out] += colsum(dOut) rides along when `db` is given (fused into the tensor-core kernel, else its own launch)
 static int wgrad(const float* dOut, int64_t ldo, int n_out, const float* act, int64_t lda, int k_in, int64_t R,
-                 float* dW, int64_t ldw, int flags_extra, float drop_p, uint64_t seed, int drop_width, cudaStream_t s,
-                 float* db = nullptr) {
+                 float* dW, int64_t ldw, int flags_extra, cudaStream_t s, float* db = nullptr) {
   fp_gemm_args g{};
   g.A = dOut; g.lda = ldo; g.a_kmajor = 0;   // logical A'[n_out, R], element (n, r) at dOut[r*ldo + n]
   g.B = act; g.ldb = lda; g.b_kmajor = 0;    // logical B'[k_in, R], element (k, r) at act[r*lda + k]
   g.C = dW; g.ldc = ldw; g.M = n_out; g.N = k_in; g.K = R;
   g.flags = FP_G_ATOMIC | flags_extra | (db ? FP_G_COLSUM_A : 0);
   g.U = db;
-  if (drop_p == 0.f) {
+  {
     int r = launch_gemm_tc_tn(&g, s);
     if (r != FP_E_NOTREADY) return r;
   }
   if (db) FP_TRY(launch_colsum(dOut, ldo, R, n_out, db, s));
   g.flags &= ~FP_G_COLSUM_A; g.U = nullptr;
   g.split_k = pick_split(n_out, k_in, R);
-  return launch_gemm(&g, drop_p, seed, drop_width, s);
+  return launch_gemm(&g, s);
 }
 
 // dIn[R, K_in] (=|+=) dOut[R, N_out] @ W[N_out, K_in]
@@ -118,42 +134,40 @@ static fp_gemm_args dgrad_args(const float* dOut, int64_t ldo, int n_out, const 
 
 // forward GEMM against a weight matrix living at `woff` in the parameter buffer: tcgen05 3xTF32 when the shape
 // allows (pre-split weights in `prepared`), else the fp32 SIMT kernel
-static int gemm_weight(const Layout& L, const float* prepared, int64_t woff, fp_gemm_args* g, float drop_p, uint64_t seed,
-                       int drop_width, cudaStream_t s) {
-  if (drop_p == 0.f && prepared) {
+static int gemm_weight(const Layout& L, const float* prepared, int64_t woff, fp_gemm_args* g, cudaStream_t s) {
+  if (prepared) {
     int r = launch_gemm_tc(g, prepared + L.prepHi() + woff, prepared + L.prepLo() + woff, s);
     if (r != FP_E_NOTREADY) return r;
   }
-  return launch_gemm(g, drop_p, seed, drop_width, s);
+  return launch_gemm(g, s);
 }
 
 // dIn[R, k_in] (=|+=) dOut[R, n_out] @ W[n_out, k_in] with the epilogue flags in `flags`:
 // tcgen05 against the pre-transposed + split copy W^T [k_in, ld_t] at `toff`, else SIMT against W itself
 static int dgrad_weight(const Layout& L, const float* prepared, int64_t toff, int64_t ld_t, const float* dOut, int64_t ldo,
                         int n_out, const float* W, int64_t ldw, int k_in, int64_t R, float* dIn, int64_t ldi, int flags,
-                        const float* Msk, int64_t ldm, float drop_p, uint64_t seed, int drop_width, cudaStream_t s) {
-  if (drop_p == 0.f && prepared) {
+                        const float* Msk, int64_t ldm, float mask_scale, cudaStream_t s) {
+  if (prepared) {
     fp_gemm_args g{};
     g.A = dOut; g.lda = ldo; g.a_kmajor = 1;
     g.B = prepared + L.prepTHi() + toff; g.ldb = ld_t; g.b_kmajor = 1;
     g.C = dIn; g.ldc = ldi; g.M = R; g.N = k_in; g.K = n_out; g.flags = flags; g.split_k = 1;
-    g.Msk = Msk; g.ldm = ldm;
+    g.Msk = Msk; g.ldm = ldm; g.mask_scale = mask_scale;
     int r = launch_gemm_tc(&g, prepared + L.prepTHi() + toff, prepared + L.prepTLo() + toff, s);
     if (r != FP_E_NOTREADY) return r;
   }
   fp_gemm_args g = dgrad_args(dOut, ldo, n_out, W, ldw, k_in, R, dIn, ldi, flags);
-  g.Msk = Msk; g.ldm = ldm;
-  return launch_gemm(&g, drop_p, seed, drop_width, s);
+  g.Msk = Msk; g.ldm = ldm; g.mask_scale = mask_scale;
+  return launch_gemm(&g, s);
 }
 
-static inline uint64_t layer_seed(uint64_t seed, int layer, int block) {
+uint64_t layer_seed(uint64_t seed, int layer, int block) {
   return seed * 0x9E3779B97F4A7C15ull + (uint64_t)(layer * 64 + block + 1) * 0xD6E8FEB86659FD93ull;
 }
 
-// One decision per flow pass: does every layer's conditioner run as the fused kernel (cond_fused.cu)?  Dropout draws
-// masks inside the GEMM prologues, so a training pass with dropout keeps the GEMM chain.
+// One decision per flow pass: does every layer's conditioner run as the fused kernel (cond_fused.cu)?
 static bool use_fused(const fp_nsf_config* cfg, const Layout& L, const float* prepared, bool training) {
-  if (training && cfg->dropout_p > 0.f) return false;
+  (void)cfg; (void)training;
   return cond_fwd_supported(L, prepared);
 }
 
@@ -174,33 +188,36 @@ static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const 
   const float drop = training ? cfg->dropout_p : 0.f;
   if (fused) {   // hidden 128: the whole chain in one persistent tcgen05 kernel (activations stay in TMEM); the gate
                  // slots of ctx_all already hold sigmoid(gate), so there is no falling back to the GEMM chain from here
-    return launch_cond_fwd(cfg, L, params, prepared, i, theta_i, ctx_all, R, ctx_div, b.h, b.t, b.u, b.prm, training, status, s);
+    return launch_cond_fwd(cfg, L, params, prepared, i, theta_i, ctx_all, R, ctx_div, b.h, b.t, b.u, b.prm, training, drop, seed,
+                           status, s);
   }
   {  // initial layer: h0 = theta_i @ W0x^T + (ctx @ W0ctx^T + b0)   [the bracket is a column block of ctx_all]
     fp_gemm_args g = gemm_nt(theta_i, D, params + L.w0x(i), D, b.h[0], H, R, H, D, FP_G_ADD_CTX);
     g.G = ctx_all + L.ctxCol(i, 0); g.ldg = L.Nctx; g.ctx_div = ctx_div;
-    FP_TRY(gemm_weight(L, prepared, L.w0x(i), &g, 0.f, 0, 0, s));
+    FP_TRY(gemm_weight(L, prepared, L.w0x(i), &g, s));
   }
   for (int k = 0; k < L.Bk; ++k) {
-    {  // t = relu(h) @ W1^T + b1
-      fp_gemm_args g = gemm_nt(b.h[k], H, params + L.w1(i, k), H, b.t[k], H, R, H, H, FP_G_RELU_A | FP_G_BIAS);
+    {  // t' = dropout(relu(h) @ W1^T + b1): relu(t') = dropout(relu(t)), (t' > 0) = relu mask AND keep mask
+      fp_gemm_args g = gemm_nt(b.h[k], H, params + L.w1(i, k), H, b.t[k], H, R, H, H,
+                               FP_G_RELU_A | FP_G_BIAS | (drop > 0.f ? FP_G_DROP_OUT : 0));
       g.bias = params + L.b1(i, k);
-      FP_TRY(gemm_weight(L, prepared, L.w1(i, k), &g, 0.f, 0, 0, s));
+      g.drop_p = drop; g.drop_seed = layer_seed(seed, i, k);
+      FP_TRY(gemm_weight(L, prepared, L.w1(i, k), &g, s));
     }
-    {  // u = dropout(relu(t)) @ W2^T + b2 ; h_next = h + u * sigmoid(ctx gate)
-      int fl = FP_G_RELU_A | FP_G_BIAS | FP_G_GLU_RES | (drop > 0.f ? 512 : 0);
+    {  // u = relu(t') @ W2^T + b2 ; h_next = h + u * sigmoid(ctx gate)
+      int fl = FP_G_RELU_A | FP_G_BIAS | FP_G_GLU_RES;
       fp_gemm_args g = gemm_nt(b.t[k], H, params + L.w2(i, k), H, b.h[k + 1], H, R, H, H, fl);
       g.bias = params + L.b2(i, k);
       g.G = ctx_all + L.ctxCol(i, 1 + k); g.ldg = L.Nctx; g.ctx_div = ctx_div;
       g.Rsd = b.h[k]; g.ldr = H;
       g.U = b.u[k]; g.ldu = H;
-      FP_TRY(gemm_weight(L, prepared, L.w2(i, k), &g, drop, layer_seed(seed, i, k), H, s));
+      FP_TRY(gemm_weight(L, prepared, L.w2(i, k), &g, s));
     }
   }
   {  // params = h @ Wf^T + bf
     fp_gemm_args g = gemm_nt(b.h[L.Bk], H, params + L.wf(i), H, b.prm, L.ldP(i), R, L.dP(i), H, FP_G_BIAS);
     g.bias = params + L.bf(i);
-    FP_TRY(gemm_weight(L, prepared, L.wf(i), &g, 0.f, 0, 0, s));
+    FP_TRY(gemm_weight(L, prepared, L.wf(i), &g, s));
   }
   return 0;
 }
@@ -209,7 +226,7 @@ static int context_projection(const Layout& L, const float* params, const float*
                               float* ctx_all, cudaStream_t s) {
   fp_gemm_args g = gemm_nt(ctx, L.C, params + L.ctx_w, L.C, ctx_all, L.Nctx, Rc, (int)L.Nctx, L.C, FP_G_BIAS);
   g.bias = params + L.ctx_b;
-  return gemm_weight(L, prepared, L.ctx_w, &g, 0.f, 0, 0, s);
+  return gemm_weight(L, prepared, L.ctx_w, &g, s);
 }
 
 }  // namespace fp
@@ -217,6 +234,17 @@ static int context_projection(const Layout& L, const float* params, const float*
 using namespace fp;
 
 extern "C" {
+
+int fp_set_mode(int32_t tc, int32_t fused, int32_t fused_fp16, int32_t smallh) {
+  const int32_t v[4] = {tc, fused, fused_fp16, smallh};
+  int bits = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (v[i] >= 0) g_mode[i] = v[i] ? 1 : 0;
+    if (mode_on(i)) bits |= 1 << i;
+  }
+  return bits;
+}
+uint64_t fp_dropout_layer_seed(uint64_t seed, int32_t layer, int32_t block) { return layer_seed(seed, layer, block); }
 
 int64_t fp_nsf_param_count(const fp_nsf_config* cfg) {
   if (check_cfg(cfg)) return FP_E_BADARG;
@@ -359,7 +387,8 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
   float* ws = workspace;
   const int A = (int)(R / Rc);
   const int D = L.D, H = L.H;
-  const float drop = cfg->dropout_p;
+  (void)dropout_seed;      // the mask is folded into the saved activations by the forward pass; nothing is re-drawn here
+  const float drop_scale = cfg->dropout_p > 0.f ? 1.f / (1.f - cfg->dropout_p) : 1.f;
   const int sig_given = use_fused(cfg, L, prepared, true) ? 1 : 0;     // same decision as the forward pass that filled ws
 
   float* dth_a = ws + W.dth_a; float* dth_b = ws + W.dth_b;
@@ -379,31 +408,29 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
                                prepared + L.prepM(i), ws + W.thsp(i), grads + L.gradTailDM(i), grads + L.luBias(i)));
     { float* t = dth_a; dth_a = dth_b; dth_b = t; }
     // ---- final layer
-    FP_TRY(wgrad(dprm, ldP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, 0.f, 0, 0, s, grads + L.bf(i)));
-    FP_TRY(dgrad_weight(L, prepared, L.tWf(i), ldP, dprm, ldP, dP, params + L.wf(i), H, H, R, dh, H, 0, nullptr, 0, 0.f, 0, 0, s));
+    FP_TRY(wgrad(dprm, ldP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, s, grads + L.bf(i)));
+    FP_TRY(dgrad_weight(L, prepared, L.tWf(i), ldP, dprm, ldP, dP, params + L.wf(i), H, H, R, dh, H, 0, nullptr, 0, 1.f, s));
     // ---- residual blocks, last to first
     for (int k = L.Bk - 1; k >= 0; --k) {
-      const uint64_t seed = layer_seed(dropout_seed, i, k);
       FP_TRY(launch_glu_bwd(dh, ws + W.ubuf(i, k), ctx_all + L.ctxCol(i, 1 + k), L.Nctx, du,
                             dctx_all + L.ctxCol(i, 1 + k), Rc, A, H, sig_given, s));
-      FP_TRY(wgrad(du, H, H, ws + W.tbuf(i, k), H, H, R, grads + L.w2(i, k), H,
-                   FP_G_RELU_B | (drop > 0.f ? 1024 : 0), drop, seed, H, s, grads + L.b2(i, k)));
+      // the saved t is t' = dropout(t) (forward): relu(t') is the W2 operand, (t' > 0) * 1/(1-p) the mask of its gradient
+      FP_TRY(wgrad(du, H, H, ws + W.tbuf(i, k), H, H, R, grads + L.w2(i, k), H, FP_G_RELU_B, s, grads + L.b2(i, k)));
       FP_TRY(dgrad_weight(L, prepared, L.tW2(i, k), H, du, H, H, params + L.w2(i, k), H, H, R, dt, H,
-                          FP_G_RELUMASK | (drop > 0.f ? 2048 : 0), ws + W.tbuf(i, k), H, drop, seed, H, s));
-      FP_TRY(wgrad(dt, H, H, ws + W.hbuf(i, k), H, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, 0.f, 0, 0, s, grads + L.b1(i, k)));
+                          FP_G_RELUMASK, ws + W.tbuf(i, k), H, drop_scale, s));
+      FP_TRY(wgrad(dt, H, H, ws + W.hbuf(i, k), H, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, s, grads + L.b1(i, k)));
       FP_TRY(dgrad_weight(L, prepared, L.tW1(i, k), H, dt, H, H, params + L.w1(i, k), H, H, R, dh, H,
-                          FP_G_RELUMASK | FP_G_ACCUM, ws + W.hbuf(i, k), H, 0.f, 0, 0, s));
+                          FP_G_RELUMASK | FP_G_ACCUM, ws + W.hbuf(i, k), H, 1.f, s));
     }
     // ---- initial layer: h0 = theta_i @ W0x^T + ctx slot 0
     FP_TRY(launch_ctx_reduce(dh, dctx_all + L.ctxCol(i, 0), L.Nctx, Rc, A, H, s));
-    FP_TRY(wgrad(dh, H, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, 0.f, 0, 0, s));
-    FP_TRY(dgrad_weight(L, prepared, L.tW0(i), H, dh, H, H, params + L.w0x(i), D, D, R, dth_a, D, FP_G_ACCUM, nullptr, 0,
-                        0.f, 0, 0, s));
+    FP_TRY(wgrad(dh, H, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, s));
+    FP_TRY(dgrad_weight(L, prepared, L.tW0(i), H, dh, H, H, params + L.w0x(i), D, D, R, dth_a, D, FP_G_ACCUM, nullptr, 0, 1.f, s));
   }
   if (d_theta) FP_TRY(launch_affine_bwd(dth_a, zscale, d_theta, R, D, s));
 
   // ---- context projection weights: dWctx += dctx_all^T @ ctx ; db += colsum(dctx_all)
-  FP_TRY(wgrad(dctx_all, L.Nctx, (int)L.Nctx, ctx, L.C, L.C, Rc, grads + L.ctx_w, L.C, 0, 0.f, 0, 0, s, grads + L.ctx_b));
+  FP_TRY(wgrad(dctx_all, L.Nctx, (int)L.Nctx, ctx, L.C, L.C, Rc, grads + L.ctx_w, L.C, 0, s, grads + L.ctx_b));
   return 0;
 }
 
@@ -418,7 +445,7 @@ int fp_nsf_ctx_backward(const fp_nsf_config* cfg, const float* params, int64_t R
   Layout L(cfg);
   Workspace W(L, R, Rc, true);
   fp_gemm_args g = dgrad_args(workspace + W.dctx_all, L.Nctx, (int)L.Nctx, params + L.ctx_w, L.C, L.C, Rc, d_ctx, L.C, 0);
-  return launch_gemm(&g, 0.f, 0, 0, (cudaStream_t)stream);
+  return launch_gemm(&g, (cudaStream_t)stream);
 }
 
 int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* prepared, const float* z, const float* ctx,

@@ -3,7 +3,7 @@
 // The conditioner of every coupling layer (nflows ResidualNet/ResidualBlock, built by sbi build_nsf,
 // reached from /root/reference/modules.py:63) is a chain of small dense layers.  Upstream runs each as
 // addmm + separate relu / dropout / cat / glu / add kernels; here each dense layer is ONE launch whose
-// prologue applies relu (+dropout) to the activation operand and whose epilogue applies bias, the
+// prologue applies relu to the activation operand and whose epilogue applies bias (+ dropout on the result), the
 // context term, the GLU gate + residual, or the relu mask of the backward pass.  The same kernel serves
 // forward (NT), dgrad (NN) and wgrad (TN, split-K with atomics) through the two "k-major" switches.
 // This is the exact-fp32 path; the tcgen05 path (gemm_tc.cu) takes over the large context projection.
@@ -19,7 +19,7 @@ constexpr int GEMM_THREADS = (BM / TM) * (BN / TN);  // 256
 constexpr int APAD = 4, BPAD = 4;
 
 template <bool A_KMAJ, bool B_KMAJ>
-__global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k_chunk, GemmDrop drop) {
+__global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k_chunk) {
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN + BPAD];
 
@@ -36,8 +36,6 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k
   const bool relu_a = g.flags & FP_G_RELU_A, relu_b = g.flags & FP_G_RELU_B;
   const bool a_vec = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
   const bool b_vec = ((g.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
-  const bool drop_a = drop.p > 0.f && (g.flags & 512);
-  const bool drop_b = drop.p > 0.f && (g.flags & 1024);
 
   float ra[2][4];
   float rb[4];
@@ -58,10 +56,6 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k
 #pragma unroll
           for (int j = 0; j < 4; ++j) ra[i][j] = (m < g.M && k + j < kend) ? src[j] : 0.f;
         }
-        if (drop_a) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ra[i][j] *= drop_scale(drop.seed, m, (int)(k + j), drop.width, drop.p);
-        }
       } else {
         int krow = idx >> 5, mq = (idx & 31) * 4;
         int64_t k = k0 + krow, m = m0 + mq;
@@ -72,10 +66,6 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) ra[i][j] = (k < kend && m + j < g.M) ? src[j] : 0.f;
-        }
-        if (drop_a) {  // M-major A: the contraction index k is the activation ROW, m its column
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ra[i][j] *= drop_scale(drop.seed, k, (int)(m + j), drop.width, drop.p);
         }
       }
       if (relu_a) {
@@ -109,10 +99,6 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) rb[j] = (k < kend && n + j < g.N) ? src[j] : 0.f;
-      }
-      if (drop_b) {  // M-major B: k is the activation row, n its column
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rb[j] *= drop_scale(drop.seed, k, n + j, drop.width, drop.p);
       }
     }
     if (relu_b) {
@@ -180,12 +166,12 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_gemm(fp_gemm_args g, int64_t k
     for (int j = 0; j < TN; ++j) {
       int n = n0 + tx * TN + j;
       if (n >= g.N) continue;
-      gemm_epilogue_store(g, g.flags, drop, m, n, acc[i][j]);
+      gemm_epilogue_store(g, g.flags, m, n, acc[i][j]);
     }
   }
 }
 
-int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int drop_width, cudaStream_t stream) {
+int launch_gemm(const fp_gemm_args* a, cudaStream_t stream) {
   if (a->M <= 0 || a->N <= 0) return 0;
   if (a->K <= 0) return FP_E_BADARG;
   if (a->M > 2147483647LL && (a->flags & (FP_G_ADD_CTX | FP_G_GLU_RES))) return FP_E_TOOLARGE;
@@ -198,12 +184,11 @@ int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int dro
   int nt = (a->N + BN - 1) / BN;
   if (nt > 65535 || split > 65535 || mt > 2147483647LL) return FP_E_TOOLARGE;
   dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)split);
-  GemmDrop d{drop_p, drop_seed, drop_width};
   ProfScope ps(TAG_GEMM_SIMT, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
-  if (a->a_kmajor && a->b_kmajor) k_gemm<true, true><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);
-  else if (a->a_kmajor && !a->b_kmajor) k_gemm<true, false><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);
-  else if (!a->a_kmajor && a->b_kmajor) k_gemm<false, true><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);
-  else k_gemm<false, false><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc, d);
+  if (a->a_kmajor && a->b_kmajor) k_gemm<true, true><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc);
+  else if (a->a_kmajor && !a->b_kmajor) k_gemm<true, false><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc);
+  else if (!a->a_kmajor && a->b_kmajor) k_gemm<false, true><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc);
+  else k_gemm<false, false><<<grid, GEMM_THREADS, 0, stream>>>(*a, kc);
   FP_LAUNCH_CHECK();
   return 0;
 }
@@ -212,5 +197,5 @@ int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int dro
 
 extern "C" int fp_gemm(const fp_gemm_args* args, void* stream) {
   if (!args) return FP_E_BADARG;
-  return fp::launch_gemm(args, 0.f, 0, 0, (cudaStream_t)stream);
+  return fp::launch_gemm(args, (cudaStream_t)stream);
 }

@@ -31,7 +31,7 @@
 
 namespace fp {
 
-int launch_gemm(const fp_gemm_args* a, float drop_p, uint64_t drop_seed, int drop_width, cudaStream_t stream);
+int launch_gemm(const fp_gemm_args* a, cudaStream_t stream);
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB: 128 rows x 128 B
@@ -719,21 +719,12 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, cudaStream_t s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-bool tc_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("FLOPPITY_TC");
-    on = (e && e[0] == '0') ? 0 : 1;
-  }
-  return on == 1;
-}
-
 // Can this GEMM go to the tcgen05 NT kernel?  (both operands K-major, TMA-compatible strides, no dropout/split-K)
 static bool tc_supported(const fp_gemm_args* a) {
   if (!a->a_kmajor || !a->b_kmajor) return false;
   if ((a->lda & 3) || (a->ldb & 3)) return false;
   if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return false;
-  if (a->flags & (FP_G_RELU_B | FP_G_DROP_A | FP_G_DROP_B | FP_G_DROPMASK | FP_G_ATOMIC)) return false;
+  if (a->flags & (FP_G_RELU_B | FP_G_ATOMIC)) return false;
   if (a->split_k > 1) return false;
   if (a->M < 1 || a->N < 1 || a->K < 1 || a->M > 2147483647LL) return false;
   return true;
@@ -749,7 +740,7 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   if (!get_tensor_map(B_lo, a->N, a->K, a->ldb, &mBl)) return FP_E_NOTREADY;
   const int nkb = (int)((a->K + TC_BK - 1) / TC_BK);
   // long contractions are chunked (see the kernel comment); only the plain / bias epilogue can be accumulated
-  const bool plain = (a->flags & ~(FP_G_RELU_A | FP_G_BIAS)) == 0;
+  const bool plain = (a->flags & ~(FP_G_RELU_A | FP_G_BIAS | FP_G_TF32X3)) == 0;
   const int nchunks = (plain && nkb > TC_KCHUNK_BLOCKS) ? (nkb + TC_KCHUNK_BLOCKS - 1) / TC_KCHUNK_BLOCKS : 1;
   const int64_t tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + TC_BN - 1) / TC_BN);
   const int grid = (int)std::min<int64_t>(tiles, num_sms());
@@ -775,7 +766,7 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   int epi = a->flags & FP_EPI_MASK;
   switch (epi) {
     case 0: case FP_G_BIAS: case FP_G_ADD_CTX: case FP_G_BIAS | FP_G_GLU_RES: case FP_G_RELUMASK:
-    case FP_G_RELUMASK | FP_G_ACCUM: case FP_G_ACCUM: break;
+    case FP_G_RELUMASK | FP_G_ACCUM: case FP_G_ACCUM: case FP_G_BIAS | FP_G_DROP_OUT: break;
     default: epi = -1;
   }
   switch (epi) {
@@ -786,6 +777,7 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
     FP_TC_NT_CASE(FP_G_RELUMASK)
     FP_TC_NT_CASE(FP_G_RELUMASK | FP_G_ACCUM)
     FP_TC_NT_CASE(FP_G_ACCUM)
+    FP_TC_NT_CASE(FP_G_BIAS | FP_G_DROP_OUT)
     FP_TC_NT_CASE(-1)
   }
 #undef FP_TC_NT_CASE
@@ -852,7 +844,7 @@ int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params
 }
 
 // router used by the engine for the context projection (weights split by fp_nsf_prepare)
-int launch_gemm_ctx(const fp_gemm_args* a, cudaStream_t stream) { return launch_gemm(a, 0.f, 0, 0, stream); }
+int launch_gemm_ctx(const fp_gemm_args* a, cudaStream_t stream) { return launch_gemm(a, stream); }
 
 }  // namespace fp
 

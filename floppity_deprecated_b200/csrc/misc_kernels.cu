@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "layout.h"
 #include "prof.h"
+#include "gemm_epilogue.cuh"
 #include <math.h>
 #include <algorithm>
 
@@ -530,11 +531,27 @@ int launch_sum(const float* x, int64_t n, float scale, float* out, cudaStream_t 
   FP_LAUNCH_CHECK(); return 0;
 }
 
+// keep flags of the dropout mask, for the parity tests (the oracle is handed the very mask the kernels drew)
+__global__ void k_dropout_mask(uint8_t* __restrict__ keep, int64_t R, int width, DropKey dk) {
+  const int64_t n = R * (int64_t)width;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    keep[e] = drop_keep(dk, e / width, (int)(e % width), width) ? 1 : 0;
+}
+
 }  // namespace fp
 
 using namespace fp;
 
 extern "C" {
+
+int fp_dropout_mask(uint8_t* keep, int64_t R, int32_t width, float p, uint64_t seed, void* stream) {
+  if (R <= 0) return 0;
+  if (width < 1 || p < 0.f || p >= 1.f || !keep) return FP_E_BADARG;
+  ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
+  k_dropout_mask<<<(int)std::min<int64_t>((R * width + 255) / 256, 4 * num_sms()), 256, 0, (cudaStream_t)stream>>>(
+      keep, R, width, make_drop_key(seed, p));
+  FP_LAUNCH_CHECK(); return 0;
+}
 
 int fp_atom_choices(int32_t* choices, int64_t B, int32_t A, uint64_t seed, void* stream) {
   if (A < 2 || A > B || A > 4096) return FP_E_BADARG;

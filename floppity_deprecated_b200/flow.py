@@ -304,6 +304,9 @@ class NSFFlow(nn.Module):
         if ws is None:
             ws = torch.empty(self.workspace_floats(R, Rc, training), dtype=torch.float32, device=dev)
         logp = torch.empty(R, dtype=torch.float32, device=dev)
+        if status is None:
+            status = self._status()
+        self._last_status = status       # read lazily by whoever hands the result to the user (check_last_status)
         seed = 0
         if training and self.cfg["dropout_p"] > 0 and self.training:
             self._step_seed += 1
@@ -329,6 +332,19 @@ class NSFFlow(nn.Module):
     def _finish_grads(self, grads, prepared):
         _lib.check(_lib.lib().fp_nsf_finish_grads(_cfg_struct(self.cfg), _lib.ptr(self._flat), _lib.ptr(prepared),
                                                   _lib.ptr(grads), _lib.stream()), "fp_nsf_finish_grads")
+
+    def check_last_status(self) -> None:
+        """Raise if the last forward / inverse pass reported saturated 3xFP16 operands (status word 2): one small
+        device-to-host read, so callers do it where a result is about to leave the device anyway."""
+        st = getattr(self, "_last_status", None)
+        if st is None:
+            return
+        st = st.tolist()
+        if len(st) > 2 and st[2]:
+            raise FloatingPointError(
+                f"{st[2]} operand pieces of the fused conditioner reached the edge of fp16's range (|value| > 6e4): the "
+                "3xFP16 operand format does not cover this flow's activations -- set FLOPPITY_FUSED_FP16=0 (3xTF32 "
+                "operands) and check that the observations are z-scored")
 
     def _rows_per_chunk(self, Rc_is_one: bool) -> int:
         per_row = self.workspace_floats(1024, 1 if Rc_is_one else 1024, False) / 1024.0

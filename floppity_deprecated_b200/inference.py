@@ -262,7 +262,12 @@ class _TrainEngine:
         self._forward(training=False)
 
     def check_status(self):
-        st = self.status.tolist()
+        if self.world > 1:       # every rank must take the same decision, or the others hang in the next all-reduce
+            stf = self.status.float()
+            fdist.allreduce_sum_(stf)
+            st = [int(v) for v in stf.tolist()]
+        else:
+            st = self.status.tolist()
         _check_fp16_range(st)
         if st[0] or st[1]:
             raise AssertionError(f"non-finite log-probs or atoms outside the prior: {st[0]}, negative spline discriminants: {st[1]}")
@@ -331,12 +336,15 @@ class SNPE_C:
         if epoch == 0 or self._val_log_prob > self._best_val_log_prob:
             self._best_val_log_prob = self._val_log_prob
             self._epochs_since_last_improvement = 0
-            self._best_flat = net._flat.detach().clone()   # == deepcopy(state_dict) upstream; buffers never change in train()
+            # == deepcopy(state_dict) upstream (buffers never change in train()): EVERY trainable buffer, i.e. the flow's
+            # flat parameters and, with an embedding net in front (-embedding FC, modules.py:21-45), the embedding's too
+            self._best_state = [p.detach().clone() for p in net.parameters()]
         else:
             self._epochs_since_last_improvement += 1
         if self._epochs_since_last_improvement > stop_after_epochs - 1:
             with torch.no_grad():
-                net._flat.copy_(self._best_flat)
+                for p, best in zip(net.parameters(), self._best_state):
+                    p.copy_(best)
             converged = True
         return converged
 
@@ -563,6 +571,7 @@ class DirectPosterior:
         x = self._x_or_default(x)
         with torch.set_grad_enabled(track_gradients):
             lp = net.log_prob(theta, x.to(dev))
+            getattr(net, "flow", net).check_last_status()      # saturated 3xFP16 operands never pass silently
             inside = torch.empty(theta.shape[0], dtype=torch.uint8, device=dev)
             low, high = self._box(dev)
             _lib.check(_lib.lib().fp_within_box(_lib.ptr(theta.detach()), _lib.ptr(low), _lib.ptr(high), _lib.ptr(inside),

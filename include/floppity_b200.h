@@ -107,10 +107,12 @@ enum fp_gemm_flags {
   FP_G_ACCUM       = 64,  /* C += (after the above) */
   FP_G_ATOMIC      = 128, /* split-K: atomicAdd into C */
   FP_G_TF32X3      = 256, /* use the tcgen05 3xTF32 path when shapes allow (fp32-accurate) */
-  FP_G_DROP_A      = 512, /* inverted dropout on A on load (engine-internal; needs the engine's seed) */
-  FP_G_DROP_B      = 1024,
-  FP_G_DROPMASK    = 2048,/* dropout mask applied with FP_G_RELUMASK in the backward */
-  FP_G_COLSUM_A    = 4096 /* weight-gradient form only: U[m] += sum_k A[k,m] (the bias gradient rides along) */
+  FP_G_COLSUM_A    = 4096, /* weight-gradient form only: U[m] += sum_k A[k,m] (the bias gradient rides along) */
+  FP_G_DROP_OUT    = 8192  /* inverted dropout on the RESULT (after bias): C = keep(m,n) ? v/(1-drop_p) : 0 with the
+                              counter-based mask of fp_dropout_mask(drop_seed, width N).  nflows ResidualBlock applies
+                              dropout to relu(t); storing t' = dropout(t) instead gives relu(t') = dropout(relu(t)) to the
+                              next GEMM's relu prologue and (t' > 0) = relu mask AND keep mask to the backward pass, so no
+                              kernel ever has to re-draw the mask (floppity.py:57 -dropout, modules.py:63). */
 };
 typedef struct fp_gemm_args {
   const float* A; int64_t lda; int32_t a_kmajor;
@@ -124,6 +126,9 @@ typedef struct fp_gemm_args {
   float* U; int64_t ldu;
   const float* Msk; int64_t ldm;
   int32_t split_k;
+  float mask_scale;      /* FP_G_RELUMASK: C = Msk > 0 ? v * mask_scale : 0 ; 0 is read as 1 */
+  float drop_p;          /* FP_G_DROP_OUT */
+  uint64_t drop_seed;    /* FP_G_DROP_OUT */
 } fp_gemm_args;
 int fp_gemm(const fp_gemm_args* args, void* stream);
 /* Same contract on the tcgen05 tensor cores with the fp32-accurate 3xTF32 split (A split in-kernel, B_hi/B_lo
@@ -135,6 +140,18 @@ int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream)
  * [| FP_G_COLSUM_A with the bias-gradient vector [M] in `U`]); contraction split across CTAs, partial tiles added
  * with vector atomics.  FP_E_NOTREADY -> use fp_gemm (which ignores FP_G_COLSUM_A: the caller sums columns itself). */
 int fp_gemm_tc_tn(const fp_gemm_args* args, void* stream);
+/* keep[r, c] (uint8, row-major [R, width]) = 1 where the dropout mask keeps element (r, c): the same counter-based draw
+ * FP_G_DROP_OUT and the fused conditioner use (one 32-bit hash of (seed, element pair) gives two 16-bit uniforms; an
+ * element is dropped when its uniform is below round(p * 65536)).  fp_nsf_logprob_forward(training=1, dropout_seed=s)
+ * draws block `block` of coupling layer `layer` with seed fp_dropout_layer_seed(s, layer, block). */
+int fp_dropout_mask(uint8_t* keep, int64_t R, int32_t width, float p, uint64_t seed, void* stream);
+uint64_t fp_dropout_layer_seed(uint64_t seed, int32_t layer, int32_t block);
+/* Run-time switches of the conditioner paths (the FLOPPITY_TC / FLOPPITY_FUSED / FLOPPITY_FUSED_FP16 / FLOPPITY_SMALLH
+ * environment variables give the initial values): tc = tcgen05 GEMMs (else exact fp32 SIMT), fused = one persistent
+ * kernel per coupling layer for hidden 128, fused_fp16 = 3xFP16 operands in it (else 3xTF32), smallh = shared-memory-
+ * resident fused MLP for hidden <= 64.  A negative argument leaves that switch as it is.  Returns the switches as bits
+ * (1 tc, 2 fused, 4 fused_fp16, 8 smallh). */
+int fp_set_mode(int32_t tc, int32_t fused, int32_t fused_fp16, int32_t smallh);
 /* debug: SM-clock stamps of CTA 0 of the next fp_gemm_tc launches into a device int64[512] buffer (NULL = off) */
 int fp_tc_set_trace(void* buf);
 /* debug: ablation switches for timing experiments on the weight-gradient kernel (1 skip split, 2 skip reductions,

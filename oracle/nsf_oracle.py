@@ -817,3 +817,25 @@ def randomize_lu(flow: Flow, generator: torch.Generator, scale: float = 0.2):
             if isinstance(t, LULinear):
                 for p in (t.lower_entries, t.upper_entries, t.unconstrained_upper_diag, t.bias):
                     p.add_(scale * torch.randn(p.shape, generator=generator, dtype=p.dtype))
+
+
+class InjectedDropout(nn.Module):
+    """``nn.Dropout`` with the keep mask handed in (inverted dropout: kept activations are scaled by 1/(1-p)), so a
+    parity test can give the oracle the very mask the CUDA kernels drew (their RNG is not torch's).  Identity in
+    ``eval()`` mode, like ``nn.Dropout``."""
+
+    def __init__(self, keep: Tensor, p: float):
+        super().__init__()
+        self.keep, self.p = keep, float(p)
+
+    def forward(self, x):
+        if not self.training:
+            return x
+        return x * self.keep.to(x.dtype) / (1.0 - self.p)
+
+
+def inject_dropout_masks(flow: Flow, keep_masks, p: float):
+    """``keep_masks[layer][block]`` ([rows, hidden] 0/1) replaces the dropout module of every residual block."""
+    for i, c in enumerate(coupling_layers(flow)):
+        for k, blk in enumerate(c.transform_net.blocks):
+            blk.dropout = InjectedDropout(keep_masks[i][k], p)

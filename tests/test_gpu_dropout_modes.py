@@ -1,0 +1,263 @@
+"""GPU parity, part 3: the configurations the reference runs out of the box.
+
+* ``-dropout 0.1`` (the default at /root/reference/floppity.py:57, forwarded at modules.py:63): the kernels' own
+  counter-based mask is exported through the C ABI and handed to the oracle, so forward values and every gradient
+  are compared on IDENTICAL masks; eval() must equal the dropout-free oracle; the mask itself is checked for its
+  keep rate and independence.
+* every run-time variant of the conditioner (3xFP16 / 3xTF32 fused kernel, tcgen05 GEMM chain, exact-fp32 SIMT chain,
+  shared-memory-resident small-hidden kernel) goes through the same parity assertions inside this suite
+  (``fp_set_mode``), not only the default one.
+* the real context widths of BASELINE.json configs[2] / configs[3]: contractions over 2000 / 3000 spectral bins (the
+  K-chunked tensor-core path).
+Tolerance: 1e-4 relative (|a-b| / max(1,|b|)) on log_prob and samples, 2e-3 of the tensor maximum on gradients."""
+import numpy as np
+import pytest
+import torch
+
+import floppity_deprecated_b200 as fb
+from conftest import golden_oracle_net, rel_err
+from floppity_deprecated_b200 import _lib
+from oracle import nsf_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+# (tc, fused, fused_fp16, smallh)
+MODES = {
+    "default": (1, 1, 1, 1),
+    "fused_3xtf32": (1, 1, 0, 1),
+    "gemm_chain_tc": (1, 0, 0, 0),
+    "simt_fp32": (0, 0, 0, 0),
+}
+
+
+@pytest.fixture(params=list(MODES))
+def mode(request):
+    before = _lib.lib().fp_set_mode(-1, -1, -1, -1)
+    _lib.lib().fp_set_mode(*MODES[request.param])
+    yield request.param
+    _lib.lib().fp_set_mode(before & 1, (before >> 1) & 1, (before >> 2) & 1, (before >> 3) & 1)
+
+
+def _pair(D, C, H, T, K, Bk, p, seed, n=1024):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    theta = torch.rand(n, D, generator=g) * 6 - 3
+    x = torch.randn(n, C, generator=g)
+    hp = dict(hidden_features=H, num_transforms=T, num_bins=K, num_blocks=Bk, dropout_probability=p)
+    onet = O.build_nsf(theta, x, **hp)
+    O.randomize_lu(onet, g, 0.05)
+    with torch.no_grad():       # block second layers start at +-1e-3 upstream: make dropout matter
+        for c in O.coupling_layers(onet):
+            for blk in c.transform_net.blocks:
+                blk.linear_layers[1].weight.add_(0.05 * torch.randn(blk.linear_layers[1].weight.shape, generator=g))
+    net = fb.NSFFlow(D, C, **hp)
+    net.load_state_dict(onet.state_dict())
+    return onet, net.cuda(), theta, x
+
+
+def _masks(net, seed, R):
+    """keep masks [layer][block] of the training pass that used ``seed`` -- drawn by the library, not by torch."""
+    L = _lib.lib()
+    H, p = net.cfg["H"], net.cfg["dropout_p"]
+    out = []
+    for i in range(net.T):
+        row = []
+        for k in range(net.cfg["Bk"]):
+            keep = torch.empty(R, H, dtype=torch.uint8, device="cuda")
+            _lib.check(L.fp_dropout_mask(_lib.ptr(keep), R, H, p, L.fp_dropout_layer_seed(seed, i, k), _lib.stream()), "mask")
+            row.append(keep.cpu().float())
+        out.append(row)
+    return out
+
+
+def test_dropout_mask_statistics():
+    L = _lib.lib()
+    R, W = 4096, 128
+    for p in (0.1, 0.5):
+        keep = torch.empty(R, W, dtype=torch.uint8, device="cuda")
+        _lib.check(L.fp_dropout_mask(_lib.ptr(keep), R, W, p, 12345, _lib.stream()), "mask")
+        k = keep.cpu().float()
+        n = R * W
+        assert abs(k.mean().item() - (1 - p)) < 5 * np.sqrt(p * (1 - p) / n) + 1e-5         # keep rate (16-bit threshold)
+        # rows / columns / neighbouring elements are uncorrelated (the two halves of one hash word included)
+        c = k - k.mean()
+        for a, b in ((c[:, 0::2], c[:, 1::2]), (c[:-1], c[1:]), (c[:, :-1], c[:, 1:])):
+            corr = (a * b).mean().item() / (p * (1 - p))
+            assert abs(corr) < 5 / np.sqrt(a.numel()), corr
+        col_rate, row_rate = k.mean(0), k.mean(1)
+        assert (col_rate - (1 - p)).abs().max() < 6 * np.sqrt(p * (1 - p) / R)
+        assert (row_rate - (1 - p)).abs().max() < 6 * np.sqrt(p * (1 - p) / W)
+        other = torch.empty_like(keep)
+        _lib.check(L.fp_dropout_mask(_lib.ptr(other), R, W, p, 12346, _lib.stream()), "mask")
+        agree = (other == keep).float().mean().item()
+        assert abs(agree - (p * p + (1 - p) * (1 - p))) < 0.01                               # a new seed is a new mask
+    none = torch.empty(64, 50, dtype=torch.uint8, device="cuda")
+    _lib.check(L.fp_dropout_mask(_lib.ptr(none), 64, 50, 0.0, 1, _lib.stream()), "mask")
+    assert bool(none.all())
+
+
+@pytest.mark.parametrize("N,K", [(50, 50), (128, 128), (512, 96)])
+def test_gemm_dropout_epilogue_and_scaled_relu_mask(N, K):
+    """FP_G_DROP_OUT (t' = dropout(acc + bias)) and the scaled relu mask of its backward, SIMT and tcgen05."""
+    L = _lib.lib()
+    M, p, seed = 777, 0.1, 99
+    g = torch.Generator().manual_seed(N)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(N, K, generator=g).cuda() / np.sqrt(K)
+    bias = torch.randn(N, generator=g).cuda()
+    keep = torch.empty(M, N, dtype=torch.uint8, device="cuda")
+    _lib.check(L.fp_dropout_mask(_lib.ptr(keep), M, N, p, seed, _lib.stream()), "mask")
+    want = (torch.relu(A.double()) @ B.double().T + bias.double()) * keep.double() / (1 - p)
+    hi, lo = torch.empty_like(B), torch.empty_like(B)
+    _lib.check(L.fp_split_tf32(_lib.ptr(B), _lib.ptr(hi), _lib.ptr(lo), B.numel(), _lib.stream()), "split")
+    for tc in (False, True):
+        C = torch.full((M, N), 7.0, device="cuda")
+        a = _lib.GemmArgs()
+        a.A, a.lda, a.a_kmajor, a.B, a.ldb, a.b_kmajor = _lib.ptr(A), K, 1, _lib.ptr(B), K, 1
+        a.C, a.ldc, a.M, a.N, a.K = _lib.ptr(C), N, M, N, K
+        a.flags = _lib.G_RELU_A | _lib.G_BIAS | _lib.G_DROP_OUT
+        a.bias, a.split_k, a.drop_p, a.drop_seed = _lib.ptr(bias), 1, p, seed
+        r = L.fp_gemm_tc(a, _lib.ptr(hi), _lib.ptr(lo), _lib.stream()) if tc else L.fp_gemm(a, _lib.stream())
+        if tc and r == -3:
+            assert K % 4 != 0 or N == 50        # only shapes TMA cannot address may decline
+            continue
+        _lib.check(r, "gemm")
+        assert rel_err(C.cpu().numpy(), want.cpu().numpy()).max() < TOL
+        assert ((C == 0) | (keep > 0)).all()
+        # backward form: dIn = (dOut @ W) * (t' > 0) * 1/(1-p)
+        dOut = torch.randn(M, K, generator=g).cuda()
+        Wt = torch.randn(N, K, generator=g).cuda() / np.sqrt(K)      # logical B[n, k] for C[M, N] = dOut[M, K] @ Wt[N, K]^T
+        h2, l2 = torch.empty_like(Wt), torch.empty_like(Wt)
+        _lib.check(L.fp_split_tf32(_lib.ptr(Wt), _lib.ptr(h2), _lib.ptr(l2), Wt.numel(), _lib.stream()), "split")
+        dIn = torch.empty(M, N, device="cuda")
+        b = _lib.GemmArgs()
+        b.A, b.lda, b.a_kmajor, b.B, b.ldb, b.b_kmajor = _lib.ptr(dOut), K, 1, _lib.ptr(Wt), K, 1
+        b.C, b.ldc, b.M, b.N, b.K = _lib.ptr(dIn), N, M, N, K
+        b.flags, b.Msk, b.ldm, b.mask_scale, b.split_k = _lib.G_RELUMASK, _lib.ptr(C), N, 1 / (1 - p), 1
+        r = L.fp_gemm_tc(b, _lib.ptr(h2), _lib.ptr(l2), _lib.stream()) if tc else L.fp_gemm(b, _lib.stream())
+        _lib.check(r, "gemm mask")
+        want_d = (dOut.double() @ Wt.double().T) * (C > 0).double() / (1 - p)
+        assert rel_err(dIn.cpu().numpy(), want_d.cpu().numpy()).max() < TOL
+
+
+SHAPES = {
+    # name: (D, C, H, T, K, Bk)
+    "hidden128": (20, 48, 128, 3, 10, 2),     # fused tcgen05 conditioner (c2 / c4 hidden width)
+    "hidden50": (10, 40, 50, 3, 8, 3),        # the reference's default network (floppity.py:34,35,50): small-hidden kernel
+    "hidden512": (30, 64, 512, 2, 16, 4),     # c3 width: tcgen05 GEMM chain
+}
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
+def test_dropout_training_matches_oracle_on_the_same_mask(shape, mode):
+    D, C, H, T, K, Bk = SHAPES[shape]
+    p, R = 0.1, 300
+    onet, net, theta, x = _pair(D, C, H, T, K, Bk, p, seed=5 + list(SHAPES).index(shape))
+    # eval(): dropout is the identity, the result is the dropout-free oracle
+    net.eval(); onet.eval()
+    with torch.no_grad():
+        got = net.log_prob(theta[:R].cuda(), x[:R].cuda()).cpu().numpy()
+        want = onet.log_prob(theta[:R], x[:R]).numpy()
+    assert rel_err(got, want).max() < TOL, rel_err(got, want).max()
+    # train(): forward + hand-written backward under the library's own mask
+    net.train(); onet.train()
+    th = theta[:R].cuda().requires_grad_(True)
+    lp = net.log_prob(th, x[:R].cuda())
+    seed = net._step_seed
+    assert seed > 0
+    (-lp.mean()).backward()
+    masks = _masks(net, seed, R)
+    kept = np.mean([m.mean().item() for row in masks for m in row])
+    assert abs(kept - (1 - p)) < 0.01
+    O.inject_dropout_masks(onet, masks, p)
+    tho = theta[:R].clone().requires_grad_(True)
+    lpo = onet.log_prob(tho, x[:R])
+    (-lpo.mean()).backward()
+    assert rel_err(lp.detach().cpu().numpy(), lpo.detach().numpy()).max() < TOL
+    # the masked pass really differs from the unmasked one (the test would otherwise prove nothing)
+    assert np.abs(lpo.detach().numpy() - want).max() > 1e-3
+    assert np.abs(th.grad.cpu().numpy() - tho.grad.numpy()).max() < 2e-3 * np.abs(tho.grad.numpy()).max()
+    got_g = net.unpack(net._flat.grad)
+    for k, prm in onet.named_parameters():
+        ref = prm.grad.numpy()
+        err = np.abs(got_g[k].cpu().numpy() - ref).max()
+        assert err < 2e-3 * max(np.abs(ref).max(), 1e-4), (k, err, np.abs(ref).max())
+    # a second training pass draws a different mask
+    lp2 = net.log_prob(theta[:R].cuda().requires_grad_(True), x[:R].cuda())
+    assert net._step_seed == seed + 1 and (lp2.detach() - lp.detach()).abs().max() > 1e-4
+
+
+def test_dropout_training_step_through_the_trainer():
+    """SNPE_C.train with the reference's defaults (hidden 50, 5 transforms, 3 blocks, dropout 0.1): the loss falls and the
+    returned estimator is in a consistent eval state (the engine path: atomic rows share context rows)."""
+    from floppity_deprecated_b200 import synthetic
+    theta, x, _, _ = synthetic.make_dataset("c1", 2048)
+    prior = fb.BoxUniform(-3 * torch.ones(10), 3 * torch.ones(10), device="cuda")
+    inf = fb.SNPE_C(prior, fb.posterior_nn("nsf", hidden_features=50, num_transforms=5, num_bins=8, num_blocks=3,
+                                            dropout_probability=0.1), device="cuda")
+    inf.append_simulations(torch.tensor(theta), torch.tensor(x))
+    net = inf.train(training_batch_size=256, stop_after_epochs=3, max_num_epochs=12, force_first_round_loss=True)
+    tl = inf._summary["training_log_probs"]
+    assert tl[-1] > tl[0] + 0.5, tl
+    net.eval()
+    a = net.log_prob(torch.tensor(theta[:64]).cuda(), torch.tensor(x[:64]).cuda())
+    b = net.log_prob(torch.tensor(theta[:64]).cuda(), torch.tensor(x[:64]).cuda())
+    assert torch.equal(a, b)                       # eval: no mask
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c4"])
+def test_every_conditioner_variant_matches_golden(name, mode):
+    """log_prob, fixed-noise samples and all gradients of the committed golden cases under every run-time variant."""
+    onet, g, cfg = golden_oracle_net(name)
+    D, C, T, K, H, Bk = cfg[:6]
+    net = fb.NSFFlow(D, C, hidden_features=H, num_transforms=T, num_bins=K, num_blocks=Bk)
+    net.load_state_dict(onet.state_dict())
+    net = net.cuda().eval()
+    theta, x, z = torch.tensor(g["theta"]), torch.tensor(g["x"]), torch.tensor(g["z"])
+    with torch.no_grad():
+        lp = net.log_prob(theta.cuda(), x.cuda()).cpu().numpy()
+    assert rel_err(lp, g["logp"]).max() < TOL, (mode, rel_err(lp, g["logp"]).max())
+    s1 = net.sample(z.shape[0], context=x[:1].cuda(), noise=z.cuda())[0].cpu().numpy()
+    assert rel_err(s1, g["samples_one_x"]).max() < TOL, (mode, rel_err(s1, g["samples_one_x"]).max())
+    net.train()
+    th = theta.cuda().requires_grad_()
+    (-net.log_prob(th, x.cuda()).mean()).backward()
+    grads = {k: v.cpu().numpy() for k, v in net.unpack(net._flat.grad).items()}
+    keys = [str(k) for k in g["grad_keys"]]
+    norms = np.array([np.linalg.norm(grads[k]) for k in keys])
+    bad = [(k, a, b) for k, a, b in zip(keys, norms, g["grad_norms"]) if abs(a - b) > 2e-3 * max(b, 1e-3)]
+    assert not bad, (mode, bad[:5])
+    assert np.abs(th.grad.cpu().numpy() - g["d_theta"]).max() < 2e-3 * np.abs(g["d_theta"]).max()
+
+
+@pytest.mark.parametrize("C,N,M", [(2000, 1280, 300), (3000, 384, 257), (2000, 38400, 130)])
+def test_context_projection_at_real_spectrum_widths(C, N, M):
+    """The context GEMM of c3 / c4: contraction over 2000 / 3000 spectral bins runs K-chunked on the tensor cores (chunks
+    of 1024, partial sums added in fp32 by the epilogue); checked against an fp64 matmul, output width up to c3's
+    T*(1+Bk)*H = 38400."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(C + N)
+    A = torch.randn(M, C, generator=g).cuda()
+    B = (torch.randn(N, C, generator=g) / np.sqrt(C)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    hi, lo = torch.empty_like(B), torch.empty_like(B)
+    _lib.check(L.fp_split_tf32(_lib.ptr(B), _lib.ptr(hi), _lib.ptr(lo), B.numel(), _lib.stream()), "split")
+    out = torch.empty(M, N, device="cuda")
+    a = _lib.GemmArgs()
+    a.A, a.lda, a.a_kmajor, a.B, a.ldb, a.b_kmajor = _lib.ptr(A), C, 1, _lib.ptr(B), C, 1
+    a.C, a.ldc, a.M, a.N, a.K, a.flags, a.bias, a.split_k = _lib.ptr(out), N, M, N, C, _lib.G_BIAS, _lib.ptr(bias), 1
+    _lib.check(L.fp_gemm_tc(a, _lib.ptr(hi), _lib.ptr(lo), _lib.stream()), "ctx gemm")
+    want = (A.double() @ B.double().T + bias.double()).cpu().numpy()
+    err = np.abs(out.cpu().numpy() - want).max()
+    assert err < 2e-5, err                                   # operands O(1), |result| O(1): absolute == relative here
+    # the weight-gradient form over the same widths: dW[N, C] += dOut[M, N]^T @ A[M, C]
+    Nw = min(N, 1280)
+    dOut = torch.randn(M, Nw, generator=g).cuda()
+    dW = torch.zeros(Nw, C, device="cuda")
+    b = _lib.GemmArgs()
+    b.A, b.lda, b.a_kmajor, b.B, b.ldb, b.b_kmajor = _lib.ptr(dOut), Nw, 0, _lib.ptr(A), C, 0
+    b.C, b.ldc, b.M, b.N, b.K, b.flags, b.split_k = _lib.ptr(dW), C, Nw, C, M, _lib.G_ATOMIC, 1
+    _lib.check(L.fp_gemm_tc_tn(b, _lib.stream()), "ctx wgrad")
+    want_w = (dOut.double().T @ A.double()).cpu().numpy()
+    assert np.abs(dW.cpu().numpy() - want_w).max() < 2e-4 * np.abs(want_w).max()

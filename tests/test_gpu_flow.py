@@ -25,7 +25,7 @@ def _twin(onet, cfg):
     return net.cuda().eval()
 
 
-@pytest.mark.parametrize("name", ["c1", "odd", "c2"])
+@pytest.mark.parametrize("name", ["c1", "odd", "c2", "c3", "c4"])
 def test_log_prob_matches_golden_and_oracle(name):
     onet, g, cfg = golden_oracle_net(name)
     net = _twin(onet, cfg)
@@ -42,7 +42,7 @@ def test_log_prob_matches_golden_and_oracle(name):
     assert rel_err(lp1, want1).max() < TOL
 
 
-@pytest.mark.parametrize("name", ["c1", "odd", "c2"])
+@pytest.mark.parametrize("name", ["c1", "odd", "c2", "c3", "c4"])
 def test_samples_match_golden_for_fixed_noise(name):
     onet, g, cfg = golden_oracle_net(name)
     net = _twin(onet, cfg)
@@ -59,7 +59,7 @@ def test_samples_match_golden_for_fixed_noise(name):
     assert rel_err(lp.cpu().numpy(), want.numpy()).max() < TOL
 
 
-@pytest.mark.parametrize("name", ["c1", "odd", "c2"])
+@pytest.mark.parametrize("name", ["c1", "odd", "c2", "c3", "c4"])
 def test_gradients_match_golden_and_oracle(name):
     onet, g, cfg = golden_oracle_net(name)
     net = _twin(onet, cfg)

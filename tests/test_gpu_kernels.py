@@ -84,16 +84,24 @@ def test_bin_index_census_at_scale():
     out, ld = torch.empty_like(th_d), torch.zeros(R, device="cuda")
     for inverse in (False, True):
         _, _, want_bins, kd = _oracle_coupling(theta, params, D, K, H, 0, inverse)
+        _, _, bins64, _ = _oracle_coupling(theta, params, D, K, H, 0, inverse, torch.float64)
         bins = torch.empty(R, D // 2, dtype=torch.int32, device="cuda")
         fn = _lib.lib().fp_rqs_inverse if inverse else _lib.lib().fp_rqs_forward
         _lib.check(fn(cfg, 0, _lib.ptr(th_d), _lib.ptr(p_d), _lib.ptr(out), _lib.ptr(ld), _lib.ptr(bins), R, None, _lib.stream()), "rqs")
-        flips = bins.cpu().long() != want_bins
+        got = bins.cpu().long()
+        flips = got != want_bins
         n = int(flips.sum())
-        print(f"bin census inverse={inverse}: {n} flips / {flips.numel()} elements; max knot distance of a flip "
-              f"{float(kd[flips].max()) if n else 0.0:.2e}")
-        assert n <= flips.numel() * 2e-5
-        if n:
-            assert kd[flips].max() < 1e-5
+        print(f"bin census inverse={inverse}: {n} flips / {flips.numel()} elements")
+        # every flip is enumerated with the fp64 oracle as arbiter: the input sits on a knot to within fp32 rounding
+        # (measured: 1 flip in 1.3 M elements), the kernel's bin is a neighbour of the fp32 oracle's, and the fp32 oracle
+        # itself disagrees with fp64 at least as often as the kernel does
+        for r, f in zip(*np.nonzero(flips.numpy())):
+            print(f"  flip at ({r}, {f}): kernel {int(got[r, f])}, fp32 oracle {int(want_bins[r, f])}, fp64 oracle "
+                  f"{int(bins64[r, f])}, distance to the knot {float(kd[r, f]):.2e}")
+            assert abs(int(got[r, f]) - int(want_bins[r, f])) == 1
+            assert float(kd[r, f]) < 3e-6
+        assert n <= 4, n
+        assert int((got != bins64).sum()) <= int((want_bins != bins64).sum()) + 4
 
 
 def test_rqs_empty_and_roundtrip_large():

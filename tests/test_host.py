@@ -207,3 +207,26 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_early_stopping_restores_flow_and_embedding_together():
+    """sbi deep-copies the whole state_dict at the best epoch; with an FC embedding in front of the flow (-embedding FC,
+    /root/reference/modules.py:21-45) both parameter buffers must come back from the SAME epoch."""
+    import floppity_deprecated_b200 as fb
+    theta, x = torch.rand(64, 4) * 2 - 1, torch.randn(64, 12)
+    net = fb.build_nsf(theta, x, hidden_features=16, num_transforms=2, num_bins=4, embedding_net=fb.FCEmbedding(12, 5, 2, 8))
+    inf = fb.SNPE_C(None, "nsf")
+    inf._neural_net = net
+    inf._val_log_prob = 1.0
+    assert not inf._converged(0, 2)
+    best = [p.detach().clone() for p in net.parameters()]
+    assert len(best) == 2
+    for epoch in (1, 2):
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(0.1)                       # training moves on, validation gets worse
+        inf._val_log_prob = 1.0 - 0.1 * epoch
+        done = inf._converged(epoch, 2)
+    assert done
+    for p, b in zip(net.parameters(), best):
+        assert torch.equal(p.detach(), b)

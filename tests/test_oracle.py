@@ -115,7 +115,7 @@ def test_atomic_loss_matches_manual():
             assert abs(out[b] - want) < 1e-4
 
 
-@pytest.mark.parametrize("name", ["c1", "odd", "c2"])
+@pytest.mark.parametrize("name", ["c1", "odd", "c2", "c3", "c4"])
 def test_oracle_reproduces_golden(name):
     """The committed vectors were written by tests/golden/make_golden.py; the oracle must still produce them."""
     net, g, (D, C, T, K, H, Bk, B, _) = golden_oracle_net(name)
