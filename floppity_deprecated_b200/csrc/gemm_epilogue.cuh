@@ -16,14 +16,13 @@ __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   return x;
 }
 struct DropKey {
-  uint32_t k0, k1;      // folded seed
+  uint32_t k0;          // folded seed
   uint32_t thr;         // drop when u16 < thr
   float scale;          // 1 / (1 - p)
 };
 __host__ __device__ __forceinline__ DropKey make_drop_key(uint64_t seed, float p) {
   DropKey k;
-  k.k0 = lowbias32((uint32_t)seed ^ 0x9E3779B9u);
-  k.k1 = lowbias32((uint32_t)(seed >> 32) + 0x85EBCA6Bu) ^ k.k0;
+  k.k0 = lowbias32(lowbias32((uint32_t)seed ^ 0x9E3779B9u) + (uint32_t)(seed >> 32) * 0x85EBCA6Bu);
   float t = p * 65536.f + 0.5f;
   k.thr = t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
   k.scale = 1.f / (1.f - p);
@@ -31,7 +30,7 @@ __host__ __device__ __forceinline__ DropKey make_drop_key(uint64_t seed, float p
 }
 // the two 16-bit uniforms of element pair `word` (= element index >> 1): low half = even element
 __device__ __forceinline__ uint32_t drop_word(const DropKey& k, uint64_t word) {
-  return lowbias32(((uint32_t)word * 0x9E3779B1u) ^ k.k0 ^ ((uint32_t)(word >> 32) * 0x85EBCA77u + k.k1));
+  return lowbias32(((uint32_t)word * 0x9E3779B1u) ^ k.k0 ^ ((uint32_t)(word >> 32) * 0x85EBCA77u));
 }
 __device__ __forceinline__ bool drop_keep(const DropKey& k, int64_t row, int col, int width) {
   const uint64_t e = (uint64_t)row * (uint64_t)width + (uint64_t)col;

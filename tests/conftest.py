@@ -59,3 +59,76 @@ def golden_oracle_net(name):
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / np.maximum(1.0, np.abs(b))
+
+
+# ---- gradient parity with relu knife-edges accounted for ------------------------------------------------------------
+# A hidden unit whose pre-activation is within rounding of zero takes relu'(x) = 0 in one implementation and 1 in the
+# other (the CUDA path and the oracle sum their dot products in different orders): the gradient of THAT unit's row of the
+# preceding linear layers then differs by a whole term, however accurate both are.  With ~1e6 relu decisions per golden
+# case this happens about once per case (measured: c3, coupling layer 2, unit 233, a single row).  The helpers below find
+# those units in the oracle's own activations so the gradient assertion can be tight (2e-4 of the tensor maximum --
+# measured worst 6e-5, the fp32 oracle itself sits 2-4e-5 from its fp64 twin) everywhere else.
+GRAD_TOL = 2e-4
+
+
+def knife_edge_units(onet, theta, x, eps=4e-6, keep_mode=False):
+    """{coupling layer index: set of hidden units}, and the set of batch rows, where some relu input of the oracle's
+    conditioner lies within ``eps`` (relative to 1 + |row max|) of zero."""
+    from oracle import nsf_oracle as O
+    acts, hooks = [], []
+    layers = O.coupling_layers(onet)
+    for i, c in enumerate(layers):
+        net = c.transform_net
+        mods = [net.initial_layer] + [b for b in net.blocks[:-1]] + [b.linear_layers[0] for b in net.blocks]
+        for m in mods:
+            hooks.append(m.register_forward_hook(lambda mod, inp, out, i=i: acts.append((i, out.detach()))))
+    was = onet.training
+    if not keep_mode:        # (keep_mode: training mode with injected dropout masks -- the masks change the activations)
+        onet.eval()
+    with torch.no_grad():
+        onet.log_prob(theta, x)
+    onet.train(was)
+    for h in hooks:
+        h.remove()
+    units, rows = {}, set()
+    for i, a in acts:
+        near = a.abs() < eps * (1.0 + a.abs().amax(dim=1, keepdim=True))
+        if near.any():
+            r, j = torch.nonzero(near, as_tuple=True)
+            units.setdefault(i, set()).update(int(v) for v in j)
+            rows.update(int(v) for v in r)
+    return units, rows
+
+
+def assert_grads_close(got, ref, knife=None, tol=GRAD_TOL, layer_of=None):
+    """``got`` / ``ref``: dicts of numpy arrays keyed like the upstream state_dict.  Every element must agree within
+    ``tol`` of the reference tensor's maximum, except rows (output units) that are knife-edge units of that layer; when
+    such a flip is actually observed, its diffuse effect on the other tensors (the changed gradient flows on through the
+    layers below) is allowed for with 10 x ``tol``."""
+    import re
+    units = knife[0] if knife else {}
+    flips, rest = [], {}
+    for k, r in ref.items():
+        g = np.asarray(got[k], dtype=np.float64)
+        r = np.asarray(r, dtype=np.float64)
+        err = np.abs(g - r) / max(np.abs(r).max(), 1e-4)
+        bad = err > tol
+        m = re.search(r"_transforms\.(\d+)\.transform_net", k)
+        if bad.any() and m is not None:
+            t_idx = int(m.group(1))
+            layer = layer_of(t_idx) if layer_of else (t_idx - 1) // 2
+            allowed = units.get(layer, set())
+            rows = np.nonzero(bad.reshape(bad.shape[0], -1).any(axis=1))[0]
+            hit = [int(v) for v in rows if int(v) in allowed]
+            if hit:
+                flips.append((k, hit))
+                keep = np.ones(err.shape[0], bool)
+                keep[hit] = False
+                err = err[keep]
+        rest[k] = float(err.max()) if err.size else 0.0
+    lim = tol * (10.0 if flips else 1.0)
+    over = {k: v for k, v in rest.items() if v > lim}
+    assert not over, (sorted(over.items(), key=lambda kv: -kv[1])[:5], flips, {i: sorted(u) for i, u in units.items()})
+    if flips:
+        print("relu knife-edge flips (exempt):", flips)
+    return max(rest.values())

@@ -92,7 +92,7 @@ def test_joint_training_step_gradients_match_autograd(hidden):
         assert k in got, k
         scale = max(float(p.grad.abs().max()), 1e-4)
         worst = max(worst, float((got[k].cpu() - p.grad).abs().max()) / scale)
-    assert worst < 2e-3, worst
+    assert worst < 3e-4, worst          # (measured 3e-5; no knife-edge bookkeeping through the embedding net)
     assert float((net.flow._flat.detach() - before_flow).abs().max()) > 1e-5
     assert float((net.embedding._flat.detach() - before_emb).abs().max()) > 1e-5     # the embedding is trained too
 

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import floppity_deprecated_b200 as fb
-from conftest import golden_oracle_net, rel_err
+from conftest import GRAD_TOL, assert_grads_close, golden_oracle_net, knife_edge_units, rel_err
 from floppity_deprecated_b200 import synthetic
 from oracle import nsf_oracle as O
 
@@ -71,19 +71,26 @@ def test_gradients_match_golden_and_oracle(name):
     grads = {k: v.cpu().numpy() for k, v in net.unpack(net._flat.grad).items()}
     keys = [str(k) for k in g["grad_keys"]]
     assert sorted(grads) == keys
-    norms = np.array([np.linalg.norm(grads[k]) for k in keys])
-    bad = [(k, a, b) for k, a, b in zip(keys, norms, g["grad_norms"]) if abs(a - b) > 2e-3 * max(b, 1e-3)]
-    assert not bad, bad[:5]
-    kb = str(g["grad_final_bias_key"])
-    assert np.abs(grads[kb] - g["grad_final_bias"]).max() < 2e-3 * np.abs(g["grad_final_bias"]).max()
-    assert np.abs(theta.grad.cpu().numpy() - g["d_theta"]).max() < 2e-3 * np.abs(g["d_theta"]).max()
-    # full tensor-by-tensor check against the oracle's autograd
+    # full tensor-by-tensor check against the oracle's autograd: 2e-4 of each tensor's maximum (GRAD_TOL), rows of relu
+    # knife-edge units excepted (conftest.assert_grads_close)
     onet.zero_grad()
     (-onet.log_prob(torch.tensor(g["theta"]), torch.tensor(g["x"])).mean()).backward()
-    for k, p in onet.named_parameters():
-        ref = p.grad.numpy()
-        err = np.abs(grads[k] - ref).max()
-        assert err < 2e-3 * max(np.abs(ref).max(), 1e-4), (k, err, np.abs(ref).max())
+    knife = knife_edge_units(onet, torch.tensor(g["theta"]), torch.tensor(g["x"]))
+    ref = {k: p.grad.numpy() for k, p in onet.named_parameters()}
+    worst = assert_grads_close(grads, ref, knife)
+    print(f"gradients {name}: worst {worst:.2e} of the tensor maximum")
+    # the committed vectors: per-tensor norms, one whole tensor, and the input gradient (rows with a knife-edge unit excepted)
+    flipped = worst > GRAD_TOL or any(np.abs(grads[k] - ref[k]).max() > GRAD_TOL * max(np.abs(ref[k]).max(), 1e-4) for k in ref)
+    tol_n = 10 * GRAD_TOL if flipped else GRAD_TOL
+    norms = np.array([np.linalg.norm(grads[k]) for k in keys])
+    bad = [(k, a, b) for k, a, b in zip(keys, norms, g["grad_norms"]) if abs(a - b) > 5 * tol_n * max(b, 1e-3)]
+    assert not bad, bad[:5]
+    kb = str(g["grad_final_bias_key"])
+    assert np.abs(grads[kb] - g["grad_final_bias"]).max() < tol_n * np.abs(g["grad_final_bias"]).max()
+    ok_rows = np.array([r not in knife[1] for r in range(theta.shape[0])])
+    dth = theta.grad.cpu().numpy()
+    assert np.abs(dth[ok_rows] - g["d_theta"][ok_rows]).max() < tol_n * np.abs(g["d_theta"]).max()
+    assert np.abs(dth - g["d_theta"]).max() < 2e-3 * np.abs(g["d_theta"]).max()
 
 
 def test_atomic_loss_path_matches_golden():
@@ -140,11 +147,10 @@ def test_training_steps_track_the_oracle():
             loss = -lp.mean()
             loss.backward()
             assert abs(eng.loss_sum.item() / B - loss.item()) < 1e-4 * max(1.0, abs(loss.item())), (atomic, s)
-            got = net.unpack(eng.grads[: net.param_count])
-            for k, p in o.named_parameters():
-                ref = p.grad
-                err = (got[k].cpu() - ref).abs().max().item()
-                assert err < 2e-3 * max(ref.abs().max().item(), 1e-4), (atomic, s, k, err)
+            got = {k: v.cpu().numpy() for k, v in net.unpack(eng.grads[: net.param_count]).items()}
+            rows = torch.cat([tb[:, None], tb[ch]], dim=1).reshape(-1, D) if atomic else tb
+            knife = knife_edge_units(o, rows, xb.repeat_interleave(rows.shape[0] // B, dim=0))
+            assert_grads_close(got, {k: p.grad.numpy() for k, p in o.named_parameters()}, knife)
             if s == 0:   # first Adam step from zero moments: update = -lr * clip*g / (|clip*g| + eps)
                 torch.nn.utils.clip_grad_norm_(o.parameters(), 5.0)
                 opt.step()
@@ -277,11 +283,8 @@ def test_fused_conditioner_training_gradients_many_tiles():
     loss = -onet.log_prob(theta[:B], x[:B]).mean()
     loss.backward()
     assert abs(eng.loss_sum.item() / B - loss.item()) < 1e-4 * max(1.0, abs(loss.item()))
-    got = net.unpack(eng.grads[: net.param_count])
-    worst = 0.0
-    for k, p in onet.named_parameters():
-        worst = max(worst, float((got[k].cpu() - p.grad).abs().max()) / max(float(p.grad.abs().max()), 1e-4))
-    assert worst < 2e-3, worst
+    got = {k: v.cpu().numpy() for k, v in net.unpack(eng.grads[: net.param_count]).items()}
+    assert_grads_close(got, {k: p.grad.numpy() for k, p in onet.named_parameters()}, knife_edge_units(onet, theta[:B], x[:B]))
 
 
 def test_cpu_device_request_gets_cpu_results():
@@ -409,11 +412,8 @@ def test_wide_conditioner_gemm_chain_hidden_512():
     eng = _TrainEngine(net, prior, B, False, 10, True, 5e-4, 5.0)
     eng.step_on_batch(theta[:B].cuda(), net._standardize(x[:B].cuda()))
     (-onet.log_prob(theta[:B], x[:B]).mean()).backward()
-    got_g = net.unpack(eng.grads[: net.param_count])
-    worst = 0.0
-    for k, p in onet.named_parameters():
-        worst = max(worst, float((got_g[k].cpu() - p.grad).abs().max()) / max(float(p.grad.abs().max()), 1e-4))
-    assert worst < 2e-3, worst
+    got_g = {k: v.cpu().numpy() for k, v in net.unpack(eng.grads[: net.param_count]).items()}
+    assert_grads_close(got_g, {k: p.grad.numpy() for k, p in onet.named_parameters()}, knife_edge_units(onet, theta[:B], x[:B]))
 
 
 def test_fp16_operand_range_guard():
