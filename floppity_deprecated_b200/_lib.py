@@ -101,8 +101,9 @@ SIGNATURES = {
     "fp_nsf_ctx_backward": (c_int32, [_CFG, _P, c_int64, c_int64, _P, _P, _P]),
     "fp_launch_count": (c_int64, []),
     "fp_prof_enable": (c_int32, [c_int32]),
-    "fp_prof_collect": (c_int32, [_P, _P, _P]),
-    "fp_prof_collect2": (c_int32, [_P, _P, _P, _P]),
+    "fp_prof_ntags": (c_int32, []),
+    "fp_prof_tag_name": (c_char_p, [c_int32]),
+    "fp_prof_collect": (c_int32, [_P, _P, _P, _P]),
     "fp_tc_set_debug": (c_int32, [c_int32]),
     "fp_cf_set_trace": (c_int32, [_P]),
     "fp_version": (c_char_p, []),

@@ -691,7 +691,7 @@ int launch_cond_fwd(const fp_nsf_config* cfg, const Layout& L, const float* para
   const double flops = 2.0 * (double)R * ((double)L.D * 128 + (double)L.Bk * 2 * 128 * 128 + 128.0 * dP);
   const double bytes = 4.0 * ((double)R * (L.D + dP + (training ? (3.0 * L.Bk + 1) * 128 : 0.0)) +
                               (double)(128 * L.D + L.Bk * 2 * 128 * 128 + dP * 128) * 2);
-  ProfScope ps(TAG_GEMM_TC, flops, stream, bytes);
+  ProfScope ps(TAG_COND_FWD, flops, stream, bytes);
   static int pdl_on = -1;
   if (pdl_on < 0) { const char* e = getenv("FLOPPITY_PDL"); pdl_on = (e && e[0] == '0') ? 0 : 1; }
   cudaLaunchConfig_t lc = {};

@@ -43,11 +43,20 @@ int launch_affine_bwd(const float*, const float*, float*, int64_t, int, cudaStre
 int launch_base_logprob(const float*, const float*, float*, int64_t, int, int32_t*, cudaStream_t);
 int launch_base_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
 int launch_rows_affine(const float*, const float*, const float*, float, const float*, float*, int64_t, int, cudaStream_t);
-int launch_glu_bwd(const float*, const float*, const float*, int64_t, float*, float*, int64_t, int, int, int, cudaStream_t);
+int launch_glu_bwd(const float*, const float*, const float*, int64_t, float*, float*, int64_t, int, int, int, int, cudaStream_t);
 int launch_gate_sigmoid(float*, int64_t, int64_t, int, int, cudaStream_t);
 bool cond_fwd_supported(const Layout& L, const float* prepared);      // cond_fused.cu
+bool cond_small_supported(const Layout& L, const float* prepared);    // cond_small.cu
+int launch_small_prepare(const fp_nsf_config* cfg, const float* params, float* prepared, cudaStream_t stream);
+int launch_cond_small_fwd(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
+                          const float* theta_i, const float* ctx_all, int64_t R, int ctx_div, float* const* h, float* const* t,
+                          float* const* u, float* prm, bool training, float drop_p, uint64_t drop_seed, cudaStream_t stream);
+int launch_cond_small_bwd(const fp_nsf_config* cfg, const Layout& L, const float* prepared, int i, const float* dprm,
+                          const float* const* h, const float* const* t, const float* const* u, const float* ctx_all,
+                          int ctx_div, int64_t R, float* const* du, float* const* dt, float* dh0, float* dctx_all, float* dth,
+                          float mask_scale, cudaStream_t stream);
 int launch_cond_prepare(const fp_nsf_config* cfg, const float* params, float* prepared, cudaStream_t stream);
-int launch_ctx_reduce(const float*, float*, int64_t, int64_t, int, int, cudaStream_t);
+int launch_ctx_reduce(const float*, float*, int64_t, int64_t, int, int, int, cudaStream_t);
 int launch_colsum(const float*, int64_t, int64_t, int, float*, cudaStream_t);
 int launch_sum(const float*, int64_t, float, float*, cudaStream_t);
 __global__ void k_lu_prepare(const float*, float*, fp_nsf_config);
@@ -165,10 +174,14 @@ uint64_t layer_seed(uint64_t seed, int layer, int block) {
   return seed * 0x9E3779B97F4A7C15ull + (uint64_t)(layer * 64 + block + 1) * 0xD6E8FEB86659FD93ull;
 }
 
-// One decision per flow pass: does every layer's conditioner run as the fused kernel (cond_fused.cu)?
-static bool use_fused(const fp_nsf_config* cfg, const Layout& L, const float* prepared, bool training) {
+// One decision per flow pass: does every layer's conditioner run as ONE kernel -- the tcgen05 kernel for hidden 128
+// (cond_fused.cu, returns 1) or the shared-memory-resident kernel for hidden <= 64 (cond_small.cu, returns 2)?  Both read
+// sigmoid(gate) from the gate slots of the context projection (k_gate_sigmoid).
+static int use_fused(const fp_nsf_config* cfg, const Layout& L, const float* prepared, bool training) {
   (void)cfg; (void)training;
-  return cond_fwd_supported(L, prepared);
+  if (cond_fwd_supported(L, prepared)) return 1;
+  if (cond_small_supported(L, prepared)) return 2;
+  return 0;
 }
 
 // conditioner forward of layer i: theta_i [R, D] -> spline params [R, dP_i]
@@ -183,22 +196,25 @@ struct CondBufs {
 static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
                                const float* theta_i,
                                const float* ctx_all, int64_t R, int ctx_div, const CondBufs& b, bool training,
-                               uint64_t seed, bool fused, int32_t* status, cudaStream_t s) {
-  const int H = L.H, D = L.D;
+                               uint64_t seed, int fused, int32_t* status, cudaStream_t s) {
+  const int H = L.H, D = L.D, lH = L.ldH();      // lH: row stride of the hidden-activation buffers
   const float drop = training ? cfg->dropout_p : 0.f;
+  if (fused == 2)   // hidden <= 64: the whole chain in one persistent kernel with the layer's weights resident in shared memory
+    return launch_cond_small_fwd(cfg, L, params, prepared, i, theta_i, ctx_all, R, ctx_div, b.h, b.t, b.u, b.prm, training, drop,
+                                 seed, s);
   if (fused) {   // hidden 128: the whole chain in one persistent tcgen05 kernel (activations stay in TMEM); the gate
                  // slots of ctx_all already hold sigmoid(gate), so there is no falling back to the GEMM chain from here
     return launch_cond_fwd(cfg, L, params, prepared, i, theta_i, ctx_all, R, ctx_div, b.h, b.t, b.u, b.prm, training, drop, seed,
                            status, s);
   }
   {  // initial layer: h0 = theta_i @ W0x^T + (ctx @ W0ctx^T + b0)   [the bracket is a column block of ctx_all]
-    fp_gemm_args g = gemm_nt(theta_i, D, params + L.w0x(i), D, b.h[0], H, R, H, D, FP_G_ADD_CTX);
+    fp_gemm_args g = gemm_nt(theta_i, D, params + L.w0x(i), D, b.h[0], lH, R, H, D, FP_G_ADD_CTX);
     g.G = ctx_all + L.ctxCol(i, 0); g.ldg = L.Nctx; g.ctx_div = ctx_div;
     FP_TRY(gemm_weight(L, prepared, L.w0x(i), &g, s));
   }
   for (int k = 0; k < L.Bk; ++k) {
     {  // t' = dropout(relu(h) @ W1^T + b1): relu(t') = dropout(relu(t)), (t' > 0) = relu mask AND keep mask
-      fp_gemm_args g = gemm_nt(b.h[k], H, params + L.w1(i, k), H, b.t[k], H, R, H, H,
+      fp_gemm_args g = gemm_nt(b.h[k], lH, params + L.w1(i, k), H, b.t[k], lH, R, H, H,
                                FP_G_RELU_A | FP_G_BIAS | (drop > 0.f ? FP_G_DROP_OUT : 0));
       g.bias = params + L.b1(i, k);
       g.drop_p = drop; g.drop_seed = layer_seed(seed, i, k);
@@ -206,16 +222,16 @@ static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const 
     }
     {  // u = relu(t') @ W2^T + b2 ; h_next = h + u * sigmoid(ctx gate)
       int fl = FP_G_RELU_A | FP_G_BIAS | FP_G_GLU_RES;
-      fp_gemm_args g = gemm_nt(b.t[k], H, params + L.w2(i, k), H, b.h[k + 1], H, R, H, H, fl);
+      fp_gemm_args g = gemm_nt(b.t[k], lH, params + L.w2(i, k), H, b.h[k + 1], lH, R, H, H, fl);
       g.bias = params + L.b2(i, k);
       g.G = ctx_all + L.ctxCol(i, 1 + k); g.ldg = L.Nctx; g.ctx_div = ctx_div;
-      g.Rsd = b.h[k]; g.ldr = H;
-      g.U = b.u[k]; g.ldu = H;
+      g.Rsd = b.h[k]; g.ldr = lH;
+      g.U = b.u[k]; g.ldu = lH;
       FP_TRY(gemm_weight(L, prepared, L.w2(i, k), &g, s));
     }
   }
   {  // params = h @ Wf^T + bf
-    fp_gemm_args g = gemm_nt(b.h[L.Bk], H, params + L.wf(i), H, b.prm, L.ldP(i), R, L.dP(i), H, FP_G_BIAS);
+    fp_gemm_args g = gemm_nt(b.h[L.Bk], lH, params + L.wf(i), H, b.prm, L.ldP(i), R, L.dP(i), H, FP_G_BIAS);
     g.bias = params + L.bf(i);
     FP_TRY(gemm_weight(L, prepared, L.wf(i), &g, s));
   }
@@ -316,6 +332,7 @@ int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepare
     FP_TRY(launch_transpose_split_weights(cfg, params, prepared + L.prepTHi(), prepared + L.prepTLo(), (cudaStream_t)stream));
     FP_TRY(launch_cond_prepare(cfg, params, prepared, (cudaStream_t)stream));     // fp16 operand copies for the fused conditioner
   }
+  FP_TRY(launch_small_prepare(cfg, params, prepared, (cudaStream_t)stream));      // shared-memory images for hidden <= 64
   return 0;
 }
 
@@ -345,7 +362,7 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
   float* ctx_all = ws + W.ctx_all;
   float* logdet = ws + W.logdet;
   FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
-  const bool fused = use_fused(cfg, L, prepared, training != 0);
+  const int fused = use_fused(cfg, L, prepared, training != 0);
   if (fused) FP_TRY(launch_gate_sigmoid(ctx_all, Rc, L.Nctx, L.H, L.S, s));
 
   float* th_cur = training ? ws + W.thst(0) : ws + W.th_a;
@@ -386,15 +403,19 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
   Workspace W(L, R, Rc, true);
   float* ws = workspace;
   const int A = (int)(R / Rc);
-  const int D = L.D, H = L.H;
+  const int D = L.D, H = L.H, lH = L.ldH();
   (void)dropout_seed;      // the mask is folded into the saved activations by the forward pass; nothing is re-drawn here
   const float drop_scale = cfg->dropout_p > 0.f ? 1.f / (1.f - cfg->dropout_p) : 1.f;
-  const int sig_given = use_fused(cfg, L, prepared, true) ? 1 : 0;     // same decision as the forward pass that filled ws
+  const int fused = use_fused(cfg, L, prepared, true);      // same decision as the forward pass that filled ws
+  const int sig_given = fused ? 1 : 0;
 
   float* dth_a = ws + W.dth_a; float* dth_b = ws + W.dth_b;
   float* dh = ws + W.dh; float* dt = ws + W.dt; float* du = ws + W.du; float* dprm = ws + W.dprm;
   float* dctx_all = ws + W.dctx_all;
   const float* ctx_all = ws + W.ctx_all;
+
+  // the shared-memory-resident backward adds its context gradients with reductions: start from zero
+  if (fused == 2) FP_CUDA_OK(cudaMemsetAsync(dctx_all, 0, sizeof(float) * (size_t)Rc * (size_t)L.Nctx, s));
 
   // d logp / d z_T  and  sum(d_logp) for the batch-constant LU log-dets
   FP_TRY(launch_base_bwd(ws + W.thst(L.T), d_logp, dth_a, R, D, s));
@@ -407,25 +428,40 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
     FP_TRY(launch_rqs_backward(cfg, i & 1, ws + W.thst(i), ws + W.prmbuf(i), dth_a, d_logp, dprm, dth_b, R, ldP, s,
                                prepared + L.prepM(i), ws + W.thsp(i), grads + L.gradTailDM(i), grads + L.luBias(i)));
     { float* t = dth_a; dth_a = dth_b; dth_b = t; }
+    if (fused == 2) {
+      // ---- hidden <= 64: the dgrad chain of the whole conditioner in one kernel (dh in registers), then the weight
+      //      gradients from the operands it leaves (du_k, dt_k, dh0)
+      const float* hs[17]; const float* ts[16]; const float* us[16]; float* dus[16]; float* dts[16];
+      for (int k = 0; k <= L.Bk; ++k) hs[k] = ws + W.hbuf(i, k);
+      for (int k = 0; k < L.Bk; ++k) { ts[k] = ws + W.tbuf(i, k); us[k] = ws + W.ubuf(i, k); dus[k] = ws + W.dubuf(k); dts[k] = ws + W.dtbuf(k); }
+      FP_TRY(launch_cond_small_bwd(cfg, L, prepared, i, dprm, hs, ts, us, ctx_all, A, R, dus, dts, dh, dctx_all, dth_a, drop_scale, s));
+      FP_TRY(wgrad(dprm, ldP, dP, hs[L.Bk], lH, H, R, grads + L.wf(i), H, 0, s, grads + L.bf(i)));
+      for (int k = L.Bk - 1; k >= 0; --k) {
+        FP_TRY(wgrad(dus[k], lH, H, ts[k], lH, H, R, grads + L.w2(i, k), H, FP_G_RELU_B, s, grads + L.b2(i, k)));
+        FP_TRY(wgrad(dts[k], lH, H, hs[k], lH, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, s, grads + L.b1(i, k)));
+      }
+      FP_TRY(wgrad(dh, lH, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, s));
+      continue;
+    }
     // ---- final layer
-    FP_TRY(wgrad(dprm, ldP, dP, ws + W.hbuf(i, L.Bk), H, H, R, grads + L.wf(i), H, 0, s, grads + L.bf(i)));
-    FP_TRY(dgrad_weight(L, prepared, L.tWf(i), ldP, dprm, ldP, dP, params + L.wf(i), H, H, R, dh, H, 0, nullptr, 0, 1.f, s));
+    FP_TRY(wgrad(dprm, ldP, dP, ws + W.hbuf(i, L.Bk), lH, H, R, grads + L.wf(i), H, 0, s, grads + L.bf(i)));
+    FP_TRY(dgrad_weight(L, prepared, L.tWf(i), ldP, dprm, ldP, dP, params + L.wf(i), H, H, R, dh, lH, 0, nullptr, 0, 1.f, s));
     // ---- residual blocks, last to first
     for (int k = L.Bk - 1; k >= 0; --k) {
       FP_TRY(launch_glu_bwd(dh, ws + W.ubuf(i, k), ctx_all + L.ctxCol(i, 1 + k), L.Nctx, du,
-                            dctx_all + L.ctxCol(i, 1 + k), Rc, A, H, sig_given, s));
+                            dctx_all + L.ctxCol(i, 1 + k), Rc, A, H, lH, sig_given, s));
       // the saved t is t' = dropout(t) (forward): relu(t') is the W2 operand, (t' > 0) * 1/(1-p) the mask of its gradient
-      FP_TRY(wgrad(du, H, H, ws + W.tbuf(i, k), H, H, R, grads + L.w2(i, k), H, FP_G_RELU_B, s, grads + L.b2(i, k)));
-      FP_TRY(dgrad_weight(L, prepared, L.tW2(i, k), H, du, H, H, params + L.w2(i, k), H, H, R, dt, H,
-                          FP_G_RELUMASK, ws + W.tbuf(i, k), H, drop_scale, s));
-      FP_TRY(wgrad(dt, H, H, ws + W.hbuf(i, k), H, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, s, grads + L.b1(i, k)));
-      FP_TRY(dgrad_weight(L, prepared, L.tW1(i, k), H, dt, H, H, params + L.w1(i, k), H, H, R, dh, H,
-                          FP_G_RELUMASK | FP_G_ACCUM, ws + W.hbuf(i, k), H, 1.f, s));
+      FP_TRY(wgrad(du, lH, H, ws + W.tbuf(i, k), lH, H, R, grads + L.w2(i, k), H, FP_G_RELU_B, s, grads + L.b2(i, k)));
+      FP_TRY(dgrad_weight(L, prepared, L.tW2(i, k), H, du, lH, H, params + L.w2(i, k), H, H, R, dt, lH,
+                          FP_G_RELUMASK, ws + W.tbuf(i, k), lH, drop_scale, s));
+      FP_TRY(wgrad(dt, lH, H, ws + W.hbuf(i, k), lH, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, s, grads + L.b1(i, k)));
+      FP_TRY(dgrad_weight(L, prepared, L.tW1(i, k), H, dt, lH, H, params + L.w1(i, k), H, H, R, dh, lH,
+                          FP_G_RELUMASK | FP_G_ACCUM, ws + W.hbuf(i, k), lH, 1.f, s));
     }
     // ---- initial layer: h0 = theta_i @ W0x^T + ctx slot 0
-    FP_TRY(launch_ctx_reduce(dh, dctx_all + L.ctxCol(i, 0), L.Nctx, Rc, A, H, s));
-    FP_TRY(wgrad(dh, H, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, s));
-    FP_TRY(dgrad_weight(L, prepared, L.tW0(i), H, dh, H, H, params + L.w0x(i), D, D, R, dth_a, D, FP_G_ACCUM, nullptr, 0, 1.f, s));
+    FP_TRY(launch_ctx_reduce(dh, dctx_all + L.ctxCol(i, 0), L.Nctx, Rc, A, H, lH, s));
+    FP_TRY(wgrad(dh, lH, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, s));
+    FP_TRY(dgrad_weight(L, prepared, L.tW0(i), H, dh, lH, H, params + L.w0x(i), D, D, R, dth_a, D, FP_G_ACCUM, nullptr, 0, 1.f, s));
   }
   if (d_theta) FP_TRY(launch_affine_bwd(dth_a, zscale, d_theta, R, D, s));
 
@@ -462,7 +498,7 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
   const int D = L.D;
   float* ctx_all = ws + W.ctx_all;
   FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
-  const bool fused = use_fused(cfg, L, prepared, false);
+  const int fused = use_fused(cfg, L, prepared, false);
   if (fused) FP_TRY(launch_gate_sigmoid(ctx_all, Rc, L.Nctx, L.H, L.S, s));
 
   // inverse of the last LULinear on the base noise

@@ -744,7 +744,7 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   const int nchunks = (plain && nkb > TC_KCHUNK_BLOCKS) ? (nkb + TC_KCHUNK_BLOCKS - 1) / TC_KCHUNK_BLOCKS : 1;
   const int64_t tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + TC_BN - 1) / TC_BN);
   const int grid = (int)std::min<int64_t>(tiles, num_sms());
-  ProfScope ps(TAG_GEMM_TC, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
+  ProfScope ps(TAG_GEMM_TC_NT, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
   // float4 epilogue needs every pointer the flags touch to be 16-byte aligned with a leading dimension % 4 == 0
   auto ok = [](const void* p, int64_t ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 3) == 0)); };
   int vec_all = ok(a->C, a->ldc) ? 1 : 0;
@@ -817,7 +817,7 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   const int grid = (int)std::min<int64_t>(tiles * nsplit, num_sms());
   int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
   if ((a->flags & FP_G_COLSUM_A) && (reinterpret_cast<uintptr_t>(a->U) & 15)) vec_all = 0;
-  ProfScope ps(TAG_GEMM_TC, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
+  ProfScope ps(TAG_GEMM_TC_TN, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
   FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg));
   FP_LAUNCH_CHECK();
   return 0;

@@ -38,6 +38,7 @@ struct Layout {
   FP_LHD int dPmax() const { return dtr(0) * P; }
   FP_LHD int ldP(int i) const { return (dP(i) + 3) & ~3; }      // padded row stride of the spline-parameter buffers
   FP_LHD int ldPmax() const { return (dPmax() + 3) & ~3; }
+  FP_LHD int ldH() const { return (H + 3) & ~3; }               // padded row stride of the hidden-activation buffers
   FP_LHD int64_t block_sz() const { return al4_((int64_t)H * H) * 2 + al4_(H) * 2; }
   FP_LHD int64_t layer_sz(int i) const {
     return al4_((int64_t)H * D) + Bk * block_sz() + al4_((int64_t)dP(i) * H) + al4_(dP(i)) + 2 * al4_(ntri) + 2 * al4_(D);
@@ -101,7 +102,22 @@ struct Layout {
   FP_LHD int64_t f16Floats() const { return ((f16LayerOff(T) / 2) + 63) & ~int64_t(63); }
   FP_LHD int64_t prepF16Hi() const { return ((prepTLo() + tTotal()) + 63) & ~int64_t(63); }
   FP_LHD int64_t prepF16Lo() const { return prepF16Hi() + f16Floats(); }
-  FP_LHD int64_t prepAll() const { return prepF16Lo() + f16Floats(); }
+  // shared-memory-resident conditioner for small hidden widths (cond_small.cu, H <= 64): per layer the exact byte image
+  // the kernels copy into shared memory, fp16 hi and scaled-residual lo of
+  //   forward : W0x [64][K0+8] | 2*Bk x (W1_k, W2_k) [64][72] | Wf [NF][72]                 (rows = output unit, k contiguous)
+  //   backward: Wf^T [64][KF+8] | 2*Bk x (W1_k^T, W2_k^T) [64][72] | W0x^T [D8][72]
+  // row strides are (contraction + 8) halves = an odd multiple of 16 bytes: ldmatrix reads are bank-conflict-free
+  FP_LHD bool smallH() const { return H <= 64; }
+  FP_LHD int shK0() const { return (D + 15) & ~15; }
+  FP_LHD int shNF(int i) const { return (dP(i) + 7) & ~7; }
+  FP_LHD int shKF(int i) const { return (dP(i) + 15) & ~15; }
+  FP_LHD int shD8() const { return (D + 7) & ~7; }
+  FP_LHD int64_t shFwdHalves(int i) const { return (int64_t)64 * (shK0() + 8) + (int64_t)2 * Bk * 64 * 72 + (int64_t)shNF(i) * 72; }
+  FP_LHD int64_t shBwdHalves(int i) const { return (int64_t)64 * (shKF(i) + 8) + (int64_t)2 * Bk * 64 * 72 + (int64_t)shD8() * 72; }
+  FP_LHD int64_t shLayerHalves(int i) const { return 2 * (shFwdHalves(i) + shBwdHalves(i)); }      // [F hi | F lo | B hi | B lo]
+  FP_LHD int64_t shLayerOff(int i) const { int64_t o = 0; for (int l = 0; l < i; ++l) o += shLayerHalves(l); return o; }   // halves
+  FP_LHD int64_t prepSmall() const { return (prepF16Lo() + f16Floats() + 63) & ~int64_t(63); }
+  FP_LHD int64_t prepAll() const { return prepSmall() + (smallH() ? ((shLayerOff(T) / 2 + 63) & ~int64_t(63)) : 0); }
 };
 
 // workspace carve; identical arithmetic in forward and backward so saved activations are found again
@@ -111,7 +127,7 @@ struct Workspace {
   int64_t th_a, th_b, h, t, prm;
   // training
   int64_t th_st, th_sp, act;  // act: per-layer region
-  int64_t dth_a, dth_b, dh, dt, du, dprm, dctx_all;
+  int64_t dth_a, dth_b, dh, dt, du, dprm, dctx_all, dub;
   int64_t total;
   int64_t R, Rc;
   int64_t act_layer_sz[64];
@@ -123,37 +139,40 @@ struct Workspace {
     auto take = [&](int64_t n) { int64_t r = o; o += al32(n); return r; };
     ctx_all = take(Rc * L.Nctx);
     logdet = take(R);
-    th_a = th_b = h = t = prm = th_st = th_sp = act = dth_a = dth_b = dh = dt = du = dprm = dctx_all = 0;
+    th_a = th_b = h = t = prm = th_st = th_sp = act = dth_a = dth_b = dh = dt = du = dprm = dctx_all = dub = 0;
     if (!training) {
       th_a = take(R * L.D); th_b = take(R * L.D);
-      h = take(R * L.H); t = take(R * L.H); prm = take(R * L.ldPmax());
+      h = take(R * L.ldH()); t = take(R * L.ldH()); prm = take(R * L.ldPmax());
     } else {
       th_st = take((int64_t)(L.T + 1) * al32(R * L.D));
       th_sp = take((int64_t)L.T * al32(R * L.D));
       act = o;
       for (int i = 0; i < L.T && i < 64; ++i) {
         act_layer_off[i] = o;
-        take((int64_t)(L.Bk + 1) * al32(R * L.H));  // h_0..h_Bk
-        take((int64_t)L.Bk * al32(R * L.H));        // t_b (pre-relu output of linear 0)
-        take((int64_t)L.Bk * al32(R * L.H));        // u_b (pre-gate output of linear 1)
+        take((int64_t)(L.Bk + 1) * al32(R * L.ldH()));  // h_0..h_Bk
+        take((int64_t)L.Bk * al32(R * L.ldH()));        // t_b (pre-relu output of linear 0, after dropout)
+        take((int64_t)L.Bk * al32(R * L.ldH()));        // u_b (pre-gate output of linear 1)
         take(R * L.ldP(i));                   // spline params (padded rows)
         act_layer_sz[i] = o - act_layer_off[i];
       }
       dth_a = take(R * L.D); dth_b = take(R * L.D);
-      dh = take(R * L.H); dt = take(R * L.H); du = take(R * L.H);
+      dh = take(R * L.ldH()); dt = take(R * L.ldH()); du = take(R * L.ldH());
       dprm = take(R * L.ldPmax());
       dctx_all = take(Rc * L.Nctx);
+      // the fused small-hidden backward keeps every block's du / dt for the weight gradients that follow it
+      dub = L.smallH() ? take((int64_t)2 * L.Bk * al32(R * L.ldH())) : 0;
     }
     total = o;
   }
   int64_t thst(int i) const { return th_st + (int64_t)i * al32(R * L.D); }
   int64_t thsp(int i) const { return th_sp + (int64_t)i * al32(R * L.D); }
-  int64_t hbuf(int i, int b) const { return act_layer_off[i] + (int64_t)b * al32(R * L.H); }
-  int64_t tbuf(int i, int b) const { return act_layer_off[i] + (int64_t)(L.Bk + 1) * al32(R * L.H) + (int64_t)b * al32(R * L.H); }
-  int64_t ubuf(int i, int b) const {
-    return act_layer_off[i] + (int64_t)(2 * L.Bk + 1) * al32(R * L.H) + (int64_t)b * al32(R * L.H);
-  }
-  int64_t prmbuf(int i) const { return act_layer_off[i] + (int64_t)(3 * L.Bk + 1) * al32(R * L.H); }
+  int64_t hsz() const { return al32(R * L.ldH()); }
+  int64_t hbuf(int i, int b) const { return act_layer_off[i] + (int64_t)b * hsz(); }
+  int64_t tbuf(int i, int b) const { return act_layer_off[i] + (int64_t)(L.Bk + 1) * hsz() + (int64_t)b * hsz(); }
+  int64_t ubuf(int i, int b) const { return act_layer_off[i] + (int64_t)(2 * L.Bk + 1) * hsz() + (int64_t)b * hsz(); }
+  int64_t prmbuf(int i) const { return act_layer_off[i] + (int64_t)(3 * L.Bk + 1) * hsz(); }
+  int64_t dubuf(int b) const { return dub + (int64_t)(2 * b) * hsz(); }
+  int64_t dtbuf(int b) const { return dub + (int64_t)(2 * b + 1) * hsz(); }
 };
 
 }  // namespace fp

@@ -86,7 +86,7 @@ __global__ void k_rows_affine(const float* __restrict__ x, const float* __restri
 // du = dh*sig ; dG[cr] = sum over the `A` rows sharing context row cr of dh*u*sig*(1-sig).
 // sig_given: G already holds sigmoid(gate) (the fused conditioner path applies k_gate_sigmoid to the context projection).
 __global__ void k_glu_bwd(const float* __restrict__ dh, const float* __restrict__ u, const float* __restrict__ G,
-                          int64_t ldg, float* __restrict__ du, float* __restrict__ dG, int64_t Rc, int A, int H,
+                          int64_t ldg, float* __restrict__ du, float* __restrict__ dG, int64_t Rc, int A, int H, int ldh,
                           int sig_given) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Rc * H) return;
@@ -96,9 +96,9 @@ __global__ void k_glu_bwd(const float* __restrict__ dh, const float* __restrict_
   float acc = 0.f;
   for (int a = 0; a < A; ++a) {
     int64_t r = cr * A + a;
-    float d = dh[r * H + j];
-    du[r * H + j] = d * sg;
-    acc = fmaf(d, u[r * H + j], acc);
+    float d = dh[r * ldh + j];
+    du[r * ldh + j] = d * sg;
+    acc = fmaf(d, u[r * ldh + j], acc);
   }
   dG[cr * ldg + j] = acc * sg * (1.f - sg);
 }
@@ -114,13 +114,17 @@ __global__ void k_gate_sigmoid(float* __restrict__ ctx_all, int64_t n4, int H, i
     reinterpret_cast<float4*>(ctx_all)[i] = v;
   }
 }
+__global__ void k_gate_sigmoid1(float* __restrict__ ctx_all, int64_t n, int H, int S) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    if (((e / H) % S) != 0) ctx_all[e] = 1.f / (1.f + expf(-ctx_all[e]));
+}
 // first-layer context gradient: dG[cr, j] = sum_a dh[cr*A+a, j]
-__global__ void k_ctx_reduce(const float* __restrict__ dh, float* __restrict__ dG, int64_t ldg, int64_t Rc, int A, int H) {
+__global__ void k_ctx_reduce(const float* __restrict__ dh, float* __restrict__ dG, int64_t ldg, int64_t Rc, int A, int H, int ldh) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Rc * H) return;
   int64_t cr = i / H; int j = (int)(i - cr * H);
   float acc = 0.f;
-  for (int a = 0; a < A; ++a) acc += dh[(cr * A + a) * H + j];
+  for (int a = 0; a < A; ++a) acc += dh[(cr * A + a) * ldh + j];
   dG[cr * ldg + j] = acc;
 }
 
@@ -488,22 +492,29 @@ int launch_rows_affine(const float* x, const float* M, const float* pre, float s
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_glu_bwd(const float* dh, const float* u, const float* G, int64_t ldg, float* du, float* dG, int64_t Rc, int A,
-                   int H, int sig_given, cudaStream_t s) {
+                   int H, int ldh, int sig_given, cudaStream_t s) {
   ProfScope ps(TAG_OTHER, 0.0, s);
-  k_glu_bwd<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, u, G, ldg, du, dG, Rc, A, H, sig_given);
+  k_glu_bwd<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, u, G, ldg, du, dG, Rc, A, H, ldh, sig_given);
   FP_LAUNCH_CHECK(); return 0;
 }
-// requires H % 4 == 0 and a 16-byte aligned buffer
+// float4 path: H % 4 == 0 and a 16-byte aligned buffer; any other hidden width goes element by element
 int launch_gate_sigmoid(float* ctx_all, int64_t Rc, int64_t Nctx, int H, int S, cudaStream_t s) {
+  if ((H & 3) != 0 || (reinterpret_cast<uintptr_t>(ctx_all) & 15) != 0) {
+    const int64_t n = Rc * Nctx;
+    if (n <= 0) return 0;
+    ProfScope ps(TAG_OTHER, 0.0, s);
+    k_gate_sigmoid1<<<(unsigned)std::min<int64_t>((n + 255) / 256, 16 * (int64_t)num_sms()), 256, 0, s>>>(ctx_all, n, H, S);
+    FP_LAUNCH_CHECK(); return 0;
+  }
   const int64_t n4 = Rc * Nctx / 4;
   if (n4 <= 0) return 0;
   ProfScope ps(TAG_OTHER, 0.0, s);
   k_gate_sigmoid<<<(unsigned)std::min<int64_t>((n4 + 255) / 256, 16 * (int64_t)num_sms()), 256, 0, s>>>(ctx_all, n4, H, S);
   FP_LAUNCH_CHECK(); return 0;
 }
-int launch_ctx_reduce(const float* dh, float* dG, int64_t ldg, int64_t Rc, int A, int H, cudaStream_t s) {
+int launch_ctx_reduce(const float* dh, float* dG, int64_t ldg, int64_t Rc, int A, int H, int ldh, cudaStream_t s) {
   ProfScope ps(TAG_OTHER, 0.0, s);
-  k_ctx_reduce<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, dG, ldg, Rc, A, H);
+  k_ctx_reduce<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, dG, ldg, Rc, A, H, ldh);
   FP_LAUNCH_CHECK(); return 0;
 }
 int launch_colsum(const float* X, int64_t ldx, int64_t M, int N, float* out, cudaStream_t s) {

@@ -45,24 +45,25 @@ int fp_prof_enable(int32_t on) {
   g_on = on != 0;
   return 0;
 }
-// Synchronises the device, then fills per-class totals: ms[NTAGS], launches[NTAGS], work[NTAGS]; clears the records.
-static int collect(double* ms, int64_t* launches, double* work, double* bytes) {
+static const char* const g_tag_names[NTAGS] = {"k_gemm", "k_gemm_tc_nt", "k_gemm_tc_tn", "k_cond_fwd", "k_rqs_apply_fwd", "k_rqs_apply_inv",
+                                               "k_rqs_backward", "k_cond_small_fwd", "k_cond_small_bwd", "k_embed_conv", "other"};
+int32_t fp_prof_ntags(void) { return NTAGS; }
+const char* fp_prof_tag_name(int32_t tag) { return (tag >= 0 && tag < NTAGS) ? g_tag_names[tag] : ""; }
+// Synchronises the device, then fills per-kernel totals (arrays of fp_prof_ntags() entries): elapsed ms (CUDA events on
+// the launching stream), launches, algorithmic flops and algorithmic HBM bytes; clears the records.
+int fp_prof_collect(double* ms, int64_t* launches, double* flops, double* bytes) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return (int)e;
   std::lock_guard<std::mutex> lk(g_mu);
-  for (int i = 0; i < NTAGS; ++i) { ms[i] = 0; launches[i] = 0; work[i] = 0; if (bytes) bytes[i] = 0; }
+  for (int i = 0; i < NTAGS; ++i) { ms[i] = 0; launches[i] = 0; flops[i] = 0; bytes[i] = 0; }
   for (auto& r : g_recs) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
-      ms[r.tag] += t; launches[r.tag] += 1; work[r.tag] += r.work;
-      if (bytes) bytes[r.tag] += r.bytes;
+      ms[r.tag] += t; launches[r.tag] += 1; flops[r.tag] += r.work; bytes[r.tag] += r.bytes;
     }
     g_pool.push_back(r.a); g_pool.push_back(r.b);
   }
   g_recs.clear();
   return 0;
 }
-int fp_prof_collect(double* ms, int64_t* launches, double* work) { return collect(ms, launches, work, nullptr); }
-// same, plus the algorithmic HBM bytes of the GEMM classes (bytes[NTAGS])
-int fp_prof_collect2(double* ms, int64_t* launches, double* work, double* bytes) { return collect(ms, launches, work, bytes); }
 }

@@ -1,16 +1,29 @@
 // prof.h -- launch accounting: a global launch counter (always on) and, when enabled by bench.py, CUDA-event
-// timing of every launch grouped by kernel class, together with the ALGORITHMIC work (bytes or flops) each
-// launch was asked to do.  Events are recorded on the launching stream.
+// timing of every launch grouped BY KERNEL, together with the ALGORITHMIC work (flops and HBM bytes) each launch
+// was asked to do.  Events are recorded on the launching stream.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace fp {
-enum ProfTag { TAG_GEMM_SIMT = 0, TAG_GEMM_TC = 1, TAG_RQS_FWD = 2, TAG_RQS_INV = 3, TAG_RQS_BWD = 4, TAG_OTHER = 5, NTAGS = 6 };
+enum ProfTag {
+  TAG_GEMM_SIMT = 0,       // k_gemm (exact fp32 SIMT GEMM)
+  TAG_GEMM_TC_NT = 1,      // k_gemm_tc_nt (tcgen05 forward / dgrad / context projection)
+  TAG_GEMM_TC_TN = 2,      // k_gemm_tc_tn (tcgen05 weight gradients)
+  TAG_COND_FWD = 3,        // k_cond_fwd (fused tcgen05 conditioner, hidden 128)
+  TAG_RQS_FWD = 4,         // k_rqs_apply<forward>
+  TAG_RQS_INV = 5,         // k_rqs_apply<inverse>
+  TAG_RQS_BWD = 6,         // k_rqs_backward
+  TAG_COND_SMALL_FWD = 7,  // k_cond_small_fwd (shared-memory-resident conditioner, hidden <= 64)
+  TAG_COND_SMALL_BWD = 8,  // k_cond_small_bwd
+  TAG_EMBED = 9,           // convolutional embedding kernels
+  TAG_OTHER = 10,
+  NTAGS = 11
+};
 
 struct ProfScope {
-  // work = algorithmic flops (GEMM classes) or bytes (HBM-bound classes); bytes = algorithmic HBM bytes of a GEMM
-  ProfScope(int tag, double work, cudaStream_t s, double bytes = 0.0);
+  // flops / bytes: the algorithmic work of the launch (either may be 0)
+  ProfScope(int tag, double flops, cudaStream_t s, double bytes = 0.0);
   ~ProfScope();
   cudaStream_t s_;
   int slot_;

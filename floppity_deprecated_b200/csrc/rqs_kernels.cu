@@ -441,7 +441,7 @@ int launch_rqs_apply(bool inverse, const fp_nsf_config* cfg, int parity, const f
   int64_t ntiles = (R + a.rows - 1) / a.rows;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
   // algorithmic bytes: params + theta in + theta out (transformed features) + logdet
-  ProfScope ps(inverse ? TAG_RQS_INV : TAG_RQS_FWD, 4.0 * (double)R * ((double)(a.d_tr * a.c.P) + 2.0 * a.d_tr + 1.0), stream);
+  ProfScope ps(inverse ? TAG_RQS_INV : TAG_RQS_FWD, 0.0, stream, 4.0 * (double)R * ((double)(a.d_tr * a.c.P) + 2.0 * a.d_tr + 1.0));
   kern<<<grid, threads, smem, stream>>>(a);
   FP_LAUNCH_CHECK();
   return 0;
@@ -483,7 +483,7 @@ int launch_rqs_backward(const fp_nsf_config* cfg, int parity, const float* theta
   if (occ < 1) occ = 1;
   int64_t ntiles = (R + a.rows - 1) / a.rows;
   int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * occ);
-  ProfScope ps(TAG_RQS_BWD, 4.0 * (double)R * (2.0 * (a.d_tr * a.c.P) + 3.0 * a.d_tr + 1.0), stream);
+  ProfScope ps(TAG_RQS_BWD, 0.0, stream, 4.0 * (double)R * (2.0 * (a.d_tr * a.c.P) + 3.0 * a.d_tr + 1.0));
   kern<<<grid, threads, smem, stream>>>(a);
   FP_LAUNCH_CHECK();
   return 0;

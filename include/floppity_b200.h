@@ -245,18 +245,21 @@ int fp_relu_bwd(const float* d, const float* z, float* out, int64_t n, void* str
 
 int fp_within_box(const float* theta, const float* low, const float* high, uint8_t* inside, int64_t R, int32_t D, void* stream);
 
-/* ---- launch accounting (bench.py: gpu_launches and the live roofline numbers) -----------------------
- * classes: 0 SIMT GEMM (work = flops), 1 tcgen05 GEMM (flops), 2 spline fwd, 3 spline inverse, 4 spline
- * backward (work = algorithmic bytes), 5 everything else. */
+/* ---- launch accounting (bench.py: gpu_launches and the live per-kernel roofline numbers) -----------------------
+ * Kernels are tagged individually (fp_prof_ntags() tags, fp_prof_tag_name(i) = the __global__ function's name):
+ * k_gemm, k_gemm_tc_nt, k_gemm_tc_tn, k_cond_fwd, k_rqs_apply_fwd, k_rqs_apply_inv, k_rqs_backward, k_cond_small_fwd,
+ * k_cond_small_bwd, k_embed_conv, other.  fp_prof_collect synchronises the device and fills, per tag, the elapsed
+ * milliseconds (CUDA events recorded around every launch on the launching stream), the launch count and the
+ * ALGORITHMIC flops and HBM bytes those launches were asked to do, then clears the records. */
 /* Rejection step of accept_reject_sample: append the rows of theta [R, D] that lie inside [low, high] to out (row
  * capacity `cap`) behind the device counter *counter (rows accepted so far, also counts rows beyond cap). */
 int fp_compact_inside(const float* theta, const float* low, const float* high, float* out, uint64_t* counter, int64_t R,
                       int32_t D, int64_t cap, void* stream);
 int64_t fp_launch_count(void);
 int fp_prof_enable(int32_t on);
-int fp_prof_collect(double* ms /*[6]*/, int64_t* launches /*[6]*/, double* work /*[6]*/);
-/* same, plus the algorithmic HBM bytes of the GEMM classes (operands + result + epilogue streams, each once) */
-int fp_prof_collect2(double* ms /*[6]*/, int64_t* launches /*[6]*/, double* work /*[6]*/, double* bytes /*[6]*/);
+int32_t fp_prof_ntags(void);
+const char* fp_prof_tag_name(int32_t tag);
+int fp_prof_collect(double* ms, int64_t* launches, double* flops, double* bytes);
 
 const char* fp_version(void);
 

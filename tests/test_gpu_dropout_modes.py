@@ -268,3 +268,88 @@ def test_context_projection_at_real_spectrum_widths(C, N, M):
     _lib.check(L.fp_gemm_tc_tn(b, _lib.stream()), "ctx wgrad")
     want_w = (dOut.double().T @ A.double()).cpu().numpy()
     assert np.abs(dW.cpu().numpy() - want_w).max() < 2e-4 * np.abs(want_w).max()
+
+
+def _kernel_launches(fn):
+    """{kernel name: launches} of the library kernels ``fn`` enqueues (the library's own per-kernel accounting)."""
+    import ctypes
+    L = _lib.lib()
+    n = L.fp_prof_ntags()
+    ms, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    L.fp_prof_enable(1)
+    try:
+        L.fp_prof_collect(ms, cnt, fl, by)
+        fn()
+        _lib.check(L.fp_prof_collect(ms, cnt, fl, by), "prof")
+    finally:
+        L.fp_prof_enable(0)
+    return {L.fp_prof_tag_name(i).decode(): int(cnt[i]) for i in range(n)}
+
+
+def test_reference_default_network_runs_on_the_shared_memory_kernel():
+    """The network FlopPITy builds when no flag is given (-hidden 50 -transforms 10 -bins 8 -blocks 3 -dropout 0.1,
+    /root/reference/floppity.py:34,35,48,50,57) on c1-sized inputs: log_prob, samples and training-mode gradients under
+    the library's own dropout mask match the oracle, and the conditioner really is the shared-memory-resident kernel --
+    one launch per coupling layer and direction, no per-layer SIMT GEMMs."""
+    D, C, H, T, K, Bk, p, R = 10, 100, 50, 10, 8, 3, 0.1, 777
+    onet, net, theta, x = _pair(D, C, H, T, K, Bk, p, seed=31)
+    net.eval(); onet.eval()
+    with torch.no_grad():
+        want = onet.log_prob(theta[:R], x[:R]).numpy()
+    box = {}
+    counts = _kernel_launches(lambda: box.setdefault("lp", net.log_prob(theta[:R].cuda(), x[:R].cuda())))
+    assert rel_err(box["lp"].detach().cpu().numpy(), want).max() < TOL
+    assert counts["k_cond_small_fwd"] == T and counts["k_cond_small_bwd"] == 0, counts
+    assert counts["k_gemm"] + counts["k_gemm_tc_nt"] <= 1, counts            # the context projection is the only GEMM left
+    z = torch.randn(500, D, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        s = net.sample(500, context=x[:1].cuda(), noise=z.cuda())[0].cpu().numpy()
+        ws = onet.sample(500, context=x[:1], noise=z)[0].numpy()
+    assert rel_err(s, ws).max() < TOL
+    # ragged sizes: a single row, one row more than a 16-row warp tile, atoms sharing context rows
+    with torch.no_grad():
+        for n, a in ((1, 1), (17, 1), (130, 10)):
+            got = net.log_prob(theta[:n * a].cuda(), x[:n].cuda()).cpu().numpy()
+            ref = onet.log_prob(theta[:n * a], x[:n].repeat_interleave(a, dim=0)).numpy()
+            assert rel_err(got, ref).max() < TOL, (n, a)
+    net.train(); onet.train()
+    th = theta[:R].cuda().requires_grad_(True)
+    counts = _kernel_launches(lambda: (-net.log_prob(th, x[:R].cuda()).mean()).backward())
+    assert counts["k_cond_small_fwd"] == T and counts["k_cond_small_bwd"] == T, counts
+    O.inject_dropout_masks(onet, _masks(net, net._step_seed, R), p)
+    tho = theta[:R].clone().requires_grad_(True)
+    (-onet.log_prob(tho, x[:R]).mean()).backward()
+    knife = knife_edge_units(onet, theta[:R], x[:R], keep_mode=True)
+    got_g = {k: v.cpu().numpy() for k, v in net.unpack(net._flat.grad).items()}
+    worst = assert_grads_close(got_g, {k: prm.grad.numpy() for k, prm in onet.named_parameters()}, knife)
+    ok_rows = np.array([r not in knife[1] for r in range(R)])
+    assert np.abs(th.grad.cpu().numpy()[ok_rows] - tho.grad.numpy()[ok_rows]).max() < GRAD_TOL * np.abs(tho.grad.numpy()).max()
+    print(f"reference-default network: worst gradient error {worst:.2e} of the tensor maximum")
+
+
+def test_small_hidden_kernel_handles_wide_ranges():
+    """Row-wise power-of-two scaling keeps the 3xFP16 products fp32-accurate whatever the magnitudes: activations of order
+    1e5 (beyond fp16's range unscaled) and gradients of order 1e-9 give the same relative accuracy."""
+    D, C, H, T, K, Bk = 8, 16, 40, 2, 6, 2
+    onet, net, theta, x = _pair(D, C, H, T, K, Bk, 0.0, seed=77)
+    with torch.no_grad():
+        for c in O.coupling_layers(onet):
+            c.transform_net.initial_layer.bias.add_(2.0e5)          # h0 ~ 2e5 everywhere
+            c.transform_net.final_layer.weight.mul_(1e-5)           # keep the spline parameters O(1)
+    net.load_state_dict(onet.state_dict())
+    net.eval(); onet.eval()
+    with torch.no_grad():
+        got = net.log_prob(theta[:200].cuda(), x[:200].cuda()).cpu().numpy()
+        want = onet.double().log_prob(theta[:200].double(), x[:200].double()).numpy()
+    assert rel_err(got, want).max() < TOL, rel_err(got, want).max()
+    net.flow_check = getattr(net, "check_last_status", lambda: None)
+    net.flow_check()                                                 # no fp16-range complaint on this path
+    onet.float()
+    net.train(); onet.train()
+    th = theta[:200].cuda().requires_grad_(True)
+    (net.log_prob(th, x[:200].cuda()).sum() * 1e-9).backward()
+    tho = theta[:200].clone().requires_grad_(True)
+    (onet.log_prob(tho, x[:200]).sum() * 1e-9).backward()
+    ref = tho.grad.numpy()
+    assert np.abs(th.grad.cpu().numpy() - ref).max() < 2e-3 * np.abs(ref).max()
