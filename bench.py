@@ -1,16 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- NSF training pairs/s (headline) + posterior samples/s on the BASELINE.json workload.
+"""bench.py -- NSF training pairs/s (headline) and posterior samples/s / log_prob/s on the BASELINE.json workloads.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the restated sbi path (oracle/) on the host CPU cores
 
-A "step" is one optimiser step of ``SNPE_C.train`` (sbi PosteriorEstimator.train, /root/reference/floppity.py:219)
-on one batch: gather batch from the HBM-resident dataset -> flow forward -> loss -> hand-written backward ->
-[NCCL all-reduce] -> clip_grad_norm_(5) + Adam.  Workload = BASELINE.json configs[1] (c2: NSF T10 K10 H128 Bk2,
-20 params / 500 bins, atoms 10), synthetic spectra (ARCiS is external Fortran), random-init weights.
-Weak scaling: the per-GPU batch is fixed.  One JSON line on stdout (rank 0).
+A "step" is one optimiser step of ``SNPE_C.train`` (sbi PosteriorEstimator.train, /root/reference/floppity.py:219) on
+one batch: gather the batch from the HBM-resident dataset -> flow forward -> loss -> hand-written backward ->
+[NCCL all-reduce] -> clip_grad_norm_(5) + Adam.
+
+Headline workload (``value``): BASELINE.json configs[2] (c3: NSF T15 K16 H512 Bk4, 30 parameters / 2000-bin spectra) --
+the largest configuration that fits one GPU -- with the maximum-likelihood loss (configs[2] names no atoms, and it is the
+branch the reference takes on every round: force_first_round_loss=True, floppity.py:220).  configs[1] (c2, atoms 10),
+configs[0] (c1, the reference-default hidden 50) and configs[3] (c4, atoms 20) ride along as ``extras`` with their own
+roofline blocks; configs[4] (sampling / log_prob from a trained flow, sharded over the ranks) gives
+``posterior_samples_per_s`` and ``log_prob_per_s``.  Synthetic spectra (ARCiS is external Fortran), random-init
+weights.  Weak scaling: the per-GPU batch is fixed.  ``e2e`` goes through the public call a user makes --
+``SNPE_C.append_simulations(pinned host tensors)`` + ``SNPE_C.train()`` (upload, epochs, validation, returned copy).
+One JSON line on stdout (rank 0).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -24,7 +33,19 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CLASS_NAMES = ["gemm_simt_fp32", "gemm_tcgen05", "rqs_forward", "rqs_inverse", "rqs_backward", "other"]
+# per-config bench settings: loss, per-GPU batch, resident rows per GPU
+#   c3: 18 944 rows = 148 row tiles of 128 -> whole waves of the 128x128 GEMM tiles on 148 SMs
+#   c1 / c2 / c4: 9 472 pairs x atoms = 740 / 1480 row tiles = 5 / 10 per SM
+WORKLOADS = {
+    "c1": dict(loss="atomic", batch=9472, rows=65536),
+    "c2": dict(loss="atomic", batch=9472, rows=65536),
+    "c3": dict(loss="mle", batch=18944, rows=65536),
+    "c4": dict(loss="atomic", batch=9472, rows=32768),
+}
+CONFIG_INDEX = {"c1": 0, "c2": 1, "c3": 2, "c4": 3}
+# operand format of each tensor-core kernel: passes of the fp32-accurate split and the rate of one pass relative to bf16
+TENSOR_KERNELS = {"k_gemm_tc_nt": ("3xTF32", 6.0), "k_gemm_tc_tn": ("3xTF32", 6.0), "k_cond_fwd": ("3xFP16", 3.0),
+                  "k_cond_small_fwd": ("3xFP16 mma.sync", 3.0), "k_cond_small_bwd": ("3xFP16 mma.sync", 3.0)}
 
 
 def parse():
@@ -33,19 +54,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4"])
-    ap.add_argument("--batch", type=int, default=9472,
-                    help="per-GPU batch (rows of (theta, x) pairs).  Default 9472 = 148 SMs x 64: with atoms 10 a step is "
-                         "94 720 flow rows = 740 row tiles of 128 = exactly 5 per SM, so the persistent kernels run whole "
-                         "waves (4096 leaves 2.16 tiles per SM: 3 waves of work for 2.16 waves of rows)")
-    ap.add_argument("--loss", default="atomic", choices=["atomic", "mle"],
-                    help="atomic = SNPE-C APT loss with `atoms` contrastive proposals (subsystem 3); mle = the branch "
-                         "the reference actually takes (force_first_round_loss=True, floppity.py:220)")
-    ap.add_argument("--rows", type=int, default=65536, help="resident dataset rows per GPU (c2: 50k pairs/round -> 65 536)")
-    ap.add_argument("--ref-batch", type=int, default=256, help="bounded per-step sample for the CPU arm")
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4"], help="headline workload")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = the workload's default)")
+    ap.add_argument("--loss", default="", choices=["", "atomic", "mle"])
+    ap.add_argument("--rows", type=int, default=0, help="resident dataset rows per GPU (0 = the workload's default)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="bounded per-step sample of the CPU arm (0 = sized per config)")
+    ap.add_argument("--dropout", type=float, default=0.0)
     ap.add_argument("--graph", type=int, default=0, help="replay the optimiser step from a CUDA graph")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
@@ -105,62 +123,110 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_data(cfg_name, rows, seed):
+def make_data(cfg_name, rows, seed, base_rows=4096):
+    """Synthetic (theta, x) rows of the named shape.  The spectrum generator is evaluated for ``base_rows`` distinct
+    parameter vectors; the resident set is those spectra tiled with FRESH noise draws (what -naug does in the reference,
+    floppityFUN.py:383-428): throughput does not depend on the content, and the generator's exp() cost stays bounded."""
     from floppity_deprecated_b200 import synthetic
     cfg = synthetic.CONFIGS[cfg_name]
     rng = np.random.default_rng(seed)
-    theta = rng.uniform(-3, 3, (rows, cfg.D))          # prior draws in the -ynorm box (same support as the Sobol round 0)
-    th, x, scaler, _ = synthetic.make_dataset(cfg_name, theta=theta, noise_seed=4321 + seed)
-    return cfg, torch.tensor(th), torch.tensor(x)
+    nb = min(rows, base_rows)
+    theta = synthetic.swap_hotter_first(cfg, rng.uniform(-3, 3, (nb, cfg.D)))   # prior draws in the -ynorm box
+    spec = synthetic.simulate(cfg, theta)
+    sigma = 0.01 * np.median(spec, axis=0)
+    reps = (rows + nb - 1) // nb
+    th = np.tile(theta, (reps, 1))[:rows].astype(np.float32)
+    x = np.tile(spec.astype(np.float32), (reps, 1))[:rows]
+    x += (sigma[None, :] * rng.standard_normal((rows, cfg.C), dtype=np.float32)).astype(np.float32)
+    mean, std = x.mean(axis=0), x.std(axis=0)
+    std[std == 0] = 1.0
+    x = (x - mean) / std
+    return cfg, torch.from_numpy(th), torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+
+
+def workload_desc(name, cfg, loss, B, rows, world, dropout):
+    """The ``config`` object: identical in both arms (``--impl reference`` prints the same one)."""
+    atoms = f", atoms {cfg.atoms}" if loss == "atomic" else ""
+    return {"workload": f"{name}: NSF T{cfg.transforms} K{cfg.bins} H{cfg.hidden} Bk{cfg.blocks}, {cfg.D} params / {cfg.C} bins"
+                        f"{atoms} (BASELINE.json configs[{CONFIG_INDEX[name]}])",
+            "loss": loss + (" (SNPE-C APT)" if loss == "atomic" else " (force_first_round_loss=True, floppity.py:220)"),
+            "per_gpu_batch": B, "global_batch": B * world, "resident_rows_per_gpu": rows, "dropout": dropout,
+            "parallelism": f"dp{world}",
+            "l2": "no flush: the per-step activation workspace (GBs) is far larger than the 126 MB L2"}
+
+
+def settings(args, name):
+    w = dict(WORKLOADS[name])
+    if name == args.config:
+        if args.batch:
+            w["batch"] = args.batch
+        if args.loss:
+            w["loss"] = args.loss
+        if args.rows:
+            w["rows"] = args.rows
+    return w
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
+def oracle_steps(cfg, loss, Bc, theta, x, warmup, steps=None, seconds=None, dropout=0.0):
+    """Optimiser steps of the restated sbi path (oracle/nsf_oracle.py, eager fp32 PyTorch) on all host cores; returns
+    (pairs/s, steps timed, seconds)."""
+    from oracle import nsf_oracle as O
+    net = O.build_nsf(theta[:2048], x[:2048], hidden_features=cfg.hidden, num_transforms=cfg.transforms, num_bins=cfg.bins,
+                      num_blocks=cfg.blocks, dropout_probability=dropout)
+    prior = O.BoxUniform(-3 * torch.ones(cfg.D), 3 * torch.ones(cfg.D))
+    opt = torch.optim.Adam(net.parameters(), lr=5e-4)
+    masks = torch.zeros(Bc, 1)
+    net.train()
+
+    def step():
+        idx = torch.randint(0, theta.shape[0], (Bc,))
+        opt.zero_grad()
+        lp = (O.log_prob_proposal_posterior_atomic(net, prior, theta[idx], x[idx], masks, cfg.atoms, True)
+              if loss == "atomic" else net.log_prob(theta[idx], x[idx]))
+        (-lp.mean()).backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 5.0)
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        dt = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (seconds is not None and dt > seconds and n >= 2):
+            break
+    return Bc * n / dt, n, dt
+
+
+def ref_batch_for(args, cfg):
+    if args.ref_batch:
+        return args.ref_batch
+    return 64 if cfg.hidden >= 512 else 256
+
+
 def run_reference(args):
-    """Restated sbi path (oracle/nsf_oracle.py, plain eager PyTorch fp32) on ALL host cores.  sbi/nflows cannot be
-    installed here, so `kind` is "port".  Each step is a bounded sample (batch --ref-batch) of the same workload."""
+    """Restated sbi path (oracle/, "port": sbi / nflows cannot be installed here) on ALL host cores.  Same config object
+    as our arm; each step is a bounded sample (batch --ref-batch) of that workload's per-GPU batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import nsf_oracle as O
+    from floppity_deprecated_b200 import synthetic
+    w = settings(args, args.config)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg, theta, x = make_data(args.config, max(2048, args.ref_batch * 4), 0)
+    cfg, theta, x = make_data(args.config, 4096, 0)
+    Bc = ref_batch_for(args, cfg)
     torch.manual_seed(0)
-    net = O.build_nsf(theta, x, hidden_features=cfg.hidden, num_transforms=cfg.transforms, num_bins=cfg.bins,
-                      num_blocks=cfg.blocks)
-    prior = O.BoxUniform(-3 * torch.ones(cfg.D), 3 * torch.ones(cfg.D))
-    opt = torch.optim.Adam(net.parameters(), lr=5e-4)
-    B = args.ref_batch
-    masks = torch.zeros(B, 1)
-    net.train()
-
-    def step(i):
-        idx = torch.randint(0, theta.shape[0], (B,))
-        opt.zero_grad()
-        if args.loss == "atomic":
-            lp = O.log_prob_proposal_posterior_atomic(net, prior, theta[idx], x[idx], masks, cfg.atoms, True)
-        else:
-            lp = net.log_prob(theta[idx], x[idx])
-        loss = -lp.mean()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(net.parameters(), 5.0)
-        opt.step()
-        return float(loss)
-
-    for i in range(args.warmup):
-        step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
-    dt = time.perf_counter() - t0
-    v = B * args.steps / dt
-    sample = f"{args.steps} optimiser steps at batch {B} (bounded sample of the per-GPU batch {args.batch}), {args.loss} loss"
+    v, n, dt = oracle_steps(cfg, w["loss"], Bc, theta, x, args.warmup, steps=args.steps, dropout=args.dropout)
+    sample = (f"{n} optimiser steps at batch {Bc} (a bounded sample of the per-GPU batch {w['batch']}), {w['loss']} loss, "
+              f"oracle/nsf_oracle.py eager fp32 on {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": "NSF train pairs/s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / n, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: SNPE-C NSF T{cfg.transforms} K{cfg.bins} H{cfg.hidden} Bk{cfg.blocks}, "
-                               f"{cfg.D} params / {cfg.C} bins, atoms {cfg.atoms}", "loss": args.loss, "batch": B},
+        "config": workload_desc(args.config, cfg, w["loss"], w["batch"], w["rows"], max(args.gpus, 1), args.dropout),
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -168,6 +234,10 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- our arm
+class Ctx:
+    pass
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -187,27 +257,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     import floppity_deprecated_b200 as fb
-    from floppity_deprecated_b200 import _lib
+    from floppity_deprecated_b200 import _lib, dist as fdist
     from floppity_deprecated_b200.inference import _TrainEngine
     L = _lib.lib()
     PK = peaks()
+    K, W = args.steps, max(args.warmup, 3)
+    NT = L.fp_prof_ntags()
+    TAGS = [L.fp_prof_tag_name(i).decode() for i in range(NT)]
 
-    cfg, theta, x = make_data(args.config, args.rows, rank)
-    torch.manual_seed(0)
-    net = fb.build_nsf(theta, x, hidden_features=cfg.hidden, num_transforms=cfg.transforms, num_bins=cfg.bins,
-                       num_blocks=cfg.blocks, generator=torch.Generator().manual_seed(0)).to(dev)
-    if world > 1:
-        dist.broadcast(net._flat.data, src=0)
-    net.train()
-    prior = fb.BoxUniform(-3 * torch.ones(cfg.D), 3 * torch.ones(cfg.D), device=dev)
-    B, K, W = args.batch, args.steps, args.warmup
-    atomic = args.loss == "atomic"
-    eng = _TrainEngine(net, prior, B, atomic, cfg.atoms, True, 5e-4, 5.0, use_graph=bool(args.graph))
-    theta_dev = theta.to(dev).contiguous()
-    x_dev = net._standardize(x.to(dev))
-    masks_dev = torch.zeros(args.rows, device=dev)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    batches = [torch.randint(0, args.rows, (B,), device=dev, generator=g) for _ in range(8)]
+    def log(msg):
+        print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
 
     def barrier():
         if world > 1:
@@ -215,6 +274,7 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, n):
+        """n calls of fn between two CUDA events on the current stream, barrier + synchronize on both sides, max over ranks"""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -228,221 +288,246 @@ def main():
         barrier()
         return float(ms.item())
 
-    def step(i):
-        eng.step(batches[i % len(batches)], theta_dev, x_dev, masks_dev)
-
-    for i in range(max(W, 3)):
-        step(i)
-    clocks = ClockSampler(local)
-    clocks.start()
-    n0 = L.fp_launch_count()
-    ms = timed(step, K)
-    launches = int(L.fp_launch_count() - n0)
-    if eng.graph is not None:            # replays do not pass through the launch counter: kernels per captured step x K
-        launches = eng.launches_per_step * K
-    clk = clocks.stop()
-    eng.check_status()
-    value = world * B * K / (ms * 1e-3)
-    print(f"[bench] rank {rank}: {ms / K:.3f} ms/step, {value:.0f} pairs/s", file=sys.stderr, flush=True)
-
-    # ---- e2e: host (pinned) batch -> H2D -> standardise -> step -> D2H loss, through the host-facing step call
-    th_pin = [theta[b.cpu()].pin_memory() for b in batches[:4]]
-    x_pin = [x[b.cpu()].pin_memory() for b in batches[:4]]
-    # two device staging buffers: the H2D copy of step i+1 (copy stream) runs under the kernels of step i, the way a
-    # prefetching loader feeds a training loop; every step still copies its own inputs and reads its own loss back
-    stage = [(torch.empty(B, cfg.D, device=dev), torch.empty(B, cfg.C, device=dev)) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
-    losses = []
-
-    def issue_copy(i):
-        b = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(free[b])                 # the step that last used this buffer is done with it
-            stage[b][0].copy_(th_pin[i % 4], non_blocking=True)
-            stage[b][1].copy_(x_pin[i % 4], non_blocking=True)
-            ready[b].record(copy_stream)
-
-    def e2e_step(i):
-        b = i % 2
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ready[b])
-        issue_copy(i + 1)
-        eng.loss_sum.zero_()
-        eng.step_on_batch(stage[b][0], net._standardize(stage[b][1]))
-        free[b].record(cur)
-        losses.append(float(eng.loss_sum.item()) / B)      # device -> host read of the step's loss
-
-    def e2e_run(n):
-        for b in range(2):
-            free[b].record(torch.cuda.current_stream())
-        issue_copy(0)
+    def kernel_table(fn, n):
+        """Per-kernel CUDA-event timing of n calls of fn (events recorded around every launch on the launching stream)."""
+        arr = lambda t: (t * NT)()
+        pms, pl, pf, pb = arr(ctypes.c_double), arr(ctypes.c_int64), arr(ctypes.c_double), arr(ctypes.c_double)
+        L.fp_prof_enable(1)
+        L.fp_prof_collect(pms, pl, pf, pb)
         for i in range(n):
-            e2e_step(i)
+            fn(i)
+        _lib.check(L.fp_prof_collect(pms, pl, pf, pb), "prof")
+        L.fp_prof_enable(0)
+        tot = sum(pms) or 1.0
+        table = {}
+        for i, name in enumerate(TAGS):
+            if pl[i] == 0:
+                continue
+            sec = pms[i] * 1e-3
+            d = {"share": pms[i] / tot, "launches_per_step": pl[i] / n, "avg_us": 1e3 * pms[i] / pl[i]}
+            if pb[i] > 0:
+                d["algorithmic_bytes_per_launch"] = pb[i] / pl[i]
+                d["achieved_gbs"] = pb[i] / sec / 1e9
+                d["frac_of_hbm_peak"] = d["achieved_gbs"] / PK["hbm"]
+            if pf[i] > 0:
+                d["algorithmic_flops_per_launch"] = pf[i] / pl[i]
+                d["achieved_tflops"] = pf[i] / sec / 1e12
+                if name in TENSOR_KERNELS:
+                    fmt, div = TENSOR_KERNELS[name]
+                    d["operands"] = fmt
+                    d["frac_of_tensor_ceiling"] = d["achieved_tflops"] / (PK["tf_sust"] / div)
+                    d["frac_of_bf16_peak"] = d["achieved_tflops"] / PK["tf_sust"]
+            table[name] = d
+        return table
 
-    e2e_run(2)
-    torch.cuda.synchronize()
-
-    def timed_e2e(n):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_run(n)                                          # includes the first step's exposed copy
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        barrier()
-        return float(t.item())
-
-    ms_e2e = timed_e2e(K)
-    e2e = {"value": world * B * K / (ms_e2e * 1e-3), "unit": "pairs/s",
-           "h2d_bytes_per_step": int(B * (cfg.D + cfg.C) * 4), "d2h_bytes_per_step": 4}
-
-    # ---- per-kernel-class CUDA-event timing inside a second pass over the same K steps
-    out_extra = {}
-    L.fp_prof_enable(1)
-    for i in range(K):      # plain launches (a graph replay would bypass the per-launch event hooks)
-        eng.idx.copy_(batches[i % len(batches)])
-        eng._step_body(theta_dev, x_dev, masks_dev)
-    import ctypes
-    pms, pl, pw, pb = (ctypes.c_double * 6)(), (ctypes.c_int64 * 6)(), (ctypes.c_double * 6)(), (ctypes.c_double * 6)()
-    _lib.check(L.fp_prof_collect2(pms, pl, pw, pb), "prof")
-    L.fp_prof_enable(0)
-    tot = sum(pms) or 1.0
-    # 3xTF32: three TF32 passes per fp32-accurate product; TF32 dense peak = half the measured bf16 peak
-    tf32x3_peak = PK["tf_sust"] / 2.0 / 3.0
-    classes = {}
-    for i, name in enumerate(CLASS_NAMES):
-        if pl[i] == 0:
-            continue
-        d = {"share": pms[i] / tot, "launches_per_step": pl[i] / K, "avg_us": 1e3 * pms[i] / pl[i]}
-        if i in (0, 1):
-            d["achieved_tflops_fp32_equiv"] = pw[i] / (pms[i] * 1e-3) / 1e12
-            d["frac_of_3xtf32_tensor_peak"] = d["achieved_tflops_fp32_equiv"] / tf32x3_peak
-            d["achieved_gbs"] = pb[i] / (pms[i] * 1e-3) / 1e9
-            d["frac_of_hbm_peak"] = d["achieved_gbs"] / PK["hbm"]
-        elif i in (2, 3, 4):
-            d["achieved_gbs"] = pw[i] / (pms[i] * 1e-3) / 1e9
-            d["frac_of_hbm_peak"] = d["achieved_gbs"] / PK["hbm"]
-        classes[name] = d
-    dom = max(range(6), key=lambda i: pms[i])
-    if dom in (0, 1):
-        # The conditioner GEMMs of this workload are skinny (hidden 128): arithmetic intensity ~32 flop/B in fp32, i.e.
-        # below the ridge even at three TF32 passes.  Both fractions are measured; the binding one is reported.
-        ach_t = pw[dom] / (pms[dom] * 1e-3) / 1e12
-        ach_b = pb[dom] / (pms[dom] * 1e-3) / 1e9
-        if ach_b / PK["hbm"] >= ach_t / tf32x3_peak:
-            roof = {"bound": "hbm", "achieved": ach_b, "peak": PK["hbm"], "unit": "GB/s", "frac": ach_b / PK["hbm"],
-                    "traffic": None, "kernel": CLASS_NAMES[dom], "peak_source": PK["source"],
-                    "tensor_frac_3xtf32": ach_t / tf32x3_peak}
+    def roofline_of(table):
+        """The roofline block of the kernel with the largest share of the step: ONE kernel, its own CUDA-event time."""
+        named = {k: v for k, v in table.items() if k != "other"}
+        if not named:
+            return None
+        name = max(named, key=lambda k: named[k]["share"])
+        d = named[name]
+        hb = d.get("frac_of_hbm_peak", 0.0)
+        tc = d.get("frac_of_tensor_ceiling", 0.0)
+        if name in TENSOR_KERNELS and tc >= hb:
+            fmt, div = TENSOR_KERNELS[name]
+            roof = {"bound": "tensor", "achieved": d["achieved_tflops"], "peak": PK["tf_sust"] / div, "unit": "TFLOP/s",
+                    "frac": tc, "traffic": None, "kernel": name, "share_of_step": d["share"], "avg_us": d["avg_us"],
+                    "peak_source": f"{PK['source']}: bf16 sustained {PK['tf_sust']:.0f} TFLOP/s / {div:.0f} -- {fmt} operands: "
+                                   f"three tensor-core passes per fp32-accurate product"
+                                   f"{' at the TF32 rate (half of bf16)' if div == 6.0 else ''}",
+                    "frac_of_bf16_peak": d["frac_of_bf16_peak"], "hbm_frac": hb}
+        elif name == "k_gemm":
+            fma = 148 * 128 * 2 * 1.965e9 / 1e12
+            roof = {"bound": "fma", "achieved": d.get("achieved_tflops", 0.0), "peak": fma, "unit": "TFLOP/s",
+                    "frac": d.get("achieved_tflops", 0.0) / fma, "traffic": None, "kernel": name, "share_of_step": d["share"],
+                    "avg_us": d["avg_us"], "peak_source": "148 SMs x 128 fp32 lanes x 2 x 1.965 GHz (FMA issue)", "hbm_frac": hb}
         else:
-            roof = {"bound": "tensor", "achieved": ach_t, "peak": tf32x3_peak, "unit": "TFLOP/s", "frac": ach_t / tf32x3_peak,
-                    "traffic": None, "kernel": CLASS_NAMES[dom],
-                    "peak_source": PK["source"] + ": bf16 sustained / 2 (TF32) / 3 (passes of the fp32-accurate split)",
-                    "hbm_frac": ach_b / PK["hbm"]}
-    else:
-        ach = pw[dom] / (pms[dom] * 1e-3) / 1e9 if pw[dom] else 0.0
-        roof = {"bound": "hbm", "achieved": ach, "peak": PK["hbm"], "unit": "GB/s", "frac": ach / PK["hbm"], "traffic": None,
-                "kernel": CLASS_NAMES[dom], "peak_source": PK["source"]}
+            roof = {"bound": "hbm", "achieved": d.get("achieved_gbs", 0.0), "peak": PK["hbm"], "unit": "GB/s", "frac": hb,
+                    "traffic": None, "kernel": name, "share_of_step": d["share"], "avg_us": d["avg_us"],
+                    "peak_source": PK["source"]}
+            if name in TENSOR_KERNELS:
+                roof["tensor_frac"] = tc
+        try:        # measured DRAM traffic of that kernel (one ncu --set full capture, profiles/traffic.json), per launch
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+            if tr:
+                roof["traffic"] = tr["dram_bytes_per_launch"]
+                roof["traffic_note"] = (f"{tr['kernel']}: algorithmic {tr['algorithmic_bytes_per_launch']} B per launch in that "
+                                        f"capture; {tr['source']}")
+        except Exception:
+            pass
+        return roof
 
-    # measured DRAM traffic of the dominant class's main kernel (one ncu --set full capture, profiles/traffic.json)
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(roof["kernel"])
-        if tr:
-            roof["traffic"] = tr["dram_bytes_per_launch"]
-            roof["traffic_note"] = f"{tr['kernel']}: algorithmic {tr['algorithmic_bytes_per_launch']} B per launch; {tr['source']}"
-    except Exception:
-        pass
+    def build_workload(name, dropout=0.0):
+        w = settings(args, name)
+        c = Ctx()
+        c.name, c.w = name, w
+        c.cfg, c.theta, c.x = make_data(name, w["rows"], rank)
+        c.B, c.loss, c.rows = w["batch"], w["loss"], w["rows"]
+        torch.manual_seed(0)
+        c.net = fb.build_nsf(c.theta[:8192], c.x[:8192], hidden_features=c.cfg.hidden, num_transforms=c.cfg.transforms,
+                             num_bins=c.cfg.bins, num_blocks=c.cfg.blocks, dropout_probability=dropout,
+                             generator=torch.Generator().manual_seed(0)).to(dev)
+        if world > 1:
+            dist.broadcast(c.net._flat.data, src=0)
+        c.net.train()
+        c.prior = fb.BoxUniform(-3 * torch.ones(c.cfg.D), 3 * torch.ones(c.cfg.D), device=dev)
+        c.eng = _TrainEngine(c.net, c.prior, c.B, c.loss == "atomic", c.cfg.atoms, True, 5e-4, 5.0, use_graph=bool(args.graph))
+        c.theta_dev = c.theta.to(dev).contiguous()
+        c.x_dev = c.net._standardize(c.x.to(dev))
+        c.masks_dev = torch.zeros(c.rows, device=dev)
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        c.batches = [torch.randint(0, c.rows, (c.B,), device=dev, generator=g) for _ in range(8)]
+        c.step = lambda i: c.eng.step(c.batches[i % len(c.batches)], c.theta_dev, c.x_dev, c.masks_dev)
+        return c
 
-    # ---- extras: posterior sampling / log_prob throughput (sharded per GPU, no collective), MLE-mode training
+    def measure(c, k, w, with_clocks=False):
+        for i in range(w):
+            c.step(i)
+        clocks = ClockSampler(local) if with_clocks else None
+        if clocks:
+            clocks.start()
+        n0 = L.fp_launch_count()
+        ms = timed(c.step, k)
+        launches = int(L.fp_launch_count() - n0)
+        if c.eng.graph is not None:      # replays do not pass through the launch counter: kernels per captured step x k
+            launches = c.eng.launches_per_step * k
+        clk = clocks.stop() if clocks else None
+        c.eng.check_status()
+        value = world * c.B * k / (ms * 1e-3)
+
+        def plain(i):       # plain launches (a graph replay would bypass the per-launch event hooks)
+            c.eng.idx.copy_(c.batches[i % len(c.batches)])
+            c.eng._step_body(c.theta_dev, c.x_dev, c.masks_dev)
+
+        table = kernel_table(plain, min(k, 10))
+        return dict(value=value, ms_per_step=ms / k, launches=launches, clocks=clk, kernels=table, roofline=roofline_of(table))
+
+    # ============================================================ headline workload
+    t_start = time.time()
+    main_c = build_workload(args.config, args.dropout)
+    cfg = main_c.cfg
+    log(f"{args.config}: data + network ready after {time.time() - t_start:.1f} s")
+    res = measure(main_c, K, W, with_clocks=True)
+    log(f"{args.config}: {res['ms_per_step']:.3f} ms/step, {res['value']:.0f} pairs/s")
+    out_extra = {}
+
+    # ============================================================ e2e: the public call, host tensors in, estimator out
+    e2e = None
+    if not args.no_e2e:
+        B = main_c.B
+        n_steps_e2e = 8
+        n_rows = int(B * n_steps_e2e / 0.9) + 64
+        reps = (n_rows + main_c.rows - 1) // main_c.rows
+        th_host = main_c.theta.repeat(reps, 1)[:n_rows].contiguous().pin_memory()
+        x_host = main_c.x.repeat(reps, 1)[:n_rows].contiguous().pin_memory()
+        builder = fb.posterior_nn(model="nsf", hidden_features=cfg.hidden, num_transforms=cfg.transforms, num_bins=cfg.bins,
+                                  num_blocks=cfg.blocks, dropout_probability=args.dropout)
+        inf = fb.SNPE_C(main_c.prior, density_estimator=builder, device=str(dev))
+        atomic = main_c.loss == "atomic"
+        if atomic:      # a later round (proposal != prior) is what selects the APT loss in SNPE_C.train
+            inf.append_simulations(th_host, x_host, proposal=object())
+        else:
+            inf.append_simulations(th_host, x_host)
+        kw = dict(training_batch_size=B, num_atoms=cfg.atoms, use_combined_loss=True, stop_after_epochs=1000,
+                  force_first_round_loss=not atomic, use_cuda_graph=False, seed=0)
+        inf.train(max_num_epochs=0, **kw)                    # builds the estimator (z-score statistics, initial weights) + warm-up epoch
+        del main_c.eng
+        torch.cuda.empty_cache()
+        epochs = 2
+        barrier()
+        t0 = time.perf_counter()
+        est = inf.train(max_num_epochs=epochs - 1, **kw)     # epochs 0 .. epochs-1
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tsec = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+        n_train = int(0.9 * n_rows) // world
+        steps_run = epochs * (n_train // B)
+        h2d = (th_host.numel() + x_host.numel() + n_rows) * 4 // max(world, 1)
+        e2e = {"value": world * steps_run * B / float(tsec.item()), "unit": "pairs/s",
+               "h2d_bytes_per_step": int(h2d / max(steps_run, 1)), "d2h_bytes_per_step": int(16 * epochs / max(steps_run, 1)) + 1,
+               "call": f"SNPE_C.append_simulations(pinned host tensors, {n_rows} rows) + SNPE_C.train(max_num_epochs={epochs - 1}): "
+                       f"dataset upload, {steps_run} optimiser steps, {epochs} validation passes, best-state snapshots, returned "
+                       f"deepcopy; wall clock {float(tsec.item()):.3f} s (max over ranks)",
+               "final_validation_log_prob": inf._summary["validation_log_probs"][-1]}
+        log(f"e2e: {e2e['value']:.0f} pairs/s through SNPE_C.train ({steps_run} steps in {float(tsec.item()):.2f} s)")
+        del inf, est, th_host, x_host
+    ws_gb = main_c.net.workspace_floats(main_c.B * (cfg.atoms if main_c.loss == "atomic" else 1), main_c.B, True) * 4 / 1e9
+    main_desc = workload_desc(args.config, cfg, main_c.loss, main_c.B, main_c.rows, world, args.dropout)
+    out_extra["activation_workspace_gb_per_step"] = ws_gb
+    theta_cpu, x_cpu = main_c.theta, main_c.x
+    del main_c
+    torch.cuda.empty_cache()
+
+    # ============================================================ configs[4]: samples/s and log_prob/s from a trained c2 flow
     if not args.no_extras:
-        net.eval()
-        post = fb.DirectPosterior(net, prior).set_default_x(x[:1])
-        n_draw = 1 << 20
-        ctx_std = net._standardize(x[:1].to(dev))
-        z = torch.randn(n_draw, cfg.D, device=dev)
-        for _ in range(2):
-            net.inverse_rows(z, ctx_std)
-        ms_s = timed(lambda i: net.inverse_rows(z, ctx_std), 5)
-        out_extra["posterior_draws_per_s"] = world * n_draw * 5 / (ms_s * 1e-3)
-        th_q = theta_dev[torch.randint(0, args.rows, (n_draw,), device=dev)]
-        x1 = x[:1].to(dev)
+        t1 = time.time()
+        c2 = build_workload("c2")
+        for i in range(150):             # a short, seeded training run: the same flow (rank 0's) at every N
+            c2.step(i)
+        if world > 1:
+            dist.broadcast(c2.net._flat.data, src=0)
+        net = c2.net.eval()
+        post = fb.DirectPosterior(net, c2.prior, max_sampling_batch_size=1 << 22).set_default_x(c2.x[:1])
+        n_total = 1 << 24
+        lo, hi = fdist.shard_rows(n_total) if world > 1 else (0, n_total)
+        post.sample((1 << 16,))
+        acc = post.leakage_correction(c2.x[:1], num_rejection_samples=1 << 18)
+        ms_s = timed(lambda i: post.sample((hi - lo,)), 1)
+        out_extra["posterior_samples_per_s"] = n_total / (ms_s * 1e-3)
+        out_extra["posterior_acceptance_rate"] = acc
+        out_extra["posterior_raw_draws_per_s"] = n_total / max(acc, 1e-9) / (ms_s * 1e-3)
+        th_q = post.sample((1 << 21,))
+        ms_l = timed(lambda i: post.log_prob(th_q, norm_posterior=False), 8)
+        out_extra["log_prob_per_s"] = world * th_q.shape[0] * 8 / (ms_l * 1e-3)
+        out_extra["sampling_workload"] = (f"c2 flow after 150 seeded optimiser steps (rank 0's weights broadcast), {n_total} accepted "
+                                          f"samples sharded over {world} rank(s), posterior.sample / posterior.log_prob "
+                                          "(floppity.py:252, floppityFUN.py:35), no collective on the data path")
+        log(f"c5: {out_extra['posterior_samples_per_s']:.3g} accepted samples/s (acceptance {acc:.3f}), "
+            f"{out_extra['log_prob_per_s']:.3g} log_prob/s  [{time.time() - t1:.1f} s]")
+        del post, th_q
+        # ======================================================== extras: the other configs, each with its own roofline
+        extras = {}
+        if world == 1:
+            c2.net.train()
+            r2 = measure(c2, max(K // 2, 5), 3)
+            extras["c2"] = dict(config=workload_desc("c2", c2.cfg, c2.loss, c2.B, c2.rows, world, 0.0), **r2)
+            del c2
+            torch.cuda.empty_cache()
+            for name, drop in (("c1", 0.0), ("c4", 0.0), ("c2", 0.1), ("c1", 0.1)):
+                c = build_workload(name, drop)
+                r = measure(c, max(K // 2, 5), 3)
+                key = name if drop == 0.0 else f"{name}_dropout{drop}"
+                extras[key] = dict(config=workload_desc(name, c.cfg, c.loss, c.B, c.rows, world, drop), **r)
+                log(f"{key}: {r['ms_per_step']:.3f} ms/step, {r['value']:.0f} pairs/s")
+                del c
+                torch.cuda.empty_cache()
+            for k, v in extras.items():
+                v.pop("clocks", None)
+            out_extra["extras"] = extras
+        else:
+            del c2
 
-        def lp_eval(i):
-            with torch.no_grad():       # posterior.log_prob (floppityFUN.py:35): no gradient, rows chunked by the flow
-                net.log_prob(th_q, x1)
-
-        for _ in range(2):
-            lp_eval(0)
-        ms_l = timed(lp_eval, 5)
-        out_extra["log_prob_per_s"] = world * n_draw * 5 / (ms_l * 1e-3)
-        net.train()
-        eng2 = _TrainEngine(net, prior, B, not atomic, cfg.atoms, True, 5e-4, 5.0, use_graph=False)
-        for i in range(3):
-            eng2.step(batches[i], theta_dev, x_dev, masks_dev)
-        ms2 = timed(lambda i: eng2.step(batches[i % 8], theta_dev, x_dev, masks_dev), K)
-        out_extra["train_pairs_per_s_" + ("mle" if atomic else "atomic")] = world * B * K / (ms2 * 1e-3)
-        if atomic:
-            # the same MLE loss at the row count the atomic step works on (B x atoms flow rows): the launch-bound small
-            # step above is a property of the batch size, not of the loss
-            Bb = B * cfg.atoms
-            del eng2
-            eng3 = _TrainEngine(net, prior, Bb, False, cfg.atoms, True, 5e-4, 5.0, use_graph=False)
-            big = [torch.randint(0, args.rows, (Bb,), device=dev, generator=g) for _ in range(2)]
-            for i in range(3):
-                eng3.step(big[i % 2], theta_dev, x_dev, masks_dev)
-            ms3 = timed(lambda i: eng3.step(big[i % 2], theta_dev, x_dev, masks_dev), max(K // 2, 2))
-            out_extra["train_pairs_per_s_mle_batch_x_atoms"] = world * Bb * max(K // 2, 2) / (ms3 * 1e-3)
-            del eng3
-
-    # ---- CPU baseline beside it (rank 0, N == 1 only): the oracle on the host cores, bounded sample
+    # ============================================================ CPU baseline beside it (rank 0, N == 1 only)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import nsf_oracle as O
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        onet = O.build_nsf(theta[:2048], x[:2048], hidden_features=cfg.hidden, num_transforms=cfg.transforms,
-                           num_bins=cfg.bins, num_blocks=cfg.blocks)
-        oprior = O.BoxUniform(-3 * torch.ones(cfg.D), 3 * torch.ones(cfg.D))
-        opt = torch.optim.Adam(onet.parameters(), lr=5e-4)
-        Bc, nsteps = args.ref_batch, 0
-        t_end = time.perf_counter() + 12.0
-        t0 = None
-        while True:
-            idx = torch.randint(0, 2048, (Bc,))
-            opt.zero_grad()
-            lp = (O.log_prob_proposal_posterior_atomic(onet, oprior, theta[idx], x[idx], torch.zeros(Bc, 1), cfg.atoms, True)
-                  if atomic else onet.log_prob(theta[idx], x[idx]))
-            (-lp.mean()).backward()
-            torch.nn.utils.clip_grad_norm_(onet.parameters(), 5.0)
-            opt.step()
-            if t0 is None:
-                t0 = time.perf_counter()       # first step is warm-up
-                continue
-            nsteps += 1
-            if time.perf_counter() > t_end and nsteps >= 2:
-                break
-        dt = time.perf_counter() - t0
-        cpu_base = {"value": Bc * nsteps / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                    "sample": f"{nsteps} optimiser steps at batch {Bc} (bounded sample), {args.loss} loss, oracle/nsf_oracle.py eager fp32"}
+        w = settings(args, args.config)
+        Bc = ref_batch_for(args, cfg)
+        v, n, dt = oracle_steps(cfg, w["loss"], Bc, theta_cpu[:4096], x_cpu[:4096], 1, seconds=12.0, dropout=args.dropout)
+        cpu_base = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                    "sample": f"{n} optimiser steps at batch {Bc} in {dt:.1f} s (a bounded sample of the per-GPU batch {w['batch']}), "
+                              f"{w['loss']} loss, oracle/nsf_oracle.py eager fp32"}
 
     if rank == 0:
-        ws_gb = net.workspace_floats(eng.R, B, True) * 4 / 1e9
         line = {
-            "metric": "NSF train pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"{args.config}: SNPE-C NSF T{cfg.transforms} K{cfg.bins} H{cfg.hidden} Bk{cfg.blocks}, "
-                                   f"{cfg.D} params / {cfg.C} bins, atoms {cfg.atoms} "
-                                   f"(BASELINE.json configs[{['c1', 'c2', 'c3', 'c4'].index(args.config)}])",
-                       "loss": args.loss, "per_gpu_batch": B, "global_batch": B * world, "flow_rows_per_step": eng.R * world,
-                       "resident_rows_per_gpu": args.rows, "parallelism": f"dp{world}",
-                       "l2": f"no flush: per-step activation workspace {ws_gb:.2f} GB >> 126 MB L2"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu_base,
-            "kernel_classes": classes, "final_loss": losses[-1] if losses else None,
+            "metric": "NSF train pairs/s", "value": res["value"], "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": main_desc, "e2e": e2e, "gpu_launches": res["launches"], "clocks": res["clocks"],
+            "roofline": res["roofline"], "cpu_baseline": cpu_base, "kernels": res["kernels"],
         }
         line.update(out_extra)
         sys.stdout.flush()

@@ -198,7 +198,9 @@ class _TrainEngine:
             self.emb.backward_raw(self.x_b, self._emb_saved[1], self.d_ctx, self.emb_grads)
         scale = 1.0
         if self.world > 1:
+            torch.cuda.nvtx.range_push("fp.allreduce")
             fdist.allreduce_sum_(self.grads[:n])
+            torch.cuda.nvtx.range_pop()
             if self.emb is not None:
                 fdist.allreduce_sum_(self.emb_grads)
             scale = 1.0 / self.world
@@ -217,9 +219,16 @@ class _TrainEngine:
 
     # -- public -------------------------------------------------------------------------------------------
     def _step_body(self, theta_all, x_all, masks_all):
+        nvtx = torch.cuda.nvtx
+        nvtx.range_push("fp.gather")
         self._gather(theta_all, x_all, masks_all)
+        nvtx.range_pop()
+        nvtx.range_push("fp.forward+loss")
         self._forward(training=True)
+        nvtx.range_pop()
+        nvtx.range_push("fp.backward+allreduce+clip+adam")
         self._backward_update()
+        nvtx.range_pop()
 
     def step(self, idx: Tensor, theta_all: Tensor, x_all: Tensor, masks_all: Optional[Tensor]):
         """One optimiser step on the rows ``idx`` of the resident dataset."""
@@ -314,7 +323,7 @@ class SNPE_C:
             ok = _valid_rows(x)
             if (~ok).any():
                 warnings.warn(f"Found {int((~ok).sum())} NaN/Inf simulations; they are excluded from training.")
-            theta, x = theta[ok], x[ok]
+                theta, x = theta[ok], x[ok]
         elif not _valid_rows(x).all():
             raise ValueError("multi-round SNPE-C cannot drop NaN/Inf simulations; remove them before appending")
         masks = torch.ones(theta.shape[0], 1) if current_round == 0 else torch.zeros(theta.shape[0], 1)
@@ -327,6 +336,9 @@ class SNPE_C:
 
     def get_simulations(self, starting_round: int = 0):
         idx = [i for i, r in enumerate(self._data_round_index) if r >= starting_round]
+        if len(idx) == 1:        # one round: hand the stored tensors over as they are (no host copy of a multi-GB dataset)
+            i = idx[0]
+            return self._theta_roundwise[i], self._x_roundwise[i], self._prior_masks[i]
         return (torch.cat([self._theta_roundwise[i] for i in idx]), torch.cat([self._x_roundwise[i] for i in idx]),
                 torch.cat([self._prior_masks[i] for i in idx]))
 
@@ -384,9 +396,17 @@ class SNPE_C:
         my_train = fdist.shard_indices(train_idx) if world > 1 else train_idx
         my_val = fdist.shard_indices(val_idx) if world > 1 else val_idx
         used = torch.cat([my_train, my_val])
-        theta_dev = theta[used].to(dev).contiguous()
-        x_dev = net._standardize(x[used].to(dev))
-        masks_dev = masks[used].reshape(-1).to(dev).contiguous()
+        if world == 1:
+            # the whole dataset goes up in one copy (asynchronous when the caller's tensors are pinned) and the split is
+            # gathered on the device: no host-side gather of a multi-GB array
+            used_dev = used.to(dev)
+            theta_dev = theta.to(dev, non_blocking=True)[used_dev].contiguous()
+            x_dev = net._standardize(x.to(dev, non_blocking=True)[used_dev])
+            masks_dev = masks.reshape(-1).to(dev, non_blocking=True)[used_dev].contiguous()
+        else:                    # data-parallel: only this rank's shard crosses the bus
+            theta_dev = theta[used].to(dev).contiguous()
+            x_dev = net._standardize(x[used].to(dev))
+            masks_dev = masks[used].reshape(-1).to(dev).contiguous()
         nt, nv = my_train.numel(), my_val.numel()
         B = int(min(training_batch_size, nt))
         Bv = int(min(training_batch_size, nv)) if nv > 0 else 0
