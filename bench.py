@@ -465,8 +465,14 @@ def main():
     if not args.no_extras:
         t1 = time.time()
         c2 = build_workload("c2")
-        for i in range(150):             # a short, seeded training run: the same flow (rank 0's) at every N
-            c2.step(i)
+        # a short, seeded training run with the round-0 loss (maximum likelihood, what floppity.py:220 runs): the same
+        # flow -- rank 0's -- at every N, so accepted samples/s are comparable across N
+        pre = _TrainEngine(c2.net, c2.prior, 4096, False, c2.cfg.atoms, True, 2e-3, 5.0)
+        gp = torch.Generator(device=dev).manual_seed(99)
+        for i in range(400):
+            pre.step(torch.randint(0, c2.rows, (4096,), device=dev, generator=gp), c2.theta_dev, c2.x_dev, c2.masks_dev)
+        pre.check_status()
+        del pre
         if world > 1:
             dist.broadcast(c2.net._flat.data, src=0)
         net = c2.net.eval()
@@ -482,7 +488,7 @@ def main():
         th_q = post.sample((1 << 21,))
         ms_l = timed(lambda i: post.log_prob(th_q, norm_posterior=False), 8)
         out_extra["log_prob_per_s"] = world * th_q.shape[0] * 8 / (ms_l * 1e-3)
-        out_extra["sampling_workload"] = (f"c2 flow after 150 seeded optimiser steps (rank 0's weights broadcast), {n_total} accepted "
+        out_extra["sampling_workload"] = (f"c2 flow after 400 seeded maximum-likelihood steps (rank 0's weights broadcast), {n_total} accepted "
                                           f"samples sharded over {world} rank(s), posterior.sample / posterior.log_prob "
                                           "(floppity.py:252, floppityFUN.py:35), no collective on the data path")
         log(f"c5: {out_extra['posterior_samples_per_s']:.3g} accepted samples/s (acceptance {acc:.3f}), "

@@ -11,11 +11,11 @@ from . import _lib
 from .flow import NSFFlow, build_nsf, posterior_nn
 from .inference import BoxUniform, DirectPosterior, SNPE_C
 from .density_estimator import NSFDensityEstimator
-from .embedding import FCEmbedding, EmbeddedNSF
+from .embedding import CNNEmbedding, FCEmbedding, EmbeddedNSF
 from . import utils, synthetic, dist, retrieval
 
 __all__ = ["NSFFlow", "build_nsf", "posterior_nn", "BoxUniform", "DirectPosterior", "SNPE_C",
-           "NSFDensityEstimator", "FCEmbedding", "EmbeddedNSF", "utils", "synthetic", "dist", "retrieval", "build"]
+           "NSFDensityEstimator", "FCEmbedding", "CNNEmbedding", "EmbeddedNSF", "utils", "synthetic", "dist", "retrieval", "build"]
 
 
 def build(verbose: bool = False) -> str:

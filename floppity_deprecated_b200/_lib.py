@@ -98,6 +98,9 @@ SIGNATURES = {
     "fp_gauss_loglik": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P]),
     "fp_relu": (c_int32, [_P, _P, c_int64, _P]),
     "fp_relu_bwd": (c_int32, [_P, _P, _P, c_int64, _P]),
+    "fp_conv1d_relu_pool_fwd": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P]),
+    "fp_conv1d_relu_pool_bwd": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                          c_int32, _P]),
     "fp_nsf_ctx_backward": (c_int32, [_CFG, _P, c_int64, c_int64, _P, _P, _P]),
     "fp_launch_count": (c_int64, []),
     "fp_prof_enable": (c_int32, [c_int32]),

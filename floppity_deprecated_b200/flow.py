@@ -461,13 +461,20 @@ def build_nsf(batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score
               use_batch_norm: bool = False, generator: Optional[torch.Generator] = None, **kwargs) -> NSFFlow:
     """sbi ``build_nsf`` (sbi naming: ``batch_x`` is theta, ``batch_y`` the spectrum).  Statistics for the two
     z-scorings come from the given batches exactly as upstream (unbiased std, clamp 1e-14 / 1e-7)."""
-    from .embedding import EmbeddedNSF, FCEmbedding
+    from .embedding import CNNEmbedding, EmbeddedNSF, FCEmbedding, FrozenEmbedding
     emb = None
     if embedding_net is not None and not isinstance(embedding_net, nn.Identity):
-        if not isinstance(embedding_net, FCEmbedding):
-            raise NotImplementedError("only nn.Identity() and floppity_deprecated_b200.embedding.FCEmbedding (modules.py:25, "
-                                      "-embedding_type FC) are implemented; the CNN / multi embeddings are not")
-        emb = embedding_net
+        if isinstance(embedding_net, (FCEmbedding, CNNEmbedding)):        # -embedding_type FC / CNN (modules.py:25-33)
+            emb = embedding_net
+        elif isinstance(embedding_net, nn.Module) and not any(p.requires_grad and p.numel() for p in embedding_net.parameters()):
+            # no registered trainable parameters: a fixed feature map (the reference's multiNet, floppityFUN.py:93-134)
+            _y = torch.as_tensor(batch_y, dtype=torch.float32)
+            with torch.no_grad():
+                probe = embedding_net(_y[:2].reshape(2, -1))
+            emb = FrozenEmbedding(embedding_net, _y[0].numel(), probe.reshape(2, -1).shape[1])
+        else:
+            raise NotImplementedError("embedding nets with trainable parameters must be this package's FCEmbedding / CNNEmbedding "
+                                      "(modules.py:25-33): their backward passes are hand-written kernels, not autograd graphs")
     if use_batch_norm:
         raise NotImplementedError("use_batch_norm=True is not on the FlopPITy path")
     batch_x = torch.as_tensor(batch_x, dtype=torch.float32)

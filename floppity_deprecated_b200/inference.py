@@ -85,6 +85,7 @@ class _TrainEngine:
         # an embedding net in front of the flow (modules.py:21-45, -embedding FC) is trained jointly: its forward runs
         # before the flow's, its backward after, and both parameter sets share one clip norm and one Adam step count
         self.emb = getattr(net, "embedding", None)
+        self.emb_trainable = self.emb is not None and self.emb.param_count > 0
         self.x_dim = net.C                           # width of the (standardised) observation rows
         if self.emb is not None:
             net = net.flow
@@ -110,7 +111,7 @@ class _TrainEngine:
         self.theta_b = torch.empty(self.B, net.D, **f32)
         self.x_b = torch.empty(self.B, self.x_dim, **f32)
         if self.emb is not None:
-            self.emb_grads = torch.zeros(self.emb.param_count, **f32)
+            self.emb_grads = torch.zeros(max(self.emb.param_count, 4), **f32)
             self.emb_m = torch.zeros(self.emb.param_count, **f32)
             self.emb_v = torch.zeros(self.emb.param_count, **f32)
             self.d_ctx = torch.empty(self.B, net.C, **f32)
@@ -191,7 +192,7 @@ class _TrainEngine:
             _lib.ptr(net._theta_scale), _lib.ptr(self.d_logp), _lib.ptr(self.grads), None, _lib.ptr(self.ws),
             self.seed if c.dropout_p > 0 else 0, s), "logprob backward")
         _lib.check(L.fp_nsf_finish_grads(c, _lib.ptr(net._flat), _lib.ptr(self.prepared), _lib.ptr(self.grads), s), "finish grads")
-        if self.emb is not None:
+        if self.emb_trainable:
             self.emb_grads.zero_()
             _lib.check(L.fp_nsf_ctx_backward(c, _lib.ptr(net._flat), self.R, self.B, _lib.ptr(self.ws), _lib.ptr(self.d_ctx), s),
                        "ctx backward")
@@ -201,18 +202,18 @@ class _TrainEngine:
             torch.cuda.nvtx.range_push("fp.allreduce")
             fdist.allreduce_sum_(self.grads[:n])
             torch.cuda.nvtx.range_pop()
-            if self.emb is not None:
+            if self.emb_trainable:
                 fdist.allreduce_sum_(self.emb_grads)
             scale = 1.0 / self.world
         # clip_grad_norm_ over ALL parameters (flow + embedding): both buffers feed one sum of squares
         _lib.check(L.fp_grad_sumsq(_lib.ptr(self.grads), n, _lib.ptr(self.sumsq), s), "sumsq")
-        if self.emb is not None:
+        if self.emb_trainable:
             _lib.check(L.fp_grad_sumsq(_lib.ptr(self.emb_grads), self.emb.param_count, _lib.ptr(self.sumsq), s), "sumsq emb")
         self.step_dev += 1
         _lib.check(L.fp_adam_step(_lib.ptr(net._flat), _lib.ptr(self.grads), _lib.ptr(self.m), _lib.ptr(self.v), n,
                                   self.lr, 0.9, 0.999, 1e-8, _lib.ptr(self.step_dev), self.clip, scale,
                                   _lib.ptr(self.sumsq), s), "adam")
-        if self.emb is not None:
+        if self.emb_trainable:
             _lib.check(L.fp_adam_step(_lib.ptr(self.emb._flat), _lib.ptr(self.emb_grads), _lib.ptr(self.emb_m),
                                       _lib.ptr(self.emb_v), self.emb.param_count, self.lr, 0.9, 0.999, 1e-8,
                                       _lib.ptr(self.step_dev), self.clip, scale, _lib.ptr(self.sumsq), s), "adam emb")
@@ -387,7 +388,7 @@ class SNPE_C:
             self._neural_net = self._build_neural_net(theta[train_idx], x[train_idx]).to(dev)
             if world > 1:
                 fdist.broadcast_(self._neural_net._flat.data)
-                if getattr(self._neural_net, "embedding", None) is not None:
+                if getattr(self._neural_net, "embedding", None) is not None and self._neural_net.embedding.param_count > 0:
                     fdist.broadcast_(self._neural_net.embedding._flat.data)
         net = self._neural_net
         net.train()

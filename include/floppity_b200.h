@@ -243,6 +243,19 @@ int fp_gauss_loglik(const double* obs, const double* err, const double* x, doubl
 int fp_relu(const float* x, float* out, int64_t n, void* stream);
 int fp_relu_bwd(const float* d, const float* z, float* out, int64_t n, void* stream);
 
+/* ---- convolutional embedding net in front of the flow: sbi CNNEmbedding's cnn_subnet, built by
+ * createEmbedding at /root/reference/modules.py:26-33 for -embedding_type CNN (the default type, floppity.py:46).
+ * One layer = Conv1d(stride 1, zero padding `pad`) -> ReLU -> MaxPool1d(pool):
+ *   x [B, Cin, L], w [Cout, Cin, k], b [Cout] -> z [B, Cout, Lc] pre-activation (Lc = L + 2 pad - k + 1, kept for the
+ *   backward), y [B, Cout, Lc / pool].
+ * Backward: dy [B, Cout, Lc / pool] -> dz [B, Cout, Lc] (scratch, overwritten), dx [B, Cin, L] (overwritten; NULL for the
+ * first layer), dw / db ACCUMULATED.  Limits: Cout*Cin*k <= 4096, Cin*k <= 64 (FP_E_TOOLARGE beyond). */
+int fp_conv1d_relu_pool_fwd(const float* x, const float* w, const float* b, float* z, float* y, int64_t B, int32_t Cin, int32_t L,
+                            int32_t Cout, int32_t k, int32_t pad, int32_t pool, void* stream);
+int fp_conv1d_relu_pool_bwd(const float* x, const float* w, const float* z, const float* dy, float* dz, float* dx, float* dw,
+                            float* db, int64_t B, int32_t Cin, int32_t L, int32_t Cout, int32_t k, int32_t pad, int32_t pool,
+                            void* stream);
+
 int fp_within_box(const float* theta, const float* low, const float* high, uint8_t* inside, int64_t R, int32_t D, void* stream);
 
 /* ---- launch accounting (bench.py: gpu_launches and the live per-kernel roofline numbers) -----------------------

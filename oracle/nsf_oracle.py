@@ -532,6 +532,59 @@ class FCEmbedding(nn.Module):
         return self.net(x)
 
 
+def calculate_filter_output_size(input_size, padding, dilation, kernel, stride) -> int:
+    """[UPSTREAM-RECALL sbi 0.22 embedding_nets.cnn]"""
+    return int((int(input_size) + 2 * int(padding) - int(dilation) * (int(kernel) - 1) - 1) / int(stride) + 1)
+
+
+class CNNEmbedding(nn.Module):
+    """[UPSTREAM-RECALL sbi 0.22 ``sbi.neural_nets.embedding_nets.CNNEmbedding``, 1-D case] as FlopPITy builds it at
+    /root/reference/modules.py:29-33 (-embedding_type CNN) and floppityFUN.py:117-125 (multiNet): num_conv_layers x
+    [Conv1d(stride 1, padding 1), ReLU, MaxPool1d(pool_kernel_size)] on the input viewed as ONE channel, flattened into
+    ``FCEmbedding(out_channels[-1] * length, output_dim, num_linear_layers, num_linear_units)``."""
+
+    def __init__(self, input_shape, in_channels=1, out_channels_per_layer=(6, 12), num_conv_layers=2, num_linear_layers=2,
+                 num_linear_units=50, output_dim=20, kernel_size=5, pool_kernel_size=2):
+        super().__init__()
+        assert len(input_shape) == 1, "1-D spectra on the FlopPITy path"
+        assert len(out_channels_per_layer) == num_conv_layers
+        self.input_shape = tuple(input_shape)
+        stride, padding = 1, 1
+        layers, size = [], int(input_shape[0])
+        for ii in range(num_conv_layers):
+            layers += [nn.Conv1d(in_channels if ii == 0 else out_channels_per_layer[ii - 1], out_channels_per_layer[ii],
+                                 kernel_size=kernel_size, stride=stride, padding=padding),
+                       nn.ReLU(inplace=True), nn.MaxPool1d(kernel_size=pool_kernel_size)]
+            size = calculate_filter_output_size(size, padding, 1, kernel_size, stride)
+            size = calculate_filter_output_size(size, 0, 1, pool_kernel_size, pool_kernel_size)
+        self.cnn_subnet = nn.Sequential(*layers)
+        self.linear_subnet = FCEmbedding(input_dim=out_channels_per_layer[-1] * size, output_dim=output_dim,
+                                         num_layers=num_linear_layers, num_hiddens=num_linear_units)
+
+    def forward(self, x: Tensor) -> Tensor:
+        batch_size = x.size(0)
+        x = self.cnn_subnet(x.view(batch_size, 1, *self.input_shape))
+        return self.linear_subnet(x.view(batch_size, -1))
+
+
+class MultiNet(nn.Module):
+    """Restatement of the reference's own ``multiNet`` (/root/reference/floppityFUN.py:93-134): one CNNEmbedding per
+    observation on consecutive column slices, outputs concatenated.  As in the reference the sub-nets sit in a plain list:
+    their parameters are NOT registered (never trained, not part of the state_dict)."""
+
+    def __init__(self, nwvl, make_net):
+        super().__init__()
+        self.nwvl = [int(n) for n in nwvl]
+        self.nets = [make_net(i, n) for i, n in enumerate(self.nwvl)]
+
+    def forward(self, X: Tensor) -> Tensor:
+        out, o = [], 0
+        for n, net in zip(self.nwvl, self.nets):
+            out.append(net(X[:, o:o + n]))
+            o += n
+        return torch.cat(out, dim=1)
+
+
 def build_nsf(batch_x: Tensor, batch_y: Tensor, z_score_x="independent", z_score_y="independent",
               hidden_features=50, num_transforms=5, num_bins=10, embedding_net: nn.Module = None,
               tail_bound=3.0, hidden_layers_spline_context=1, num_blocks=2, dropout_probability=0.0,

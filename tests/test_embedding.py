@@ -112,3 +112,143 @@ def test_snpe_c_trains_with_an_fc_embedding():
     assert lps[-1] > lps[0] + 0.5, lps            # it learns
     post = inf.build_posterior(est).set_default_x(torch.tensor(x[:1]))
     assert post.sample((1000,)).shape == (1000, 10)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# -embedding_type CNN (the reference's default type, floppity.py:46-47; modules.py:26-33) and -embedding_type multi
+# ---------------------------------------------------------------------------------------------------------------------
+CNN_KW = dict(out_channels_per_layer=[4, 8], num_conv_layers=2, num_linear_layers=2, num_linear_units=64, output_dim=E,
+              kernel_size=5)          # unroll_embed_hypers('2, 4, 2, 64, 5') -- floppity.py:47's default
+
+
+def _cnn_pair(seed=0, C=C, hidden=32, kw=CNN_KW):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    theta = torch.rand(256, D, generator=g) * 6 - 3
+    x = torch.randn(256, C, generator=g) * 2.0 + 0.5
+    hp = dict(HP, hidden_features=hidden)
+    onet = O.build_nsf(theta, x, embedding_net=O.CNNEmbedding(input_shape=(C,), **kw), **hp)
+    O.randomize_lu(onet, g, 0.1)
+    net = fb.build_nsf(theta, x, embedding_net=fb.CNNEmbedding(input_shape=(C,), **kw), **hp)
+    net.load_state_dict(onet.state_dict())
+    return onet, net, theta, x
+
+
+def test_cnn_embedding_has_upstream_shapes_and_checkpoint_keys():
+    onet, net, theta, x = _cnn_pair()
+    emb = net.embedding
+    assert isinstance(emb, fb.CNNEmbedding) and emb.input_dim == C and emb.output_dim == E
+    # (40 + 2 - 4) = 38 -> pool 19 -> (19 + 2 - 4) = 17 -> pool 8: 8 channels x 8 = 64 flattened features
+    assert emb.lengths == [40, 19, 8] and emb.core.input_dim == 64
+    want = {k: tuple(v.shape) for k, v in onet.state_dict().items() if not k.endswith("_log_z")}
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert got == want
+    sd = net.state_dict()
+    for k, v in onet.state_dict().items():
+        if not k.endswith("_log_z"):
+            assert torch.equal(sd[k].cpu().float(), v.float()), k
+    import pickle
+    net2 = pickle.loads(pickle.dumps(net))
+    assert torch.equal(net2.embedding._flat, net.embedding._flat)
+    with pytest.raises(NotImplementedError):
+        fb.CNNEmbedding(input_shape=(8, 8))
+    with pytest.raises(ValueError):
+        fb.CNNEmbedding(input_shape=(6,), out_channels_per_layer=[2, 2, 2], num_conv_layers=3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C_,pool", [(40, 2), (101, 3)])
+def test_conv_layer_kernels_match_torch(C_, pool):
+    """One Conv1d(padding 1) -> ReLU -> MaxPool1d layer, forward and all three gradients, against torch autograd."""
+    from floppity_deprecated_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(C_)
+    B, Cin, Cout, k = 37, 3, 5, 5
+    x = torch.randn(B, Cin, C_, generator=g)
+    conv = torch.nn.Conv1d(Cin, Cout, k, padding=1)
+    xr = x.clone().requires_grad_(True)
+    y = torch.nn.functional.max_pool1d(torch.relu(conv(xr)), pool)
+    dy = torch.randn(y.shape, generator=g)
+    (y * dy).sum().backward()
+    Lc = C_ + 2 - k + 1
+    xd, w, b = x.cuda(), conv.weight.detach().cuda().contiguous(), conv.bias.detach().cuda()
+    z = torch.empty(B, Cout, Lc, device="cuda"); yo = torch.empty(B, Cout, Lc // pool, device="cuda")
+    _lib.check(L.fp_conv1d_relu_pool_fwd(_lib.ptr(xd), _lib.ptr(w), _lib.ptr(b), _lib.ptr(z), _lib.ptr(yo), B, Cin, C_, Cout, k, 1,
+                                         pool, _lib.stream()), "fwd")
+    assert rel_err(yo.cpu().numpy(), y.detach().numpy()).max() < 1e-5
+    dz, dx = torch.empty_like(z), torch.empty_like(xd)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    _lib.check(L.fp_conv1d_relu_pool_bwd(_lib.ptr(xd), _lib.ptr(w), _lib.ptr(z), _lib.ptr(dy.cuda()), _lib.ptr(dz), _lib.ptr(dx),
+                                         _lib.ptr(dw), _lib.ptr(db), B, Cin, C_, Cout, k, 1, pool, _lib.stream()), "bwd")
+    assert rel_err(dx.cpu().numpy(), xr.grad.numpy()).max() < 1e-5
+    assert rel_err(dw.cpu().numpy(), conv.weight.grad.numpy()).max() < 1e-4
+    assert rel_err(db.cpu().numpy(), conv.bias.grad.numpy()).max() < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hidden", [32, 128])
+def test_cnn_embedded_log_prob_samples_and_joint_gradients(hidden):
+    from floppity_deprecated_b200.inference import _TrainEngine
+    onet, net, theta, x = _cnn_pair(3, hidden=hidden)
+    net, onet = net.cuda().eval(), onet.eval()
+    with torch.no_grad():
+        got = net.log_prob(theta[:100].cuda(), x[:100].cuda()).cpu().numpy()
+        want = onet.log_prob(theta[:100], x[:100]).numpy()
+    assert rel_err(got, want).max() < 1e-4, rel_err(got, want).max()
+    z = torch.randn(50, D, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        s = net.sample(50, context=x[:1].cuda(), noise=z.cuda())[0].cpu().numpy()
+        ws = onet.sample(50, context=x[:1], noise=z)[0].numpy()
+    assert rel_err(s, ws).max() < 1e-4
+    # one joint training step: gradients of the flow AND of every convolution / linear tensor of the embedding
+    net.train(); onet.train()
+    B = 128
+    prior = fb.BoxUniform(-3 * torch.ones(D), 3 * torch.ones(D), device="cuda")
+    eng = _TrainEngine(net, prior, B, False, 10, True, 5e-4, 5.0)
+    before = net.embedding._flat.detach().clone()
+    eng.step_on_batch(theta[:B].cuda(), net._standardize(x[:B].cuda()))
+    loss = -onet.log_prob(theta[:B], x[:B]).mean()
+    loss.backward()
+    assert abs(eng.loss_sum.item() / B - loss.item()) < 1e-4 * max(1.0, abs(loss.item()))
+    got_g = dict(net.flow.unpack(eng.grads[: net.flow.param_count]))
+    got_g.update({"_embedding_net.1." + k: v for k, v in net.embedding.unpack(eng.emb_grads).items()})
+    worst = 0.0
+    for k, p in onet.named_parameters():
+        assert k in got_g, k
+        worst = max(worst, float((got_g[k].cpu() - p.grad).abs().max()) / max(float(p.grad.abs().max()), 1e-4))
+    assert worst < 5e-4, worst          # (a max-pool arg-max or relu on a knife edge moves a whole term: no bookkeeping here)
+    assert float((net.embedding._flat.detach() - before).abs().max()) > 1e-5
+
+
+@pytest.mark.gpu
+def test_multi_embedding_is_a_fixed_feature_map_like_the_reference():
+    """-embedding_type multi (floppityFUN.py:93-134): the reference keeps its per-observation CNNEmbeddings in a plain list,
+    so they are never registered or trained.  Same here: evaluated as they stand, only the flow trains."""
+    g = torch.Generator().manual_seed(9)
+    torch.manual_seed(9)
+    nwvl = [24, 30]
+    theta = torch.rand(256, D, generator=g) * 6 - 3
+    x = torch.randn(256, sum(nwvl), generator=g)
+    kw = dict(out_channels_per_layer=[2, 4], num_conv_layers=2, num_linear_layers=2, num_linear_units=16, kernel_size=3)
+    omulti = O.MultiNet(nwvl, lambda i, n: O.CNNEmbedding(input_shape=(n,), output_dim=5 + i, **kw))
+    multi = O.MultiNet(nwvl, lambda i, n: fb.CNNEmbedding(input_shape=(n,), output_dim=5 + i, **kw))
+    for a, b in zip(multi.nets, omulti.nets):
+        a.load_state_dict(b.state_dict())
+    assert len(list(multi.parameters())) == 0                    # the reference's bug, reproduced: nothing registered
+    hp = dict(HP)
+    onet = O.build_nsf(theta, x, embedding_net=omulti, **hp)
+    net = fb.build_nsf(theta, x, embedding_net=multi, **hp)
+    assert net.flow.C == 11
+    net.load_state_dict(onet.state_dict())
+    net, onet = net.cuda().eval(), onet.eval()
+    with torch.no_grad():
+        got = net.log_prob(theta[:64].cuda(), x[:64].cuda()).cpu().numpy()
+        want = onet.log_prob(theta[:64], x[:64]).numpy()
+    assert rel_err(got, want).max() < 1e-4
+    prior = fb.BoxUniform(-3 * torch.ones(D), 3 * torch.ones(D), device="cuda")
+    inf = fb.SNPE_C(prior, lambda t, xx: net, device="cuda")
+    inf.append_simulations(theta, x)
+    frozen = [n._flat.detach().clone() for n in multi.nets]
+    inf.train(training_batch_size=64, max_num_epochs=2, stop_after_epochs=5)
+    assert all(torch.equal(a, n._flat.detach()) for a, n in zip(frozen, multi.nets))     # untouched, as upstream
+    assert len(inf._summary["validation_log_probs"]) == 3

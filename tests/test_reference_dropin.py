@@ -68,14 +68,28 @@ def test_reference_builders_run_against_this_package(ref_modules, tmp_path):
     inference_fc = M.density_builder("nsf", 5, 50, 8, fc, 2, 0.0, prior, "cpu")
     net = inference_fc._build_neural_net(torch.rand(64, D) * 6 - 3, torch.randn(64, 100))
     assert isinstance(net, fb.EmbeddedNSF) and net.flow.C == 64
-    # the CNN branch cannot run from modules.py alone even upstream: it calls unroll_embed_hypers, which lives in
-    # floppityFUN.py and is never imported by modules.py (NameError at modules.py:28); through floppity.py's star
-    # imports it would reach this package's CNNEmbedding, which raises NotImplementedError
-    with pytest.raises((NameError, NotImplementedError)):
-        M.createEmbedding(True, "CNN", 64, "2, 4, 2, 64, 5", False, 100)
-    from floppity_deprecated_b200.embedding import CNNEmbedding
-    with pytest.raises(NotImplementedError):
-        CNNEmbedding(input_shape=(100,))
+    # the CNN branch cannot run from modules.py as shipped, even upstream: it calls unroll_embed_hypers, which lives in
+    # floppityFUN.py and is never imported by modules.py (NameError at modules.py:28)
+    with pytest.raises(NameError):
+        M.createEmbedding(True, "CNN", "64", "2, 4, 2, 64, 5", False, 100)
+    # with the one-line fix a maintainer would make (import the helper), it builds THIS package's CNNEmbedding with the
+    # reference's default hyper-parameters ('2, 4, 2, 64, 5': two conv layers of 4 and 8 channels, kernel 5, 2 x 64 linear)
+    import floppityFUN as FUN
+    M.unroll_embed_hypers = FUN.unroll_embed_hypers
+    try:
+        cnn = M.createEmbedding(True, "CNN", "64", "2, 4, 2, 64, 5", False, 100)
+    finally:
+        del M.unroll_embed_hypers
+    assert isinstance(cnn, fb.CNNEmbedding) and cnn.channels == [1, 4, 8] and cnn.kernel_size == 5 and cnn.output_dim == 64
+    assert cnn.lengths == [100, 49, 23] and cnn.core.shapes == [(64, 8 * 23), (64, 64)]
+    net_cnn = M.density_builder("nsf", 5, 50, 8, cnn, 2, 0.0, prior, "cpu")._build_neural_net(torch.rand(64, D) * 6 - 3,
+                                                                                          torch.randn(64, 100))
+    assert isinstance(net_cnn, fb.EmbeddedNSF) and net_cnn.flow.C == 64
+    # -embedding_type multi: the reference's own multiNet class over this package's CNNEmbedding -- its sub-nets sit in a
+    # plain list (floppityFUN.py:126-136), so nothing is registered: a fixed feature map
+    multi = FUN.multiNet([40, 60], input_shape=(100,), num_conv_layers=2, out_channels_per_layer=[4, 8], kernel_size=5,
+                         num_linear_layers=2, num_linear_units=64, output_dim=[8, 8])
+    assert len(multi.nets) == 2 and all(isinstance(n, fb.CNNEmbedding) for n in multi.nets) and not list(multi.parameters())
 
     theta0 = M.sample_proposal(0, None, 256, bounds, 3.0, "aintnothinhere", 0, 0)  # floppity.py:179, round 0: Sobol
     assert theta0.shape == (256, D) and np.abs(theta0).max() <= 3.0
