@@ -417,7 +417,9 @@ def main():
     if not args.no_e2e:
         B = main_c.B
         n_steps_e2e = 8
-        n_rows = int(B * n_steps_e2e / 0.9) + 64
+        # weak scaling: 8 optimiser steps per rank and epoch (every rank holds the whole host dataset and takes its shard,
+        # as SNPE_C.train does under data parallelism), capped at 6 GB of host rows per rank
+        n_rows = min(int(B * n_steps_e2e * world / 0.9) + 64, int(6e9 / (4 * (cfg.D + cfg.C + 1))))
         reps = (n_rows + main_c.rows - 1) // main_c.rows
         th_host = main_c.theta.repeat(reps, 1)[:n_rows].contiguous().pin_memory()
         x_host = main_c.x.repeat(reps, 1)[:n_rows].contiguous().pin_memory()
@@ -476,11 +478,12 @@ def main():
         if world > 1:
             dist.broadcast(c2.net._flat.data, src=0)
         net = c2.net.eval()
-        post = fb.DirectPosterior(net, c2.prior, max_sampling_batch_size=1 << 22).set_default_x(c2.x[:1])
+        x_obs = make_data("c2", 4096, 0)[2][:1]          # ONE observation for every rank (rank 0's data seed)
+        post = fb.DirectPosterior(net, c2.prior, max_sampling_batch_size=1 << 22).set_default_x(x_obs)
         n_total = 1 << 24
         lo, hi = fdist.shard_rows(n_total) if world > 1 else (0, n_total)
         post.sample((1 << 16,))
-        acc = post.leakage_correction(c2.x[:1], num_rejection_samples=1 << 18)
+        acc = post.leakage_correction(x_obs, num_rejection_samples=1 << 18)
         ms_s = timed(lambda i: post.sample((hi - lo,)), 1)
         out_extra["posterior_samples_per_s"] = n_total / (ms_s * 1e-3)
         out_extra["posterior_acceptance_rate"] = acc
