@@ -54,7 +54,7 @@ template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
              const __grid_constant__ CUtensorMap mapBl, const fp_gemm_args g, int nkb_total, int nchunks, int vec_all,
-             long long* trace) {
+             long long* trace, int dbg) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_a = smem_u32(smem);                                  // shared-space address of the ring
@@ -109,10 +109,10 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const uint32_t ph = (it / TC_STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* sb = smem + s * TC_STAGE_BYTES;
-          mbar_expect_tx(&full_raw[s], 3 * TC_TILE_BYTES);
+          mbar_expect_tx(&full_raw[s], ((dbg & 8) ? 2 : 3) * TC_TILE_BYTES);
           tma_load_2d(sb, &mapA, kb * TC_BK, (int)m0, &full_raw[s]);
           tma_load_2d(sb + 2 * TC_TILE_BYTES, &mapBh, kb * TC_BK, n0, &full_raw[s]);
-          tma_load_2d(sb + 3 * TC_TILE_BYTES, &mapBl, kb * TC_BK, n0, &full_raw[s]);
+          if (!(dbg & 8)) tma_load_2d(sb + 3 * TC_TILE_BYTES, &mapBl, kb * TC_BK, n0, &full_raw[s]);
           if (it < 60) FP_TRACE(it * 8 + 0);
         }
       }
@@ -147,7 +147,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
               umma_tf32(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
               umma_tf32(t_x, a_lo + adv, b_hi + adv, idesc, acc);
-              umma_tf32(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
+              if (!(dbg & 4)) umma_tf32(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
             }
             umma_commit(&empty[s]);        // ring slot reusable once these MMAs have read it
             if (it < 60) FP_TRACE(it * 8 + 4);
@@ -183,6 +183,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (tid_s == 0 && it < 60) FP_TRACE(it * 8 + 1);
         const uint32_t aA = smem_a + (uint32_t)(s * TC_STAGE_BYTES) + (uint32_t)tid_s * 16u;
         float4 v[TC_TILE_BYTES / 16 / 128];
+        if (!(dbg & 1)) {
 #pragma unroll
         for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) v[i] = lds128(aA + (uint32_t)i * 2048u);
 #pragma unroll
@@ -192,6 +193,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const float4 h = make_float4(tf32_round(w.x), tf32_round(w.y), tf32_round(w.z), tf32_round(w.w));
           sts128(aA + (uint32_t)i * 2048u, h);
           sts128(aA + (uint32_t)i * 2048u + TC_TILE_BYTES, make_float4(w.x - h.x, w.y - h.y, w.z - h.z, w.w - h.w));
+        }
         }
         fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -271,7 +273,8 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
           __syncwarp();
-          if (fast) {
+          if (dbg & 2) {
+          } else if (fast) {
             // straight-line code, four independent rows at a time (the epilogue warps are few, so instruction-level
             // parallelism across rows is what hides the MUFU / shared / global latencies)
             float4 o[4];
@@ -356,8 +359,8 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   constexpr uint32_t GROUP_BYTES = TN_BK * 128;   // one 32-float MN group: TN_BK k-rows x 128 B
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TN_STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    for (int s = 0; s < TN_STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], 8); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -435,12 +438,16 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         umma_commit(&acc_full[buf]);
       }
     }
-  } else if (warp < 6) {
-    // splitter: raw A at +0 -> hi in place, lo at +TILE; raw B at +2*TILE -> hi in place, lo at +3*TILE
-    const int tid_s = threadIdx.x - 64;
+  } else if (warp < 10) {
+    // splitter, eight warps (both operands are raw activations: twice the conversion work of the NT kernel's k-block; the
+    // epilogue runs once per output tile and makes do with four warps): raw A at +0 -> hi in place, lo at +TILE; raw B at
+    // +2*TILE -> hi in place, lo at +3*TILE.  Measured (tools/c3_gemm_ablate.py): ablating the conversion altogether makes
+    // the kernel 23..31 % faster, but doubling the converting warps from four to eight changes nothing -- what the
+    // conversion costs is its LATENCY inside the three-stage ring (TMA -> convert -> MMA -> free), not its throughput.
+    const int tid_s = threadIdx.x - 64;       // 0..255
     const bool relu_b = (g.flags & FP_G_RELU_B) != 0;
     // FP_G_COLSUM_A: the bias gradient colsum(A) rides along.  This thread's eight 16-byte chunks of the raw A tile
-    // are chunk (tid_s & 7) of k-row (tid_s >> 3) (+ 16 per further pass over the same group) of successive MN groups; the 32-byte-atom swizzle XORs the
+    // are chunk (tid_s & 7) of k-row (tid_s >> 3) of successive MN groups (one group per pass); the 32-byte-atom swizzle XORs the
     // 32-byte chunk index with (k-row & 3), which does not depend on i, so the chunk is the same four logical
     // columns for every i & 1 and every k-block: one float4 accumulator per MN group.
     const bool colsum = (g.flags & FP_G_COLSUM_A) != 0;
@@ -458,11 +465,12 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const uint32_t aA = smem_a + (uint32_t)(s * TN_STAGE_BYTES) + (uint32_t)tid_s * 16u;
         if (!(dbg & 1))
 #pragma unroll
-        for (int i = 0; i < TN_TILE_BYTES / 16 / 128; ++i) {
-          const uint32_t off = aA + (uint32_t)i * 2048u;
+        for (int i = 0; i < TN_TILE_BYTES / 16 / 256; ++i) {
+          const uint32_t off = aA + (uint32_t)i * 4096u;
           const float4 v = lds128(off);
           float4 u = lds128(off + 2 * TN_TILE_BYTES);
-          constexpr int IPG = (int)(GROUP_BYTES / 2048u);      // iterations per 32-float MN group
+          constexpr int IPG = (int)(GROUP_BYTES / 4096u);      // iterations per 32-float MN group
+          static_assert(IPG == 1, "one pass of the 256 splitter threads covers one 32-float MN group");
           cs[i / IPG].x += v.x; cs[i / IPG].y += v.y; cs[i / IPG].z += v.z; cs[i / IPG].w += v.w;
           const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
           sts128(off, h);
@@ -500,9 +508,8 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   } else {
     // epilogue: accumulate the partial tile into C with vector reductions (warp-private staging, full 128-byte
     // row segments per access -- same scheme as the NT kernel)
-    const int ew = warp - 6;
+    const int ew = warp - 10;                  // 0..3: one warp per TMEM lane quarter, both column halves in turn
     const int q = warp & 3;
-    const int half = ew >> 2;
     const uint32_t slabw = cs_a + (uint32_t)ew * (uint32_t)TC_CS_WARP_BYTES;
     const uint32_t st_base = slabw + (uint32_t)lane * 128u;
     const uint32_t sw_st = (uint32_t)(lane & 7);
@@ -516,9 +523,11 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const uint32_t aph = (tile_it >> 1) & 1u;
       mbar_wait(&acc_full[buf], aph);
       tcgen05_fence_after();
-      const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+      const uint32_t t_hh0 = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int chunk = 0; chunk < 2; ++chunk) {
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int half = c4 >> 1, chunk = c4 & 1;
+        const uint32_t t_hh = t_hh0 + (uint32_t)(half * 64);
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           float v[16], x[16];
@@ -530,7 +539,7 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                    make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
                                v[4 * j + 3] + x[4 * j + 3]));
         }
-        if (chunk == 1) {
+        if (c4 == 3) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -760,7 +769,7 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
       FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E)>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E)>, grid, stream, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace));       \
+    FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E)>, grid, stream, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg));       \
     break;                                                                                                            \
   }
   int epi = a->flags & FP_EPI_MASK;
