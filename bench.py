@@ -45,7 +45,8 @@ WORKLOADS = {
 CONFIG_INDEX = {"c1": 0, "c2": 1, "c3": 2, "c4": 3}
 # operand format of each tensor-core kernel: passes of the fp32-accurate split and the rate of one pass relative to bf16
 TENSOR_KERNELS = {"k_gemm_tc_nt": ("3xTF32", 6.0), "k_gemm_tc_tn": ("3xTF32", 6.0), "k_cond_fwd": ("3xFP16", 3.0),
-                  "k_cond_small_fwd": ("3xFP16 mma.sync", 3.0), "k_cond_small_bwd": ("3xFP16 mma.sync", 3.0)}
+                  "k_cond_small_fwd": ("3xFP16 mma.sync", 3.0), "k_cond_small_bwd": ("3xFP16 mma.sync", 3.0),
+                  "k_small_wgrad": ("3xFP16 mma.sync", 3.0)}
 
 
 def parse():

@@ -477,6 +477,239 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_bwd(const CsBwdPar
   }
 }
 
+// ---- all weight gradients of one coupling layer's conditioner in ONE launch ---------------------------------------
+// dW_j[M_j, N_j] += dOut_j[R, M_j]^T act_j[R, N_j] (relu on act_j where the forward applied one), db_j[M_j] += colsum(dOut_j)
+// for the 2 Bk + 2 linear layers of a hidden <= 64 ResidualNet.  As separate launches these were 5 tcgen05 calls whose
+// 128x128 tiles held a 50x50 result (39 us each, a ring hand-shake every 32 rows) plus an fp32 SIMT call for the 10-column
+// initial layer (77 us).  Here a CTA owns one (matrix, 64-row slab of it, range of batch rows): 64-row tiles of both
+// operands are converted to fp16 hi + scaled residual with ONE POWER-OF-TWO SCALE PER COLUMN (per output unit and per
+// input unit: the scales factor out of the contraction exactly), staged row-major in shared memory and read back
+// TRANSPOSED by ldmatrix.trans -- the contraction runs over the batch rows -- into warp-level m16n8k16 MMAs; every warp
+// keeps its 16 x 32 slice of the result in fp32 registers across all tiles and adds it to dW once at the end.
+constexpr int SW_MAXPAIRS = 12;
+struct SwPair {
+  const float* A; int32_t lda, M;            // dOut [R, M]
+  const float* B; int32_t ldb, N, relu_b;    // act [R, N], N <= 64
+  float* dW; int32_t ldw; float* db;         // dW [M, N] +=, db [M] += (may be NULL)
+};
+struct SwParams {
+  SwPair pair[SW_MAXPAIRS];
+  int32_t unit_pair[4 * SW_MAXPAIRS], unit_m0[4 * SW_MAXPAIRS];      // blockIdx.y -> (pair, first output row of its 64-row slab)
+  int64_t R; int32_t rows_per_cta;
+};
+constexpr int SW_TS = 72;                    // row stride (halves) of the staged tiles: 144 B, conflict-free for ldmatrix
+
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+
+__global__ void __launch_bounds__(256, 2) k_small_wgrad(const SwParams p) {
+  __shared__ __align__(16) uint16_t tA[2][64 * SW_TS], tB[2][64 * SW_TS];     // [hi | lo][row][col]
+  __shared__ int cmaxA[64], cmaxB[64];
+  __shared__ float unA[64], unB[64], scA[64], scB[64], dbs[64];
+  const SwPair& pr = p.pair[p.unit_pair[blockIdx.y]];
+  const int m0 = p.unit_m0[blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;                   // this warp's 16 output rows / 32 output columns
+  const int c4 = (tid & 15) * 4, rr = tid >> 4;              // staging: columns c4..c4+3 of rows rr + 16 j
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+  const int64_t r_end = min(p.R, r_begin + p.rows_per_cta);
+  if (r_begin >= r_end) return;
+  const float* A = pr.A; const float* B = pr.B;
+  const int lda = pr.lda, ldb = pr.ldb, M = pr.M, N = pr.N;
+  const bool relu_b = pr.relu_b != 0;
+  const bool a_vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((m0 & 3) == 0);
+  const bool b_vec = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+
+  float master[4][4], dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) master[nb][j] = 0.f;
+
+  float va[4][4], vb[4][4];
+  auto load_tile = [&](int64_t row0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = row0 + rr + 16 * j;
+      const bool rv = r < r_end;
+      const float* ap = A + r * lda + m0 + c4;
+      if (rv && a_vec && m0 + c4 + 3 < M) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(ap));
+        va[j][0] = v.x; va[j][1] = v.y; va[j][2] = v.z; va[j][3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) va[j][e] = (rv && m0 + c4 + e < M) ? __ldg(ap + e) : 0.f;
+      }
+      const float* bp = B + r * ldb + c4;
+      if (rv && b_vec && c4 + 3 < N) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(bp));
+        vb[j][0] = v.x; vb[j][1] = v.y; vb[j][2] = v.z; vb[j][3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) vb[j][e] = (rv && c4 + e < N) ? __ldg(bp + e) : 0.f;
+      }
+      if (relu_b) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) vb[j][e] = fmaxf(vb[j][e], 0.f);
+      }
+    }
+  };
+
+  load_tile(r_begin);
+  for (int64_t row0 = r_begin; row0 < r_end; row0 += 64) {
+    if (tid < 64) { cmaxA[tid] = 0; cmaxB[tid] = 0; }
+    __syncthreads();                                        // (also: the previous tile's MMAs are done with the staged tiles)
+    // ---- per-column maxima of this tile (non-negative floats order like their bit patterns)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float ma = 0.f, mb = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ma = fmaxf(ma, fabsf(va[j][e])); mb = fmaxf(mb, fabsf(vb[j][e])); dbacc[e] += va[j][e]; }
+      if (ma > 0.f) atomicMax(&cmaxA[c4 + e], __float_as_int(ma));
+      if (mb > 0.f) atomicMax(&cmaxB[c4 + e], __float_as_int(mb));
+    }
+    __syncthreads();
+    if (tid < 64) {
+      float sc, un;
+      row_scale(__int_as_float(cmaxA[tid]), sc, un); scA[tid] = sc; unA[tid] = un;
+      row_scale(__int_as_float(cmaxB[tid]), sc, un); scB[tid] = sc; unB[tid] = un;
+    }
+    __syncthreads();
+    // ---- convert and stage: [row][col] halves, hi and scaled residual
+    {
+      const float4 sa = *reinterpret_cast<const float4*>(&scA[c4]);
+      const float4 sb = *reinterpret_cast<const float4*>(&scB[c4]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = rr + 16 * j;
+        uint32_t h0, l0, h1, l1;
+        split_f16x2(va[j][0] * sa.x, va[j][1] * sa.y, h0, l0);
+        split_f16x2(va[j][2] * sa.z, va[j][3] * sa.w, h1, l1);
+        *reinterpret_cast<uint2*>(&tA[0][row * SW_TS + c4]) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(&tA[1][row * SW_TS + c4]) = make_uint2(l0, l1);
+        split_f16x2(vb[j][0] * sb.x, vb[j][1] * sb.y, h0, l0);
+        split_f16x2(vb[j][2] * sb.z, vb[j][3] * sb.w, h1, l1);
+        *reinterpret_cast<uint2*>(&tB[0][row * SW_TS + c4]) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(&tB[1][row * SW_TS + c4]) = make_uint2(l0, l1);
+      }
+    }
+    __syncthreads();
+    if (row0 + 64 < r_end) load_tile(row0 + 64);            // the next tile's global loads fly under this tile's MMAs
+    // ---- this warp's 16 x 32 slice: contraction over the tile's 64 batch rows
+    float hh[4][4], xx[4][4];
+    zero_acc(hh, xx);
+    const uint32_t a_hi = smem_u32(&tA[0][0]), a_lo = smem_u32(&tA[1][0]);
+    const uint32_t b_hi = smem_u32(&tB[0][0]), b_lo = smem_u32(&tB[1][0]);
+    // ldmatrix.trans lane addresses: matrices {k 0-7, k 8-15} x {col 0-7, col 8-15}
+    const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 4) << 3)) * SW_TS + mt * 16 + (((lane >> 3) & 1) << 3)) * 2u;
+    const uint32_t b_off = (uint32_t)(((lane & 7) + (((lane >> 3) & 1) << 3)) * SW_TS + nh * 32 + ((lane >> 4) << 3)) * 2u;
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      uint32_t ah[4], al[4];
+      const uint32_t ko = (uint32_t)(kb * 16 * SW_TS) * 2u;
+      // A fragment order: a0 (m 0-7, k 0-7), a1 (m 8-15, k 0-7), a2 (m 0-7, k 8-15), a3 (m 8-15, k 8-15)
+      ldsm4t(a_hi + ko + a_off, ah[0], ah[1], ah[2], ah[3]);
+      ldsm4t(a_lo + ko + a_off, al[0], al[1], al[2], al[3]);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bh0, bh1, bh2, bh3, bl0, bl1, bl2, bl3;      // {n-block 2np: k lo, k hi}, {n-block 2np+1: k lo, k hi}
+        ldsm4t(b_hi + ko + b_off + (uint32_t)(np * 16) * 2u, bh0, bh1, bh2, bh3);
+        ldsm4t(b_lo + ko + b_off + (uint32_t)(np * 16) * 2u, bl0, bl1, bl2, bl3);
+        mma16816(hh[2 * np], ah, bh0, bh1); mma16816(xx[2 * np], al, bh0, bh1); mma16816(xx[2 * np], ah, bl0, bl1);
+        mma16816(hh[2 * np + 1], ah, bh2, bh3); mma16816(xx[2 * np + 1], al, bh2, bh3); mma16816(xx[2 * np + 1], ah, bl2, bl3);
+      }
+    }
+    const float ua0 = unA[mt * 16 + g], ua1 = unA[mt * 16 + g + 8];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const float ub0 = unB[nh * 32 + nb * 8 + 2 * t], ub1 = unB[nh * 32 + nb * 8 + 2 * t + 1];
+      master[nb][0] += (hh[nb][0] + FP16_LO_UNSCALE * xx[nb][0]) * ua0 * ub0;
+      master[nb][1] += (hh[nb][1] + FP16_LO_UNSCALE * xx[nb][1]) * ua0 * ub1;
+      master[nb][2] += (hh[nb][2] + FP16_LO_UNSCALE * xx[nb][2]) * ua1 * ub0;
+      master[nb][3] += (hh[nb][3] + FP16_LO_UNSCALE * xx[nb][3]) * ua1 * ub1;
+    }
+  }
+  // ---- add this CTA's partial result
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb) {
+    const int n = nh * 32 + nb * 8 + 2 * t;
+    const int ma = m0 + mt * 16 + g, mb = ma + 8;
+    if (ma < M) {
+      if (n < N) red_add_f32(pr.dW + (int64_t)ma * pr.ldw + n, master[nb][0]);
+      if (n + 1 < N) red_add_f32(pr.dW + (int64_t)ma * pr.ldw + n + 1, master[nb][1]);
+    }
+    if (mb < M) {
+      if (n < N) red_add_f32(pr.dW + (int64_t)mb * pr.ldw + n, master[nb][2]);
+      if (n + 1 < N) red_add_f32(pr.dW + (int64_t)mb * pr.ldw + n + 1, master[nb][3]);
+    }
+  }
+  if (pr.db) {
+    __syncthreads();
+    if (tid < 64) dbs[tid] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) atomicAdd(&dbs[c4 + e], dbacc[e]);
+    __syncthreads();
+    if (tid < 64 && m0 + tid < M) red_add_f32(pr.db + m0 + tid, dbs[tid]);
+  }
+}
+
+// Host side: queue the pairs of a layer, then launch once.
+struct SmallWgradBatch {
+  SwParams p;
+  int npairs = 0, nunits = 0;
+  SmallWgradBatch() { p.R = 0; p.rows_per_cta = 0; }
+  bool add(const float* dOut, int ldo, int M, const float* act, int lda, int N, bool relu, float* dW, int ldw, float* db) {
+    if (npairs >= SW_MAXPAIRS || N > 64 || N < 1 || M < 1) return false;
+    const int units = (M + 63) / 64;
+    if (nunits + units > 4 * SW_MAXPAIRS) return false;
+    SwPair& q = p.pair[npairs];
+    q.A = dOut; q.lda = ldo; q.M = M; q.B = act; q.ldb = lda; q.N = N; q.relu_b = relu ? 1 : 0; q.dW = dW; q.ldw = ldw; q.db = db;
+    for (int u = 0; u < units; ++u) { p.unit_pair[nunits] = npairs; p.unit_m0[nunits] = u * 64; ++nunits; }
+    ++npairs;
+    return true;
+  }
+};
+
+int launch_small_wgrad(SmallWgradBatch& b, int64_t R, cudaStream_t stream) {
+  if (b.nunits == 0 || R <= 0) return 0;
+  // ~4 CTAs per SM in total, whole 64-row tiles per CTA
+  int64_t gx = std::max<int64_t>(1, (4 * (int64_t)num_sms() + b.nunits - 1) / b.nunits);
+  int64_t rows = ((R + gx - 1) / gx + 63) / 64 * 64;
+  rows = std::max<int64_t>(rows, 256);
+  gx = (R + rows - 1) / rows;
+  b.p.R = R; b.p.rows_per_cta = (int32_t)rows;
+  double flops = 0.0, bytes = 0.0;
+  for (int i = 0; i < b.npairs; ++i) {
+    flops += 2.0 * (double)R * b.p.pair[i].M * b.p.pair[i].N;
+    bytes += 4.0 * (double)R * (b.p.pair[i].M + (double)b.p.pair[i].N * ((b.p.pair[i].M + 63) / 64));
+  }
+  ProfScope ps(TAG_SMALL_WGRAD, flops, stream, bytes);
+  dim3 grid((unsigned)gx, (unsigned)b.nunits);
+  k_small_wgrad<<<grid, 256, 0, stream>>>(b.p);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_small_wgrad_layer(const Layout& L, int i, const float* dprm, const float* const* hs, const float* const* ts,
+                             float* const* dus, float* const* dts, const float* dh0, const float* theta_i, int64_t R,
+                             float* grads, cudaStream_t s) {
+  const int H = L.H, lH = L.ldH(), D = L.D;
+  SmallWgradBatch b;
+  bool ok = b.add(dprm, L.ldP(i), L.dP(i), hs[L.Bk], lH, H, false, grads + L.wf(i), H, grads + L.bf(i));
+  for (int k = L.Bk - 1; k >= 0 && ok; --k) {
+    ok = ok && b.add(dus[k], lH, H, ts[k], lH, H, true, grads + L.w2(i, k), H, grads + L.b2(i, k));
+    ok = ok && b.add(dts[k], lH, H, hs[k], lH, H, true, grads + L.w1(i, k), H, grads + L.b1(i, k));
+  }
+  ok = ok && b.add(dh0, lH, H, theta_i, D, D, false, grads + L.w0x(i), D, nullptr);
+  if (!ok) return FP_E_NOTREADY;
+  return launch_small_wgrad(b, R, s);
+}
+
 // ---- fp16 hi / scaled-residual images of one layer's matrices in the kernels' shared-memory layout (layout.h sh*) ----
 __global__ void k_prep_small(const float* __restrict__ params, uint16_t* __restrict__ img, fp_nsf_config cfg) {
   const Layout L(&cfg);

@@ -174,6 +174,24 @@ uint64_t layer_seed(uint64_t seed, int layer, int block) {
   return seed * 0x9E3779B97F4A7C15ull + (uint64_t)(layer * 64 + block + 1) * 0xD6E8FEB86659FD93ull;
 }
 
+// all 2 Bk + 2 weight (and bias) gradients of layer i's hidden <= 64 conditioner in one launch (cond_small.cu)
+int launch_small_wgrad_layer(const Layout& L, int i, const float* dprm, const float* const* hs, const float* const* ts,
+                             float* const* dus, float* const* dts, const float* dh0, const float* theta_i, int64_t R,
+                             float* grads, cudaStream_t s);
+static int small_wgrads(const Layout& L, int i, const float* dprm, const float* const* hs, const float* const* ts,
+                        float* const* dus, float* const* dts, const float* dh0, const float* theta_i, int64_t R, float* grads,
+                        cudaStream_t s) {
+  int r = launch_small_wgrad_layer(L, i, dprm, hs, ts, dus, dts, dh0, theta_i, R, grads, s);
+  if (r != FP_E_NOTREADY) return r;
+  const int H = L.H, lH = L.ldH(), D = L.D;      // shapes the batched kernel does not take: one GEMM per matrix
+  FP_TRY(wgrad(dprm, L.ldP(i), L.dP(i), hs[L.Bk], lH, H, R, grads + L.wf(i), H, 0, s, grads + L.bf(i)));
+  for (int k = L.Bk - 1; k >= 0; --k) {
+    FP_TRY(wgrad(dus[k], lH, H, ts[k], lH, H, R, grads + L.w2(i, k), H, FP_G_RELU_B, s, grads + L.b2(i, k)));
+    FP_TRY(wgrad(dts[k], lH, H, hs[k], lH, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, s, grads + L.b1(i, k)));
+  }
+  return wgrad(dh0, lH, H, theta_i, D, D, R, grads + L.w0x(i), D, 0, s);
+}
+
 // One decision per flow pass: does every layer's conditioner run as ONE kernel -- the tcgen05 kernel for hidden 128
 // (cond_fused.cu, returns 1) or the shared-memory-resident kernel for hidden <= 64 (cond_small.cu, returns 2)?  Both read
 // sigmoid(gate) from the gate slots of the context projection (k_gate_sigmoid).
@@ -435,12 +453,7 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
       for (int k = 0; k <= L.Bk; ++k) hs[k] = ws + W.hbuf(i, k);
       for (int k = 0; k < L.Bk; ++k) { ts[k] = ws + W.tbuf(i, k); us[k] = ws + W.ubuf(i, k); dus[k] = ws + W.dubuf(k); dts[k] = ws + W.dtbuf(k); }
       FP_TRY(launch_cond_small_bwd(cfg, L, prepared, i, dprm, hs, ts, us, ctx_all, A, R, dus, dts, dh, dctx_all, dth_a, drop_scale, s));
-      FP_TRY(wgrad(dprm, ldP, dP, hs[L.Bk], lH, H, R, grads + L.wf(i), H, 0, s, grads + L.bf(i)));
-      for (int k = L.Bk - 1; k >= 0; --k) {
-        FP_TRY(wgrad(dus[k], lH, H, ts[k], lH, H, R, grads + L.w2(i, k), H, FP_G_RELU_B, s, grads + L.b2(i, k)));
-        FP_TRY(wgrad(dts[k], lH, H, hs[k], lH, H, R, grads + L.w1(i, k), H, FP_G_RELU_B, s, grads + L.b1(i, k)));
-      }
-      FP_TRY(wgrad(dh, lH, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, s));
+      FP_TRY(small_wgrads(L, i, dprm, hs, ts, dus, dts, dh, ws + W.thst(i), R, grads, s));
       continue;
     }
     // ---- final layer

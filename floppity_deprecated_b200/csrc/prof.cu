@@ -46,7 +46,8 @@ int fp_prof_enable(int32_t on) {
   return 0;
 }
 static const char* const g_tag_names[NTAGS] = {"k_gemm", "k_gemm_tc_nt", "k_gemm_tc_tn", "k_cond_fwd", "k_rqs_apply_fwd", "k_rqs_apply_inv",
-                                               "k_rqs_backward", "k_cond_small_fwd", "k_cond_small_bwd", "k_embed_conv", "other"};
+                                               "k_rqs_backward", "k_cond_small_fwd", "k_cond_small_bwd", "k_embed_conv", "k_small_wgrad",
+                                               "other"};
 int32_t fp_prof_ntags(void) { return NTAGS; }
 const char* fp_prof_tag_name(int32_t tag) { return (tag >= 0 && tag < NTAGS) ? g_tag_names[tag] : ""; }
 // Synchronises the device, then fills per-kernel totals (arrays of fp_prof_ntags() entries): elapsed ms (CUDA events on

@@ -17,8 +17,9 @@ enum ProfTag {
   TAG_COND_SMALL_FWD = 7,  // k_cond_small_fwd (shared-memory-resident conditioner, hidden <= 64)
   TAG_COND_SMALL_BWD = 8,  // k_cond_small_bwd
   TAG_EMBED = 9,           // convolutional embedding kernels
-  TAG_OTHER = 10,
-  NTAGS = 11
+  TAG_SMALL_WGRAD = 10,    // k_small_wgrad (all weight gradients of a hidden <= 64 conditioner layer)
+  TAG_OTHER = 11,
+  NTAGS = 12
 };
 
 struct ProfScope {

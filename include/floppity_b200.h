@@ -261,7 +261,7 @@ int fp_within_box(const float* theta, const float* low, const float* high, uint8
 /* ---- launch accounting (bench.py: gpu_launches and the live per-kernel roofline numbers) -----------------------
  * Kernels are tagged individually (fp_prof_ntags() tags, fp_prof_tag_name(i) = the __global__ function's name):
  * k_gemm, k_gemm_tc_nt, k_gemm_tc_tn, k_cond_fwd, k_rqs_apply_fwd, k_rqs_apply_inv, k_rqs_backward, k_cond_small_fwd,
- * k_cond_small_bwd, k_embed_conv, other.  fp_prof_collect synchronises the device and fills, per tag, the elapsed
+ * k_cond_small_bwd, k_embed_conv, k_small_wgrad, other.  fp_prof_collect synchronises the device and fills, per tag, the elapsed
  * milliseconds (CUDA events recorded around every launch on the launching stream), the launch count and the
  * ALGORITHMIC flops and HBM bytes those launches were asked to do, then clears the records. */
 /* Rejection step of accept_reject_sample: append the rows of theta [R, D] that lie inside [low, high] to out (row
