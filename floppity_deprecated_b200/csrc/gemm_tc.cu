@@ -50,46 +50,60 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES + 1024 /*
 // MMAs: the big hi*hi products get their own accumulator (the small cross terms cannot disturb it) and
 // contractions longer than 1024 are cut into chunks whose partial sums are added in fp32 by the epilogue
 // (only for the plain/bias epilogue, which is all the long-K context projection needs).
-template <int EPI>
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
              const __grid_constant__ CUtensorMap mapBl, const fp_gemm_args g, int nkb_total, int nchunks, int vec_all,
              long long* trace, int dbg) {
+  // PAIR: the two CTAs of a cluster compute a 256 x 128 output block with cta_group::2 MMAs (rank 0 issues them): each CTA
+  // loads its own 128 rows of A and only HALF of the B tile (64 rows), so a stage is 48 KB instead of 64 KB -- a
+  // four-deep ring in the same 192 KB and a third less L2 -> shared-memory traffic per flop.  The single-CTA ring is
+  // latency-bound on long contractions (tools/tc_trace_c3.py: ~3300 cycles around the ring for ~810 cycles of MMA work
+  // per k-block, three stages).
+  constexpr int BROWS = PAIR ? TC_BN / 2 : TC_BN;             // rows of the B tile this CTA holds
+  constexpr int B_TILE = BROWS * TC_BK * 4;
+  constexpr int STAGE = 2 * TC_TILE_BYTES + 2 * B_TILE;       // A (raw -> hi), A_lo, B_hi, B_lo
+  constexpr int STAGES = TC_STAGES * TC_STAGE_BYTES / STAGE;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_a = smem_u32(smem);                                  // shared-space address of the ring
   const uint32_t cs_a = smem_a + TC_STAGES * TC_STAGE_BYTES;              // epilogue staging slabs
   uint64_t* full_raw = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES);
-  uint64_t* ready = full_raw + TC_STAGES;
-  uint64_t* empty = ready + TC_STAGES;
-  uint64_t* acc_full = empty + TC_STAGES;      // [2]
+  uint64_t* ready = full_raw + STAGES;
+  uint64_t* empty = ready + STAGES;
+  uint64_t* acc_full = empty + STAGES;      // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   pdl_launch_dependents();      // the next kernel in the stream may start its own prologue as SMs free up
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int64_t cta_id = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;       // the pair walks ONE tile sequence
+  const int64_t cta_step = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  constexpr int ROWS_M = PAIR ? 2 * TC_BM : TC_BM;               // output rows of one work item
   const int tiles_n = (g.N + TC_BN - 1) / TC_BN;
-  const int64_t tiles_m = (g.M + TC_BM - 1) / TC_BM;
+  const int64_t tiles_m = (g.M + ROWS_M - 1) / ROWS_M;
   const int64_t n_super = tiles_m * tiles_n;
   const int kb_per_chunk = (nkb_total + nchunks - 1) / nchunks;
   // rasterisation: concurrently running CTAs should share tiles of the LARGER operand stream, i.e. walk the
   // dimension of the smaller operand fastest (activations [M,K] vs weights [N,K]); the other one stays in L2
   const bool m_fast = g.M <= (int64_t)g.N;
-  auto tile_m0 = [&](int64_t st) -> int64_t { return (m_fast ? (st % tiles_m) : (st / tiles_n)) * TC_BM; };
+  auto tile_m0 = [&](int64_t st) -> int64_t { return (m_fast ? (st % tiles_m) : (st / tiles_n)) * ROWS_M + (int64_t)rank * TC_BM; };
   auto tile_n0 = [&](int64_t st) -> int { return (int)(m_fast ? (st / tiles_m) : (st % tiles_n)) * TC_BN; };
 
   if (threadIdx.x == 0) {
     FP_TRACE(500);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], PAIR ? 8 : 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 16 : 8); }
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // both CTAs' barriers are initialised before either one signals the other's
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are only
@@ -101,58 +115,68 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;   // global k-block counter -> ring slot / phase
-      for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+      for (int64_t st = cta_id; st < n_super; st += cta_step) {
         const int64_t m0 = tile_m0(st);
-        const int n0 = tile_n0(st);
+        const int n0 = tile_n0(st) + (int)rank * BROWS;      // this CTA's rows of the B tile
         for (int kb = 0; kb < nkb_total; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (it / TC_STAGES) & 1u;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          uint8_t* sb = smem + s * TC_STAGE_BYTES;
-          mbar_expect_tx(&full_raw[s], ((dbg & 8) ? 2 : 3) * TC_TILE_BYTES);
+          uint8_t* sb = smem + s * STAGE;
+          mbar_expect_tx(&full_raw[s], TC_TILE_BYTES + ((dbg & 8) ? 1 : 2) * B_TILE);
           tma_load_2d(sb, &mapA, kb * TC_BK, (int)m0, &full_raw[s]);
           tma_load_2d(sb + 2 * TC_TILE_BYTES, &mapBh, kb * TC_BK, n0, &full_raw[s]);
-          if (!(dbg & 8)) tma_load_2d(sb + 3 * TC_TILE_BYTES, &mapBl, kb * TC_BK, n0, &full_raw[s]);
+          if (!(dbg & 8)) tma_load_2d(sb + 2 * TC_TILE_BYTES + B_TILE, &mapBl, kb * TC_BK, n0, &full_raw[s]);
           if (it < 60) FP_TRACE(it * 8 + 0);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(ROWS_M, TC_BN);
       uint32_t it = 0, tile_it = 0;
-      for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+      for (int64_t st = cta_id; st < n_super; st += cta_step) {
         for (int kc = 0; kc < nchunks; ++kc, ++tile_it) {
           const int buf = tile_it & 1;
           const uint32_t aph = (tile_it >> 1) & 1u;
-          mbar_wait(&acc_empty[buf], aph ^ 1u);             // epilogue has drained this accumulator set
+          if (PAIR) mbar_wait_cluster(&acc_empty[buf], aph ^ 1u);
+          else mbar_wait(&acc_empty[buf], aph ^ 1u);        // epilogue has drained this accumulator set
           tcgen05_fence_after();
           const uint32_t t_hh = tmem_base + (uint32_t)(buf * 256);
           const uint32_t t_x = t_hh + 128;
           const int kb0 = kc * kb_per_chunk;
           const int kb1 = min(nkb_total, kb0 + kb_per_chunk);
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
-            const int s = it % TC_STAGES;
-            const uint32_t ph = (it / TC_STAGES) & 1u;
-            mbar_wait(&ready[s], ph);
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            if (PAIR) mbar_wait_cluster(&ready[s], ph);      // both CTAs' A tiles converted, both halves of B landed
+            else mbar_wait(&ready[s], ph);
             tcgen05_fence_after();
             if (it < 60) FP_TRACE(it * 8 + 3);
-            uint8_t* sb = smem + s * TC_STAGE_BYTES;
+            uint8_t* sb = smem + s * STAGE;
             const uint64_t a_hi = make_kmajor_desc(sb), a_lo = make_kmajor_desc(sb + TC_TILE_BYTES);
-            const uint64_t b_hi = make_kmajor_desc(sb + 2 * TC_TILE_BYTES), b_lo = make_kmajor_desc(sb + 3 * TC_TILE_BYTES);
+            const uint64_t b_hi = make_kmajor_desc(sb + 2 * TC_TILE_BYTES), b_lo = make_kmajor_desc(sb + 2 * TC_TILE_BYTES + B_TILE);
 #pragma unroll
             for (int k = 0; k < TC_BK / 8; ++k) {
               const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per UMMA_K inside the swizzle row
               const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-              umma_tf32(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
-              umma_tf32(t_x, a_lo + adv, b_hi + adv, idesc, acc);
-              if (!(dbg & 4)) umma_tf32(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
+              if (PAIR) {
+                umma_tf32_pair(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
+                umma_tf32_pair(t_x, a_lo + adv, b_hi + adv, idesc, acc);
+                if (!(dbg & 4)) umma_tf32_pair(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
+              } else {
+                umma_tf32(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
+                umma_tf32(t_x, a_lo + adv, b_hi + adv, idesc, acc);
+                if (!(dbg & 4)) umma_tf32(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
+              }
             }
-            umma_commit(&empty[s]);        // ring slot reusable once these MMAs have read it
+            if (PAIR) umma_commit_pair(&empty[s]);           // the ring slot is reusable in BOTH CTAs
+            else umma_commit(&empty[s]);   // ring slot reusable once these MMAs have read it
             if (it < 60) FP_TRACE(it * 8 + 4);
           }
-          umma_commit(&acc_full[buf]);     // this accumulator set is complete
+          if (PAIR) umma_commit_pair(&acc_full[buf]);
+          else umma_commit(&acc_full[buf]);     // this accumulator set is complete
         }
       }
     }
@@ -163,10 +187,10 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int pf_fl = (EPI >= 0 ? EPI : g.flags) & (FP_G_GLU_RES | FP_G_RELUMASK | FP_G_ACCUM);
     const int pf_bytes = (pf_fl && vec_all) ? TC_BN * 4 : 0;
     uint32_t it = 0;
-    for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+    for (int64_t st = cta_id; st < n_super; st += cta_step) {
       for (int kb = 0; kb < nkb_total; ++kb, ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1u;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
         if (kb == 0 && pf_bytes > 0) {
           // L2 prefetch of this tile's epilogue operands (one row segment per thread): the epilogue warps can only
           // keep ~4 KB of loads in flight each, so at HBM latency they are bandwidth-starved; at L2-hit latency not
@@ -181,7 +205,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
         mbar_wait(&full_raw[s], ph);
         if (tid_s == 0 && it < 60) FP_TRACE(it * 8 + 1);
-        const uint32_t aA = smem_a + (uint32_t)(s * TC_STAGE_BYTES) + (uint32_t)tid_s * 16u;
+        const uint32_t aA = smem_a + (uint32_t)(s * STAGE) + (uint32_t)tid_s * 16u;
         float4 v[TC_TILE_BYTES / 16 / 128];
         if (!(dbg & 1)) {
 #pragma unroll
@@ -197,7 +221,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
         fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ready[s]);
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(&ready[s]); else mbar_arrive(&ready[s]); }
         if (tid_s == 0 && it < 60) FP_TRACE(it * 8 + 2);
       }
     }
@@ -221,7 +245,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const uint32_t ld_even = slabw + (uint32_t)rsub * 128u + ((uint32_t)(cch ^ rsub) << 4);
     const uint32_t ld_odd = slabw + (uint32_t)(rsub + 4) * 128u + ((uint32_t)(cch ^ (rsub + 4)) << 4);
     uint32_t tile_it = 0;
-    for (int64_t st = blockIdx.x; st < n_super; st += gridDim.x) {
+    for (int64_t st = cta_id; st < n_super; st += cta_step) {
       const int64_t m0 = tile_m0(st);
       const int n0 = tile_n0(st);
       const int64_t mrow = m0 + q * 32 + rsub;                              // first of this thread's 8 rows
@@ -270,7 +294,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           if (chunk == 1) {                       // all TMEM reads of this set are done: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
           }
           __syncwarp();
           if (dbg & 2) {
@@ -317,9 +341,10 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // the leader's MMAs read the partner's shared memory until the last commit
+  else __syncthreads();
   if (threadIdx.x == 0) FP_TRACE(502);
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // Stage geometry of the weight-gradient kernel.  (Measured: 16-row stages in a six-deep ring are SLOWER than 32-row
@@ -712,7 +737,7 @@ static int g_tc_dbg = 0;     // debug switches of the TN kernel (fp_tc_set_debug
 // prefetch) while the previous kernel in the stream drains; it calls griddepcontrol.wait before touching memory.
 // FLOPPITY_PDL=0 falls back to plain stream order.
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, cudaStream_t stream, Args... args) {
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, cudaStream_t stream, int cluster, Args... args) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("FLOPPITY_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
@@ -720,11 +745,20 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, cudaStream_t s
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = TC_SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {           // CTA pairs: the two CTAs of a cluster land on the two SMs of one TPC
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (on) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = on ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -743,16 +777,23 @@ static bool tc_supported(const fp_gemm_args* a) {
 int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, cudaStream_t stream) {
   if (!tc_enabled() || !tc_supported(a) || !B_hi || !B_lo) return FP_E_NOTREADY;
   if ((reinterpret_cast<uintptr_t>(B_hi) & 15) || (reinterpret_cast<uintptr_t>(B_lo) & 15)) return FP_E_NOTREADY;
+  // CTA pairs (cta_group::2, see the kernel comment) are OFF by default: measured on c3's context projection
+  // (tools/c3_gemm_ablate.py) the pair kernel is correct but slower (25.7 ms against 18.2 ms) -- one issuing thread now
+  // paces two SMs through cluster-scope hand-shakes, which costs more than the deeper ring and the halved B traffic buy.
+  // FLOPPITY_PAIR=1 or fp_tc_set_debug(32) selects it (the parity suite runs it once).
+  static int pair_on = -1;
+  if (pair_on < 0) { const char* e = getenv("FLOPPITY_PAIR"); pair_on = (e && e[0] == '1') ? 1 : 0; }
+  const bool pair = (pair_on || (g_tc_dbg & 32)) && a->K >= 256 && a->M >= 2 * TC_BM;
   CUtensorMap mA, mBh, mBl;
   if (!get_tensor_map(a->A, a->M, a->K, a->lda, &mA)) return FP_E_NOTREADY;
-  if (!get_tensor_map(B_hi, a->N, a->K, a->ldb, &mBh)) return FP_E_NOTREADY;
-  if (!get_tensor_map(B_lo, a->N, a->K, a->ldb, &mBl)) return FP_E_NOTREADY;
+  if (!get_tensor_map(B_hi, a->N, a->K, a->ldb, &mBh, pair ? TC_BN / 2 : TC_BN)) return FP_E_NOTREADY;
+  if (!get_tensor_map(B_lo, a->N, a->K, a->ldb, &mBl, pair ? TC_BN / 2 : TC_BN)) return FP_E_NOTREADY;
   const int nkb = (int)((a->K + TC_BK - 1) / TC_BK);
   // long contractions are chunked (see the kernel comment); only the plain / bias epilogue can be accumulated
   const bool plain = (a->flags & ~(FP_G_RELU_A | FP_G_BIAS | FP_G_TF32X3)) == 0;
   const int nchunks = (plain && nkb > TC_KCHUNK_BLOCKS) ? (nkb + TC_KCHUNK_BLOCKS - 1) / TC_KCHUNK_BLOCKS : 1;
-  const int64_t tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + TC_BN - 1) / TC_BN);
-  const int grid = (int)std::min<int64_t>(tiles, num_sms());
+  const int64_t tiles = ((a->M + (pair ? 2 : 1) * TC_BM - 1) / ((pair ? 2 : 1) * TC_BM)) * ((a->N + TC_BN - 1) / TC_BN);
+  const int grid = pair ? 2 * (int)std::min<int64_t>(tiles, num_sms() / 2) : (int)std::min<int64_t>(tiles, num_sms());
   ProfScope ps(TAG_GEMM_TC_NT, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
   // float4 epilogue needs every pointer the flags touch to be 16-byte aligned with a leading dimension % 4 == 0
   auto ok = [](const void* p, int64_t ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 3) == 0)); };
@@ -766,10 +807,14 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   case (E): {                                                                                                         \
     static bool attr_set = false;                                                                                     \
     if (!attr_set) {                                                                                                  \
-      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E)>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E)>, grid, stream, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg));       \
+    if (pair)                                                                                                         \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true>, grid, stream, 2, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg)); \
+    else                                                                                                              \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false>, grid, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg)); \
     break;                                                                                                            \
   }
   int epi = a->flags & FP_EPI_MASK;
@@ -827,7 +872,7 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
   if ((a->flags & FP_G_COLSUM_A) && (reinterpret_cast<uintptr_t>(a->U) & 15)) vec_all = 0;
   ProfScope ps(TAG_GEMM_TC_TN, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
-  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg));
+  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg));
   FP_LAUNCH_CHECK();
   return 0;
 }

@@ -154,8 +154,9 @@ uint64_t fp_dropout_layer_seed(uint64_t seed, int32_t layer, int32_t block);
 int fp_set_mode(int32_t tc, int32_t fused, int32_t fused_fp16, int32_t smallh);
 /* debug: SM-clock stamps of CTA 0 of the next fp_gemm_tc launches into a device int64[512] buffer (NULL = off) */
 int fp_tc_set_trace(void* buf);
-/* debug: ablation switches for timing experiments on the weight-gradient kernel (1 skip split, 2 skip reductions,
- * 4 two of three products); results are wrong while non-zero */
+/* debug: ablation switches for timing experiments on the tensor-core GEMM kernels (1 skip the operand conversion, 2 skip the
+ * epilogue's stores / reductions, 4 two of three products, 8 (NT) do not load B_lo: results are wrong while any of these
+ * is set) and 32 = run long-contraction NT GEMMs as CTA pairs (cta_group::2; correct, measured slower, off by default) */
 int fp_tc_set_debug(int32_t bits);
 /* debug: SM-clock stamps of CTA 0 of the fused conditioner kernel (cond_fused.cu) into a device int64[512] (NULL = off) */
 int fp_cf_set_trace(void* buf);

@@ -238,8 +238,15 @@ def test_every_conditioner_variant_matches_golden(name, mode):
     assert np.abs(dth - g["d_theta"]).max() < 2e-3 * np.abs(g["d_theta"]).max()
 
 
-@pytest.mark.parametrize("C,N,M", [(2000, 1280, 300), (3000, 384, 257), (2000, 38400, 130)])
-def test_context_projection_at_real_spectrum_widths(C, N, M):
+@pytest.fixture(params=[0, 32], ids=["single_cta", "cta_pair"])
+def pair_mode(request):
+    _lib.lib().fp_tc_set_debug(request.param)      # 32: long-contraction NT GEMMs as cta_group::2 pairs
+    yield request.param
+    _lib.lib().fp_tc_set_debug(0)
+
+
+@pytest.mark.parametrize("C,N,M", [(2000, 1280, 300), (3000, 384, 257), (2000, 38400, 130), (512, 512, 1000)])
+def test_context_projection_at_real_spectrum_widths(C, N, M, pair_mode):
     """The context GEMM of c3 / c4: contraction over 2000 / 3000 spectral bins runs K-chunked on the tensor cores (chunks
     of 1024, partial sums added in fp32 by the epilogue); checked against an fp64 matmul, output width up to c3's
     T*(1+Bk)*H = 38400."""
