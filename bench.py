@@ -406,6 +406,7 @@ def main():
 
     # ============================================================ headline workload
     t_start = time.time()
+    main_w = dict(settings(args, args.config))
     main_c = build_workload(args.config, args.dropout)
     cfg = main_c.cfg
     log(f"{args.config}: data + network ready after {time.time() - t_start:.1f} s")
@@ -506,10 +507,15 @@ def main():
             extras["c2"] = dict(config=workload_desc("c2", c2.cfg, c2.loss, c2.B, c2.rows, world, 0.0), **r2)
             del c2
             torch.cuda.empty_cache()
-            for name, drop in (("c1", 0.0), ("c4", 0.0), ("c2", 0.1), ("c1", 0.1)):
+            for name, drop, loss in (("c1", 0.0, None), ("c4", 0.0, None), ("c2", 0.1, None), ("c1", 0.1, None),
+                                     ("c3", 0.0, "atomic")):
+                if name == args.config and loss is None and drop == args.dropout:
+                    continue
+                if loss is not None:          # the headline config under the SNPE-C loss too (10 atoms per pair: ~46 GB of
+                    WORKLOADS[name] = dict(WORKLOADS[name], loss=loss, batch=9472)       # activations, the round-1 setting)
                 c = build_workload(name, drop)
-                r = measure(c, max(K // 2, 5), 3)
-                key = name if drop == 0.0 else f"{name}_dropout{drop}"
+                r = measure(c, max(K // 4, 3) if loss else max(K // 2, 5), 3)
+                key = (name if drop == 0.0 else f"{name}_dropout{drop}") + (f"_{loss}" if loss else "")
                 extras[key] = dict(config=workload_desc(name, c.cfg, c.loss, c.B, c.rows, world, drop), **r)
                 log(f"{key}: {r['ms_per_step']:.3f} ms/step, {r['value']:.0f} pairs/s")
                 del c
@@ -525,7 +531,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        w = settings(args, args.config)
+        w = main_w
         Bc = ref_batch_for(args, cfg)
         v, n, dt = oracle_steps(cfg, w["loss"], Bc, theta_cpu[:4096], x_cpu[:4096], 1, seconds=12.0, dropout=args.dropout)
         cpu_base = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",

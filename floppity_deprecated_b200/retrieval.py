@@ -188,7 +188,10 @@ def preprocess(np_theta, arcis_spec, r, samples_per_round, obs_spec, noise_spec,
     mode = 2 if res else (1 if rem_mean else 0)
     has_pca, has_scaler = hasattr(pca, "components_"), hasattr(xscaler, "scale_")
     if has_pca:
-        # centre with the PCA mean in the fused pass, project with one GEMM, then the scaler on the n_pca features
+        # centre with the PCA mean in the fused pass (fp64 arithmetic, fp32 store), project with one fp32 GEMM, then the
+        # scaler on the n_pca features.  The reference projects and scales in fp64 (sklearn) and casts once at the end; the
+        # fp32 projection differs from that by < 2e-5 relative on the reference's own outputs
+        # (tests/test_retrieval.py::test_preprocess_matches_reference_outputs, PCA combinations)
         centred = augment_and_scale(spec, noise_spec, naug, mode, obs_spec, shift=pca.mean_, z=z, device=dev)
         comp = torch.as_tensor(pca.components_).to(dev, torch.float32).contiguous()      # [n_pca, C']
         x_f = _project(centred, comp)
@@ -198,6 +201,10 @@ def preprocess(np_theta, arcis_spec, r, samples_per_round, obs_spec, noise_spec,
         x_f = augment_and_scale(spec, noise_spec, naug, mode, obs_spec,
                                 shift=xscaler.mean_ if has_scaler else None,
                                 scale=xscaler.scale_ if has_scaler else None, z=z, device=dev)
+    # floppityFUN.py:424-425: the diagnostic the reference prints every round (on the spectra the PCA was fitted on; the
+    # reference applies it to the raw spectra, which only differs -- it crashes there -- when rem_mean and do_pca are combined)
+    max_err = float(np.max(pca_error(pca, rem.transform(spec))))
+    print(f"Maximum PCA reconstruction error: {max_err}")
     return theta_aug, x_f, xscaler, pca
 
 
