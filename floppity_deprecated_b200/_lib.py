@@ -77,6 +77,7 @@ SIGNATURES = {
     "fp_dropout_mask": (c_int32, [_P, c_int64, c_int32, c_float, c_uint64, _P]),
     "fp_dropout_layer_seed": (c_uint64, [c_uint64, c_int32, c_int32]),
     "fp_set_mode": (c_int32, [c_int32, c_int32, c_int32, c_int32]),
+    "fp_set_precision": (c_int32, [c_int32]),
     "fp_nsf_prepare": (c_int32, [_CFG, _P, _P, _P]),
     "fp_nsf_logprob_forward": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, _P, _P, c_int32,
                                          c_uint64, _P, _P]),

@@ -63,15 +63,17 @@ __global__ void k_lu_prepare(const float*, float*, fp_nsf_config);
 __global__ void k_lu_finish(const float*, const float*, float*, fp_nsf_config);
 
 // ---- run-time switches of the conditioner paths (fp_set_mode; the environment gives the initial values) ----
-static int g_mode[4] = {-1, -1, -1, -1};     // tc, fused, fused_fp16, smallh
-static const char* const g_mode_env[4] = {"FLOPPITY_TC", "FLOPPITY_FUSED", "FLOPPITY_FUSED_FP16", "FLOPPITY_SMALLH"};
+static int g_mode[5] = {-1, -1, -1, -1, -1};     // tc, fused, fused_fp16, smallh, single_pass
+static const char* const g_mode_env[5] = {"FLOPPITY_TC", "FLOPPITY_FUSED", "FLOPPITY_FUSED_FP16", "FLOPPITY_SMALLH",
+                                          "FLOPPITY_SINGLE_PASS"};
 static bool mode_on(int i) {
   if (g_mode[i] < 0) {
     const char* e = getenv(g_mode_env[i]);
-    g_mode[i] = (e && e[0] == '0') ? 0 : 1;
+    g_mode[i] = (i == 4) ? ((e && e[0] == '1') ? 1 : 0) : ((e && e[0] == '0') ? 0 : 1);      // single_pass defaults to OFF
   }
   return g_mode[i] == 1;
 }
+bool tc_single_pass() { return mode_on(4); }
 bool tc_enabled() { return mode_on(0); }
 bool fused_enabled() { return mode_on(1); }
 bool cond_fused_f16() { return mode_on(2); }
@@ -272,11 +274,16 @@ extern "C" {
 int fp_set_mode(int32_t tc, int32_t fused, int32_t fused_fp16, int32_t smallh) {
   const int32_t v[4] = {tc, fused, fused_fp16, smallh};
   int bits = 0;
+  if (mode_on(4)) bits |= 16;
   for (int i = 0; i < 4; ++i) {
     if (v[i] >= 0) g_mode[i] = v[i] ? 1 : 0;
     if (mode_on(i)) bits |= 1 << i;
   }
   return bits;
+}
+int fp_set_precision(int32_t single_pass) {
+  if (single_pass >= 0) g_mode[4] = single_pass ? 1 : 0;
+  return mode_on(4) ? 1 : 0;
 }
 uint64_t fp_dropout_layer_seed(uint64_t seed, int32_t layer, int32_t block) { return layer_seed(seed, layer, block); }
 

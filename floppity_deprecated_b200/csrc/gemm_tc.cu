@@ -163,12 +163,12 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
               if (PAIR) {
                 umma_tf32_pair(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
-                umma_tf32_pair(t_x, a_lo + adv, b_hi + adv, idesc, acc);
-                if (!(dbg & 4)) umma_tf32_pair(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
+                if (!(dbg & 64)) umma_tf32_pair(t_x, a_lo + adv, b_hi + adv, idesc, acc);
+                if (!(dbg & (4 | 64))) umma_tf32_pair(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
               } else {
                 umma_tf32(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
-                umma_tf32(t_x, a_lo + adv, b_hi + adv, idesc, acc);
-                if (!(dbg & 4)) umma_tf32(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
+                if (!(dbg & 64)) umma_tf32(t_x, a_lo + adv, b_hi + adv, idesc, acc);      // 64: single TF32 pass (reduced precision)
+                if (!(dbg & (4 | 64))) umma_tf32(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
               }
             }
             if (PAIR) umma_commit_pair(&empty[s]);           // the ring slot is reusable in BOTH CTAs
@@ -238,6 +238,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int rsub = lane >> 3;                // row within a group of four
     const int cch = lane & 7;                  // float4 chunk within the 32-column slab row
     const EpiArgs ea = make_epi(g);
+    const bool single = (dbg & 64) != 0;       // single TF32 pass: the cross-term accumulator is never written
     const int fl_rt = g.flags & FP_EPI_MASK;
     const bool need_ctx = ((EPI >= 0 ? EPI : fl_rt) & (FP_G_ADD_CTX | FP_G_GLU_RES)) != 0;
     const uint32_t cdiv = ea.ctx_div <= 0 ? 0xFFFFFFFFu : (uint32_t)ea.ctx_div;
@@ -288,8 +289,9 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               sts128(st_base + ((((uint32_t)(p * 4 + j)) ^ sw_st) << 4),
-                     make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
-                                 v[4 * j + 3] + x[4 * j + 3]));
+                     single ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                            : make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
+                                          v[4 * j + 3] + x[4 * j + 3]));
           }
           if (chunk == 1) {                       // all TMEM reads of this set are done: hand it back to the MMA warp
             tcgen05_fence_before();
@@ -455,8 +457,8 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const uint64_t b_lo = make_mnmajor_desc(sb + 3 * TN_TILE_BYTES + koff, GROUP_BYTES);
             const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
             umma_tf32(t_hh, a_hi, b_hi, idesc, acc);
-            umma_tf32(t_x, a_lo, b_hi, idesc, acc);
-            if (!(dbg & 4)) umma_tf32(t_x, a_hi, b_lo, idesc, 1u);
+            if (!(dbg & 64)) umma_tf32(t_x, a_lo, b_hi, idesc, acc);
+            if (!(dbg & (4 | 64))) umma_tf32(t_x, a_hi, b_lo, idesc, 1u);
           }
           umma_commit(&empty[s]);
         }
@@ -540,6 +542,7 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const uint32_t sw_st = (uint32_t)(lane & 7);
     const int rsub = lane >> 3, cch = lane & 7;
     float* const gC = g.C; const int64_t g_ldc = g.ldc, gM = g.M; const int gN = g.N;
+    const bool single = (dbg & 64) != 0;
     uint32_t tile_it = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
       int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
@@ -561,8 +564,9 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(st_base + ((((uint32_t)(p * 4 + j)) ^ sw_st) << 4),
-                   make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
-                               v[4 * j + 3] + x[4 * j + 3]));
+                   single ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                          : make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
+                                        v[4 * j + 3] + x[4 * j + 3]));
         }
         if (c4 == 3) {
           tcgen05_fence_before();
@@ -731,7 +735,8 @@ bool get_tensor_map_f16(const void* base, int64_t rows, int64_t cols, int64_t ld
 }
 
 static long long* g_tc_trace = nullptr;
-static int g_tc_dbg = 0;     // debug switches of the TN kernel (fp_tc_set_debug): 1 no split, 2 no reductions, 4 two products
+static int g_tc_dbg = 0;     // debug switches (fp_tc_set_debug): 1 no split, 2 no epilogue stores, 4 two products, 8 no B_lo, 32 pairs
+bool tc_single_pass();        // flow_engine.cu (fp_set_mode): reduced-precision variant, ONE TF32 product instead of three
 
 // Launch with programmatic stream serialisation: the kernel may begin (barrier init, TMEM allocation, tensor-map
 // prefetch) while the previous kernel in the stream drains; it calls griddepcontrol.wait before touching memory.
@@ -812,9 +817,9 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     if (pair)                                                                                                         \
-      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true>, grid, stream, 2, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg)); \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true>, grid, stream, 2, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0))); \
     else                                                                                                              \
-      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false>, grid, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg)); \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false>, grid, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0))); \
     break;                                                                                                            \
   }
   int epi = a->flags & FP_EPI_MASK;
@@ -872,7 +877,7 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
   if ((a->flags & FP_G_COLSUM_A) && (reinterpret_cast<uintptr_t>(a->U) & 15)) vec_all = 0;
   ProfScope ps(TAG_GEMM_TC_TN, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
-  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg));
+  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0)));
   FP_LAUNCH_CHECK();
   return 0;
 }

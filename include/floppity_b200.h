@@ -152,6 +152,11 @@ uint64_t fp_dropout_layer_seed(uint64_t seed, int32_t layer, int32_t block);
  * resident fused MLP for hidden <= 64.  A negative argument leaves that switch as it is.  Returns the switches as bits
  * (1 tc, 2 fused, 4 fused_fp16, 8 smallh). */
 int fp_set_mode(int32_t tc, int32_t fused, int32_t fused_fp16, int32_t smallh);
+/* REDUCED-PRECISION variant of the stand-alone tensor-core GEMMs (the wide-conditioner path, c3; FLOPPITY_SINGLE_PASS=1):
+ * one TF32 product per GEMM instead of the fp32-accurate three (operands rounded to 10 mantissa bits, fp32 accumulation).
+ * NOT within the 1e-4 parity bar: log_prob agrees with the fp32 path to ~1e-3 relative (tests state the tolerance) and is
+ * reported apart in bench.py.  Negative argument = query.  Returns the current setting. */
+int fp_set_precision(int32_t single_pass);
 /* debug: SM-clock stamps of CTA 0 of the next fp_gemm_tc launches into a device int64[512] buffer (NULL = off) */
 int fp_tc_set_trace(void* buf);
 /* debug: ablation switches for timing experiments on the tensor-core GEMM kernels (1 skip the operand conversion, 2 skip the
