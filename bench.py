@@ -289,6 +289,11 @@ def main():
         barrier()
         return float(ms.item())
 
+    def tensor_fmt(name):
+        if name in ("k_gemm_tc_nt", "k_gemm_tc_tn") and L.fp_set_precision(-1) == 1:
+            return ("1xTF32 (reduced precision)", 2.0)
+        return TENSOR_KERNELS[name]
+
     def kernel_table(fn, n):
         """Per-kernel CUDA-event timing of n calls of fn (events recorded around every launch on the launching stream)."""
         arr = lambda t: (t * NT)()
@@ -314,7 +319,7 @@ def main():
                 d["algorithmic_flops_per_launch"] = pf[i] / pl[i]
                 d["achieved_tflops"] = pf[i] / sec / 1e12
                 if name in TENSOR_KERNELS:
-                    fmt, div = TENSOR_KERNELS[name]
+                    fmt, div = tensor_fmt(name)
                     d["operands"] = fmt
                     d["frac_of_tensor_ceiling"] = d["achieved_tflops"] / (PK["tf_sust"] / div)
                     d["frac_of_bf16_peak"] = d["achieved_tflops"] / PK["tf_sust"]
@@ -331,12 +336,12 @@ def main():
         hb = d.get("frac_of_hbm_peak", 0.0)
         tc = d.get("frac_of_tensor_ceiling", 0.0)
         if name in TENSOR_KERNELS and tc >= hb:
-            fmt, div = TENSOR_KERNELS[name]
+            fmt, div = tensor_fmt(name)
             roof = {"bound": "tensor", "achieved": d["achieved_tflops"], "peak": PK["tf_sust"] / div, "unit": "TFLOP/s",
                     "frac": tc, "traffic": None, "kernel": name, "share_of_step": d["share"], "avg_us": d["avg_us"],
                     "peak_source": f"{PK['source']}: bf16 sustained {PK['tf_sust']:.0f} TFLOP/s / {div:.0f} -- {fmt} operands: "
-                                   f"three tensor-core passes per fp32-accurate product"
-                                   f"{' at the TF32 rate (half of bf16)' if div == 6.0 else ''}",
+                                   f"{'one TF32 pass' if div == 2.0 else 'three tensor-core passes per fp32-accurate product'}"
+                                   f"{' at the TF32 rate (half of bf16)' if div in (2.0, 6.0) else ''}",
                     "frac_of_bf16_peak": d["frac_of_bf16_peak"], "hbm_frac": hb}
         elif name == "k_gemm":
             fma = 148 * 128 * 2 * 1.965e9 / 1e12
