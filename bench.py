@@ -364,6 +364,11 @@ def main():
             pass
         return roof
 
+    def bcast_net(net):
+        dist.broadcast(net._flat.data, src=0)
+        for b in (net._theta_shift, net._theta_scale, net._x_mean, net._x_std):
+            dist.broadcast(b, src=0)
+
     def build_workload(name, dropout=0.0):
         w = settings(args, name)
         c = Ctx()
@@ -374,8 +379,8 @@ def main():
         c.net = fb.build_nsf(c.theta[:8192], c.x[:8192], hidden_features=c.cfg.hidden, num_transforms=c.cfg.transforms,
                              num_bins=c.cfg.bins, num_blocks=c.cfg.blocks, dropout_probability=dropout,
                              generator=torch.Generator().manual_seed(0)).to(dev)
-        if world > 1:
-            dist.broadcast(c.net._flat.data, src=0)
+        if world > 1:          # one replica: rank 0's weights AND z-score statistics (every rank generated its own data)
+            bcast_net(c.net)
         c.net.train()
         c.prior = fb.BoxUniform(-3 * torch.ones(c.cfg.D), 3 * torch.ones(c.cfg.D), device=dev)
         c.eng = _TrainEngine(c.net, c.prior, c.B, c.loss == "atomic", c.cfg.atoms, True, 5e-4, 5.0, use_graph=bool(args.graph))
@@ -483,7 +488,7 @@ def main():
         pre.check_status()
         del pre
         if world > 1:
-            dist.broadcast(c2.net._flat.data, src=0)
+            bcast_net(c2.net)
         net = c2.net.eval()
         x_obs = make_data("c2", 4096, 0)[2][:1]          # ONE observation for every rank (rank 0's data seed)
         post = fb.DirectPosterior(net, c2.prior, max_sampling_batch_size=1 << 22).set_default_x(x_obs)

@@ -308,6 +308,7 @@ class SNPE_C:
     def __getstate__(self):
         d = self.__dict__.copy()
         d["_engine"] = None
+        d.pop("_pinned", None)
         return d
 
     def append_simulations(self, theta, x, proposal=None, exclude_invalid_x: Optional[bool] = None,
@@ -334,6 +335,21 @@ class SNPE_C:
         self._proposal_roundwise.append(proposal)
         self._data_round_index.append(current_round)
         return self
+
+    def _stage_rows(self, src: Tensor, rows: Tensor, key: str) -> Tensor:
+        """``src[rows]`` gathered (multi-threaded) into a pinned buffer that is kept between ``train()`` calls, so the
+        upload is one asynchronous DMA instead of a pageable staging copy."""
+        cache = self.__dict__.setdefault("_pinned", {})
+        shape = (rows.numel(),) + tuple(src.shape[1:])
+        buf = cache.get(key)
+        if buf is None or tuple(buf.shape) != shape:
+            try:
+                buf = torch.empty(shape, dtype=src.dtype, pin_memory=True)
+            except RuntimeError:
+                buf = torch.empty(shape, dtype=src.dtype)
+            cache[key] = buf
+        torch.index_select(src, 0, rows, out=buf)
+        return buf
 
     def get_simulations(self, starting_round: int = 0):
         idx = [i for i, r in enumerate(self._data_round_index) if r >= starting_round]
@@ -404,9 +420,9 @@ class SNPE_C:
             theta_dev = theta.to(dev, non_blocking=True)[used_dev].contiguous()
             x_dev = net._standardize(x.to(dev, non_blocking=True)[used_dev])
             masks_dev = masks.reshape(-1).to(dev, non_blocking=True)[used_dev].contiguous()
-        else:                    # data-parallel: only this rank's shard crosses the bus
-            theta_dev = theta[used].to(dev).contiguous()
-            x_dev = net._standardize(x[used].to(dev))
+        else:                    # data-parallel: only this rank's shard crosses the bus, gathered into pinned staging buffers
+            theta_dev = self._stage_rows(theta, used, "theta").to(dev, non_blocking=True).contiguous()
+            x_dev = net._standardize(self._stage_rows(x, used, "x").to(dev, non_blocking=True))
             masks_dev = masks[used].reshape(-1).to(dev).contiguous()
         nt, nv = my_train.numel(), my_val.numel()
         B = int(min(training_batch_size, nt))
