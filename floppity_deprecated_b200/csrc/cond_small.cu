@@ -145,6 +145,19 @@ __device__ __forceinline__ float2 ldg_pair_unaligned(const float* row, int col, 
   return make_float2(col < ncols ? __ldg(row + col) : 0.f, col + 1 < ncols ? __ldg(row + col + 1) : 0.f);
 }
 
+// The thread's 32 values (rows q0 / q1 x columns 8 nb + 2t, +1) of a row-major operand, REQUESTED EARLY: the kernels were
+// waiting on global loads for ~60 % of their stall samples (ncu source page: the first consumer of every operand loaded
+// at its point of use), so each phase's operand is fetched into this buffer before the GEMM that precedes its use
+__device__ __forceinline__ void preload_rows(float (&b)[8][4], const float* __restrict__ r0, const float* __restrict__ r1,
+                                             int ncols, int t) {
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int col = nb * 8 + 2 * t;
+    const float2 a = ldg_pair_unaligned(r0, col, ncols), c = ldg_pair_unaligned(r1, col, ncols);
+    b[nb][0] = a.x; b[nb][1] = a.y; b[nb][2] = c.x; b[nb][3] = c.y;
+  }
+}
+
 struct CsFwdParams {
   const uint4* img; int32_t img_vec;        // forward image (hi | lo), 16-byte vectors
   int32_t fwd_halves;                       // halves of ONE image (lo image offset)
@@ -215,16 +228,17 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_fwd(const CsFwdPar
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb)
         if (kb < kb0n) split_a8(tv[kb], s0, s1, ahi[kb], alo[kb]);
+      float cb[8][4];
+      preload_rows(cb, c0, c1, H, t);                  // context slot 0, requested before the GEMM
       zero_acc(hh, xx);
       tile_gemm<4, 8>(hh, xx, ahi, alo, kb0n, 0, 8, w0_a, lo_off, s0b, lane);
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         const int col = nb * 8 + 2 * t;
-        const float2 a = ldg_pair_unaligned(c0, col, H), b = ldg_pair_unaligned(c1, col, H);
-        hres[nb][0] = un0 * (hh[nb][0] + FP16_LO_UNSCALE * xx[nb][0]) + a.x;
-        hres[nb][1] = un0 * (hh[nb][1] + FP16_LO_UNSCALE * xx[nb][1]) + a.y;
-        hres[nb][2] = un1 * (hh[nb][2] + FP16_LO_UNSCALE * xx[nb][2]) + b.x;
-        hres[nb][3] = un1 * (hh[nb][3] + FP16_LO_UNSCALE * xx[nb][3]) + b.y;
+        hres[nb][0] = un0 * (hh[nb][0] + FP16_LO_UNSCALE * xx[nb][0]) + cb[nb][0];
+        hres[nb][1] = un0 * (hh[nb][1] + FP16_LO_UNSCALE * xx[nb][1]) + cb[nb][1];
+        hres[nb][2] = un1 * (hh[nb][2] + FP16_LO_UNSCALE * xx[nb][2]) + cb[nb][2];
+        hres[nb][3] = un1 * (hh[nb][3] + FP16_LO_UNSCALE * xx[nb][3]) + cb[nb][3];
         if (training) {
           if (v0) st_pair(p.h[0] + r0 * p.ldh, col, H, hres[nb][0], hres[nb][1]);
           if (v1) st_pair(p.h[0] + r1 * p.ldh, col, H, hres[nb][2], hres[nb][3]);
@@ -267,15 +281,15 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_fwd(const CsFwdPar
       }
       // ---- u = relu(t') W2^T + b2 ; h += u * sigmoid(gate)   (slot 1+k of ctx_all holds sigmoid(gate): k_gate_sigmoid)
       make_afrags<8>(x, ahi, alo, un0, un1);
+      float gb[8][4];
+      preload_rows(gb, c0 + (int64_t)H * (1 + k), c1 + (int64_t)H * (1 + k), H, t);      // sigmoid(gate), before the GEMM
       zero_acc(hh, xx);
       tile_gemm<4, 8>(hh, xx, ahi, alo, 4, 0, 8, wblk_a + (uint32_t)(2 * k + 1) * CS_HP * shb, lo_off, shb, lane);
       const float* bb2 = bb1 + CS_HP;
-      const float* g0 = c0 + (int64_t)H * (1 + k);
-      const float* g1 = c1 + (int64_t)H * (1 + k);
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         const int col = nb * 8 + 2 * t;
-        const float2 a = ldg_pair_unaligned(g0, col, H), b = ldg_pair_unaligned(g1, col, H);
+        const float2 a = make_float2(gb[nb][0], gb[nb][1]), b = make_float2(gb[nb][2], gb[nb][3]);
         float v[4];
         v[0] = un0 * (hh[nb][0] + FP16_LO_UNSCALE * xx[nb][0]) + bb2[col];
         v[1] = un0 * (hh[nb][1] + FP16_LO_UNSCALE * xx[nb][1]) + bb2[col + 1];
@@ -354,6 +368,8 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_bwd(const CsBwdPar
     float* dc1 = p.dctx + cr1 * p.ldg;
     float hh[8][4], xx[8][4], dh[8][4];
     float un0, un1;
+    float tb[8][4];                      // the next phase's saved activation, requested one GEMM ahead
+    preload_rows(tb, p.u[Bk - 1] + q0 * p.ldh, p.u[Bk - 1] + q1 * p.ldh, H, t);
 
     {  // ---- final layer: dh = dprm Wf  (contraction over the d_tr (3K-1) spline parameters, streamed from HBM)
       const float* d0 = p.dprm + q0 * p.ldp;
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_bwd(const CsBwdPar
       for (int nb = 0; nb < 8; ++nb) {
         const int col = nb * 8 + 2 * t;
         const float2 sa = ldg_pair_unaligned(g0, col, H), sb = ldg_pair_unaligned(g1, col, H);
-        const float2 ua = ld_pair(p.u[k] + q0 * p.ldh, col, H), ub = ld_pair(p.u[k] + q1 * p.ldh, col, H);
+        const float2 ua = make_float2(tb[nb][0], tb[nb][1]), ub = make_float2(tb[nb][2], tb[nb][3]);
         x[nb][0] = dh[nb][0] * sa.x; x[nb][1] = dh[nb][1] * sa.y;
         x[nb][2] = dh[nb][2] * sb.x; x[nb][3] = dh[nb][3] * sb.y;
         if (v0) {
@@ -411,32 +427,32 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_bwd(const CsBwdPar
       }
       // ---- dt = (du W2) * (t' > 0) * 1/(1-p)        (t' = dropout(t): relu mask and keep mask in one)
       make_afrags<8>(x, ahi, alo, un0, un1);
+      preload_rows(tb, p.t[k] + q0 * p.ldh, p.t[k] + q1 * p.ldh, H, t);
       zero_acc(hh, xx);
       tile_gemm<4, 8>(hh, xx, ahi, alo, 4, 0, 8, wblk_a + (uint32_t)(2 * k + 1) * CS_HP * shb, lo_off, shb, lane);
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         const int col = nb * 8 + 2 * t;
-        const float2 ta = ld_pair(p.t[k] + q0 * p.ldh, col, H), tb = ld_pair(p.t[k] + q1 * p.ldh, col, H);
-        x[nb][0] = ta.x > 0.f ? un0 * p.mask_scale * (hh[nb][0] + FP16_LO_UNSCALE * xx[nb][0]) : 0.f;
-        x[nb][1] = ta.y > 0.f ? un0 * p.mask_scale * (hh[nb][1] + FP16_LO_UNSCALE * xx[nb][1]) : 0.f;
-        x[nb][2] = tb.x > 0.f ? un1 * p.mask_scale * (hh[nb][2] + FP16_LO_UNSCALE * xx[nb][2]) : 0.f;
-        x[nb][3] = tb.y > 0.f ? un1 * p.mask_scale * (hh[nb][3] + FP16_LO_UNSCALE * xx[nb][3]) : 0.f;
+        x[nb][0] = tb[nb][0] > 0.f ? un0 * p.mask_scale * (hh[nb][0] + FP16_LO_UNSCALE * xx[nb][0]) : 0.f;
+        x[nb][1] = tb[nb][1] > 0.f ? un0 * p.mask_scale * (hh[nb][1] + FP16_LO_UNSCALE * xx[nb][1]) : 0.f;
+        x[nb][2] = tb[nb][2] > 0.f ? un1 * p.mask_scale * (hh[nb][2] + FP16_LO_UNSCALE * xx[nb][2]) : 0.f;
+        x[nb][3] = tb[nb][3] > 0.f ? un1 * p.mask_scale * (hh[nb][3] + FP16_LO_UNSCALE * xx[nb][3]) : 0.f;
         if (v0) st_pair(p.dt[k] + r0 * p.ldh, col, H, x[nb][0], x[nb][1]);
         if (v1) st_pair(p.dt[k] + r1 * p.ldh, col, H, x[nb][2], x[nb][3]);
       }
       // ---- dh += (dt W1) * (h_k > 0)
       make_afrags<8>(x, ahi, alo, un0, un1);
+      preload_rows(tb, p.h[k] + q0 * p.ldh, p.h[k] + q1 * p.ldh, H, t);
       zero_acc(hh, xx);
       tile_gemm<4, 8>(hh, xx, ahi, alo, 4, 0, 8, wblk_a + (uint32_t)(2 * k) * CS_HP * shb, lo_off, shb, lane);
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
-        const int col = nb * 8 + 2 * t;
-        const float2 ha = ld_pair(p.h[k] + q0 * p.ldh, col, H), hb = ld_pair(p.h[k] + q1 * p.ldh, col, H);
-        if (ha.x > 0.f) dh[nb][0] += un0 * (hh[nb][0] + FP16_LO_UNSCALE * xx[nb][0]);
-        if (ha.y > 0.f) dh[nb][1] += un0 * (hh[nb][1] + FP16_LO_UNSCALE * xx[nb][1]);
-        if (hb.x > 0.f) dh[nb][2] += un1 * (hh[nb][2] + FP16_LO_UNSCALE * xx[nb][2]);
-        if (hb.y > 0.f) dh[nb][3] += un1 * (hh[nb][3] + FP16_LO_UNSCALE * xx[nb][3]);
+        if (tb[nb][0] > 0.f) dh[nb][0] += un0 * (hh[nb][0] + FP16_LO_UNSCALE * xx[nb][0]);
+        if (tb[nb][1] > 0.f) dh[nb][1] += un0 * (hh[nb][1] + FP16_LO_UNSCALE * xx[nb][1]);
+        if (tb[nb][2] > 0.f) dh[nb][2] += un1 * (hh[nb][2] + FP16_LO_UNSCALE * xx[nb][2]);
+        if (tb[nb][3] > 0.f) dh[nb][3] += un1 * (hh[nb][3] + FP16_LO_UNSCALE * xx[nb][3]);
       }
+      if (k > 0) preload_rows(tb, p.u[k - 1] + q0 * p.ldh, p.u[k - 1] + q1 * p.ldh, H, t);      // for the next block's GLU backward
     }
 
     // ---- initial layer: dh0 out (weight gradient operand), d ctx slot 0 += dh0, d theta_i += dh0 W0x
