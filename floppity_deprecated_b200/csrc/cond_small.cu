@@ -368,8 +368,9 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_bwd(const CsBwdPar
     float* dc1 = p.dctx + cr1 * p.ldg;
     float hh[8][4], xx[8][4], dh[8][4];
     float un0, un1;
-    float tb[8][4];                      // the next phase's saved activation, requested one GEMM ahead
+    float tb[8][4], gb[8][4];            // the next phase's saved activation / gate, requested one GEMM ahead
     preload_rows(tb, p.u[Bk - 1] + q0 * p.ldh, p.u[Bk - 1] + q1 * p.ldh, H, t);
+    preload_rows(gb, c0 + (int64_t)H * Bk, c1 + (int64_t)H * Bk, H, t);
 
     {  // ---- final layer: dh = dprm Wf  (contraction over the d_tr (3K-1) spline parameters, streamed from HBM)
       const float* d0 = p.dprm + q0 * p.ldp;
@@ -403,14 +404,12 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_bwd(const CsBwdPar
     for (int k = Bk - 1; k >= 0; --k) {
       float x[8][4];
       // ---- GLU backward: du = dh * sig ; d gate += dh * u * sig (1 - sig), reduced over the rows sharing a context row
-      const float* g0 = c0 + (int64_t)H * (1 + k);
-      const float* g1 = c1 + (int64_t)H * (1 + k);
       float* dg0 = dc0 + (int64_t)H * (1 + k);
       float* dg1 = dc1 + (int64_t)H * (1 + k);
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         const int col = nb * 8 + 2 * t;
-        const float2 sa = ldg_pair_unaligned(g0, col, H), sb = ldg_pair_unaligned(g1, col, H);
+        const float2 sa = make_float2(gb[nb][0], gb[nb][1]), sb = make_float2(gb[nb][2], gb[nb][3]);
         const float2 ua = make_float2(tb[nb][0], tb[nb][1]), ub = make_float2(tb[nb][2], tb[nb][3]);
         x[nb][0] = dh[nb][0] * sa.x; x[nb][1] = dh[nb][1] * sa.y;
         x[nb][2] = dh[nb][2] * sb.x; x[nb][3] = dh[nb][3] * sb.y;
@@ -452,7 +451,10 @@ __global__ void __launch_bounds__(CS_THREADS, 1) k_cond_small_bwd(const CsBwdPar
         if (tb[nb][2] > 0.f) dh[nb][2] += un1 * (hh[nb][2] + FP16_LO_UNSCALE * xx[nb][2]);
         if (tb[nb][3] > 0.f) dh[nb][3] += un1 * (hh[nb][3] + FP16_LO_UNSCALE * xx[nb][3]);
       }
-      if (k > 0) preload_rows(tb, p.u[k - 1] + q0 * p.ldh, p.u[k - 1] + q1 * p.ldh, H, t);      // for the next block's GLU backward
+      if (k > 0) {       // for the next block's GLU backward
+        preload_rows(tb, p.u[k - 1] + q0 * p.ldh, p.u[k - 1] + q1 * p.ldh, H, t);
+        preload_rows(gb, c0 + (int64_t)H * k, c1 + (int64_t)H * k, H, t);
+      }
     }
 
     // ---- initial layer: dh0 out (weight gradient operand), d ctx slot 0 += dh0, d theta_i += dh0 W0x
@@ -521,8 +523,14 @@ __device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t& r0, uint32_t& r1
                : "r"(addr));
 }
 
+constexpr int SW_RAW_FLOATS = 64 * 64;                       // one raw fp32 operand tile
+constexpr int SW_SMEM_BYTES = 2 * 2 * SW_RAW_FLOATS * 4 + 4 * 64 * SW_TS * 2;     // 2 buffers x (A, B) raw + 4 fp16 tiles
+
 __global__ void __launch_bounds__(256, 2) k_small_wgrad(const SwParams p) {
-  __shared__ __align__(16) uint16_t tA[2][64 * SW_TS], tB[2][64 * SW_TS];     // [hi | lo][row][col]
+  extern __shared__ __align__(16) uint8_t sw_smem[];
+  float* raw = reinterpret_cast<float*>(sw_smem);                                         // [buf][A | B][row][64]
+  uint16_t* tA = reinterpret_cast<uint16_t*>(sw_smem + 2 * 2 * SW_RAW_FLOATS * 4);        // [hi | lo][row][SW_TS]
+  uint16_t* tB = tA + 2 * 64 * SW_TS;
   __shared__ int cmaxA[64], cmaxB[64];
   __shared__ float unA[64], unB[64], scA[64], scB[64], dbs[64];
   const SwPair& pr = p.pair[p.unit_pair[blockIdx.y]];
@@ -546,39 +554,59 @@ __global__ void __launch_bounds__(256, 2) k_small_wgrad(const SwParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) master[nb][j] = 0.f;
 
-  float va[4][4], vb[4][4];
-  auto load_tile = [&](int64_t row0) {
+  // Raw fp32 tiles arrive by cp.async (16-byte chunks, zero-filled beyond the matrix) into a two-deep buffer: the copy of
+  // tile i+1 is issued BEFORE tile i is converted and multiplied, so a whole iteration hides its latency (the kernel was
+  // waiting on its global loads: ncu long_scoreboard).  Unaligned operands take plain loads into the same buffer.
+  auto issue_tile = [&](int64_t row0, int buf) {
+    float* ra = raw + buf * 2 * SW_RAW_FLOATS;
+    float* rb = ra + SW_RAW_FLOATS;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int64_t r = row0 + rr + 16 * j;
+      const int row = rr + 16 * j;
+      const int64_t r = row0 + row;
       const bool rv = r < r_end;
-      const float* ap = A + r * lda + m0 + c4;
-      if (rv && a_vec && m0 + c4 + 3 < M) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(ap));
-        va[j][0] = v.x; va[j][1] = v.y; va[j][2] = v.z; va[j][3] = v.w;
+      const int na = rv ? max(0, min(4, M - (m0 + c4))) : 0;
+      const int nb = rv ? max(0, min(4, N - c4)) : 0;
+      if (a_vec) {
+        const float* src = na ? A + r * lda + m0 + c4 : A;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(ra + row * 64 + c4)), "l"(src), "r"(na * 4) : "memory");
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) va[j][e] = (rv && m0 + c4 + e < M) ? __ldg(ap + e) : 0.f;
+        for (int e = 0; e < 4; ++e) ra[row * 64 + c4 + e] = e < na ? __ldg(A + r * lda + m0 + c4 + e) : 0.f;
       }
-      const float* bp = B + r * ldb + c4;
-      if (rv && b_vec && c4 + 3 < N) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(bp));
-        vb[j][0] = v.x; vb[j][1] = v.y; vb[j][2] = v.z; vb[j][3] = v.w;
+      if (b_vec) {
+        const float* src = nb ? B + r * ldb + c4 : B;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(rb + row * 64 + c4)), "l"(src), "r"(nb * 4) : "memory");
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) vb[j][e] = (rv && c4 + e < N) ? __ldg(bp + e) : 0.f;
-      }
-      if (relu_b) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) vb[j][e] = fmaxf(vb[j][e], 0.f);
+        for (int e = 0; e < 4; ++e) rb[row * 64 + c4 + e] = e < nb ? __ldg(B + r * ldb + c4 + e) : 0.f;
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-
-  load_tile(r_begin);
-  for (int64_t row0 = r_begin; row0 < r_end; row0 += 64) {
+  float va[4][4], vb[4][4];
+  issue_tile(r_begin, 0);
+  int it = 0;
+  for (int64_t row0 = r_begin; row0 < r_end; row0 += 64, ++it) {
     if (tid < 64) { cmaxA[tid] = 0; cmaxB[tid] = 0; }
-    __syncthreads();                                        // (also: the previous tile's MMAs are done with the staged tiles)
+    const bool more = row0 + 64 < r_end;
+    if (more) issue_tile(row0 + 64, (it + 1) & 1);           // lands while this tile is converted and multiplied
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                        // tile `it` is in shared memory (everybody's chunks); the previous
+                                                            // tile's MMAs are done with the staged fp16 tiles
+    {
+      const float* ra = raw + (it & 1) * 2 * SW_RAW_FLOATS;
+      const float* rb = ra + SW_RAW_FLOATS;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a4 = *reinterpret_cast<const float4*>(ra + (rr + 16 * j) * 64 + c4);
+        float4 b4 = *reinterpret_cast<const float4*>(rb + (rr + 16 * j) * 64 + c4);
+        if (relu_b) { b4.x = fmaxf(b4.x, 0.f); b4.y = fmaxf(b4.y, 0.f); b4.z = fmaxf(b4.z, 0.f); b4.w = fmaxf(b4.w, 0.f); }
+        va[j][0] = a4.x; va[j][1] = a4.y; va[j][2] = a4.z; va[j][3] = a4.w;
+        vb[j][0] = b4.x; vb[j][1] = b4.y; vb[j][2] = b4.z; vb[j][3] = b4.w;
+      }
+    }
     // ---- per-column maxima of this tile (non-negative floats order like their bit patterns)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -605,21 +633,20 @@ __global__ void __launch_bounds__(256, 2) k_small_wgrad(const SwParams p) {
         uint32_t h0, l0, h1, l1;
         split_f16x2(va[j][0] * sa.x, va[j][1] * sa.y, h0, l0);
         split_f16x2(va[j][2] * sa.z, va[j][3] * sa.w, h1, l1);
-        *reinterpret_cast<uint2*>(&tA[0][row * SW_TS + c4]) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(&tA[1][row * SW_TS + c4]) = make_uint2(l0, l1);
+        *reinterpret_cast<uint2*>(&tA[row * SW_TS + c4]) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(&tA[64 * SW_TS + row * SW_TS + c4]) = make_uint2(l0, l1);
         split_f16x2(vb[j][0] * sb.x, vb[j][1] * sb.y, h0, l0);
         split_f16x2(vb[j][2] * sb.z, vb[j][3] * sb.w, h1, l1);
-        *reinterpret_cast<uint2*>(&tB[0][row * SW_TS + c4]) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(&tB[1][row * SW_TS + c4]) = make_uint2(l0, l1);
+        *reinterpret_cast<uint2*>(&tB[row * SW_TS + c4]) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(&tB[64 * SW_TS + row * SW_TS + c4]) = make_uint2(l0, l1);
       }
     }
     __syncthreads();
-    if (row0 + 64 < r_end) load_tile(row0 + 64);            // the next tile's global loads fly under this tile's MMAs
     // ---- this warp's 16 x 32 slice: contraction over the tile's 64 batch rows
     float hh[4][4], xx[4][4];
     zero_acc(hh, xx);
-    const uint32_t a_hi = smem_u32(&tA[0][0]), a_lo = smem_u32(&tA[1][0]);
-    const uint32_t b_hi = smem_u32(&tB[0][0]), b_lo = smem_u32(&tB[1][0]);
+    const uint32_t a_hi = smem_u32(tA), a_lo = smem_u32(tA + 64 * SW_TS);
+    const uint32_t b_hi = smem_u32(tB), b_lo = smem_u32(tB + 64 * SW_TS);
     // ldmatrix.trans lane addresses: matrices {k 0-7, k 8-15} x {col 0-7, col 8-15}
     const uint32_t a_off = (uint32_t)(((lane & 7) + ((lane >> 4) << 3)) * SW_TS + mt * 16 + (((lane >> 3) & 1) << 3)) * 2u;
     const uint32_t b_off = (uint32_t)(((lane & 7) + (((lane >> 3) & 1) << 3)) * SW_TS + nh * 32 + ((lane >> 4) << 3)) * 2u;
@@ -706,7 +733,12 @@ int launch_small_wgrad(SmallWgradBatch& b, int64_t R, cudaStream_t stream) {
   }
   ProfScope ps(TAG_SMALL_WGRAD, flops, stream, bytes);
   dim3 grid((unsigned)gx, (unsigned)b.nunits);
-  k_small_wgrad<<<grid, 256, 0, stream>>>(b.p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FP_CUDA_OK(cudaFuncSetAttribute(k_small_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
+    attr_set = true;
+  }
+  k_small_wgrad<<<grid, 256, SW_SMEM_BYTES, stream>>>(b.p);
   FP_LAUNCH_CHECK();
   return 0;
 }
