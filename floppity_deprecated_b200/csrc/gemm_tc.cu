@@ -54,7 +54,7 @@ template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
              const __grid_constant__ CUtensorMap mapBl, const fp_gemm_args g, int nkb_total, int nchunks, int vec_all,
-             long long* trace, int dbg) {
+             long long* trace, int dbg, int gfast) {
   // PAIR: the two CTAs of a cluster compute a 256 x 128 output block with cta_group::2 MMAs (rank 0 issues them): each CTA
   // loads its own 128 rows of A and only HALF of the B tile (64 rows), so a stage is 48 KB instead of 64 KB -- a
   // four-deep ring in the same 192 KB and a third less L2 -> shared-memory traffic per flop.  The single-CTA ring is
@@ -87,9 +87,22 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const int kb_per_chunk = (nkb_total + nchunks - 1) / nchunks;
   // rasterisation: concurrently running CTAs should share tiles of the LARGER operand stream, i.e. walk the
   // dimension of the smaller operand fastest (activations [M,K] vs weights [N,K]); the other one stays in L2
+  // `gfast` tiles of the fast dimension form a GROUP that sweeps the whole slow dimension before the next group starts:
+  // when neither operand fits the 126 MB L2 (c3's context projection: A 151 MB, B hi+lo 614 MB) the un-grouped order
+  // re-read ALL of A from DRAM for every tile of N -- 47 GB of DRAM reads for 3.4 GB of algorithmic bytes (ncu,
+  // profiles/r2n_ctx_gemm_ncu_full_summary.csv).  A group keeps its slice of the fast operand L2-resident.
   const bool m_fast = g.M <= (int64_t)g.N;
-  auto tile_m0 = [&](int64_t st) -> int64_t { return (m_fast ? (st % tiles_m) : (st / tiles_n)) * ROWS_M + (int64_t)rank * TC_BM; };
-  auto tile_n0 = [&](int64_t st) -> int { return (int)(m_fast ? (st / tiles_m) : (st % tiles_n)) * TC_BN; };
+  const int64_t tiles_f = m_fast ? tiles_m : (int64_t)tiles_n, tiles_s = m_fast ? (int64_t)tiles_n : tiles_m;
+  const int64_t gf = (gfast > 0 && gfast < tiles_f) ? gfast : tiles_f;
+  auto tile_fs = [&](int64_t st, int64_t& f, int64_t& sl) {
+    const int64_t per = gf * tiles_s;
+    const int64_t gi = st / per, idx = st - gi * per;
+    const int64_t gs = min(gf, tiles_f - gi * gf);
+    f = gi * gf + idx % gs;
+    sl = idx / gs;
+  };
+  auto tile_m0 = [&](int64_t st) -> int64_t { int64_t f, sl; tile_fs(st, f, sl); return (m_fast ? f : sl) * ROWS_M + (int64_t)rank * TC_BM; };
+  auto tile_n0 = [&](int64_t st) -> int { int64_t f, sl; tile_fs(st, f, sl); return (int)(m_fast ? sl : f) * TC_BN; };
 
   if (threadIdx.x == 0) {
     FP_TRACE(500);
@@ -365,7 +378,7 @@ static_assert(3 * TN_STAGES * 8 + 2 * 2 * 8 + 8 <= 256, "barrier block");
 // activations, so the splitter warps split BOTH (relu prologue on B for the relu'd activation operand).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const fp_gemm_args g,
-             int nkb_total, int nsplit, int vec_all, int dbg) {
+             int nkb_total, int nsplit, int vec_all, int dbg, int gm) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_a = smem_u32(smem);                                  // shared-space address of the ring
@@ -401,9 +414,24 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   // touched below this point
   pdl_wait();
 
+  // Item order.  gm == 0 (operands that fit the L2): the splits of one output tile run side by side, the tile stays hot.
+  // gm > 0 (c3's context weight gradient: A 2.9 GB, B 151 MB, C 307 MB): groups of gm M-tiles; inside a group the batch
+  // range is the SLOW index, so all concurrently running CTAs read the same ~1000 batch rows (the 8 MB slab of B and the
+  // group's slice of A stay in L2 while every tile of the group uses them) and the group's part of C stays in L2 across
+  // the ranges.  The split-minor order re-read all of B from DRAM for every M-tile: 45 GB of reads for 3.7 GB.
   auto item_decode = [&](int64_t w, int& m0, int& n0, int& kb0, int& kb1) {
-    const int sp = (int)(w % nsplit);
-    const int64_t t = w / nsplit;
+    int sp; int64_t t;
+    if (gm > 0) {
+      const int64_t per = (int64_t)gm * tiles_n * nsplit;
+      const int64_t gi = w / per, r = w - gi * per;
+      const int64_t gs = min((int64_t)gm, (int64_t)tiles_m - gi * gm);
+      sp = (int)(r / (gs * tiles_n));
+      const int64_t ti = r - (int64_t)sp * gs * tiles_n;
+      t = (gi * gm + ti / tiles_n) * tiles_n + ti % tiles_n;
+    } else {
+      sp = (int)(w % nsplit);
+      t = w / nsplit;
+    }
     m0 = (int)(t / tiles_n) * TC_BM;
     n0 = (int)(t % tiles_n) * TC_BN;
     kb0 = sp * kb_per_split;
@@ -778,6 +806,13 @@ static bool tc_supported(const fp_gemm_args* a) {
   return true;
 }
 
+// bytes of the operand slice a tile group keeps L2-resident (FLOPPITY_L2_GROUP_MB, default 40 of the 126 MB)
+static double l2_group_bytes() {
+  static double v = 0.0;
+  if (v == 0.0) { const char* e = getenv("FLOPPITY_L2_GROUP_MB"); v = 1e6 * ((e && atof(e) > 0.0) ? atof(e) : 40.0); }
+  return v;
+}
+
 // B_hi / B_lo: the pre-split weight matrix, same shape and ld as a->B
 int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, cudaStream_t stream) {
   if (!tc_enabled() || !tc_supported(a) || !B_hi || !B_lo) return FP_E_NOTREADY;
@@ -797,6 +832,14 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   // long contractions are chunked (see the kernel comment); only the plain / bias epilogue can be accumulated
   const bool plain = (a->flags & ~(FP_G_RELU_A | FP_G_BIAS | FP_G_TF32X3)) == 0;
   const int nchunks = (plain && nkb > TC_KCHUNK_BLOCKS) ? (nkb + TC_KCHUNK_BLOCKS - 1) / TC_KCHUNK_BLOCKS : 1;
+  // L2-aware tile order (see the kernel): group the fast dimension so that a group's slice of its operand is ~40 MB
+  int gfast = 0;
+  {
+    const bool m_fast = a->M <= (int64_t)a->N;
+    const double fast_bytes = m_fast ? 4.0 * (double)a->M * (double)a->K : 8.0 * (double)a->N * (double)a->K;
+    const double tile_bytes = (m_fast ? 4.0 * (pair ? 2 : 1) * TC_BM : 8.0 * TC_BN) * (double)a->K;
+    if (fast_bytes > 64e6 && !(g_tc_dbg & 128)) gfast = (int)std::max(1.0, l2_group_bytes() / tile_bytes);
+  }
   const int64_t tiles = ((a->M + (pair ? 2 : 1) * TC_BM - 1) / ((pair ? 2 : 1) * TC_BM)) * ((a->N + TC_BN - 1) / TC_BN);
   const int grid = pair ? 2 * (int)std::min<int64_t>(tiles, num_sms() / 2) : (int)std::min<int64_t>(tiles, num_sms());
   ProfScope ps(TAG_GEMM_TC_NT, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
@@ -817,9 +860,9 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     if (pair)                                                                                                         \
-      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true>, grid, stream, 2, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0))); \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true>, grid, stream, 2, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
     else                                                                                                              \
-      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false>, grid, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0))); \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false>, grid, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
     break;                                                                                                            \
   }
   int epi = a->flags & FP_EPI_MASK;
@@ -874,10 +917,14 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   const int kbps = (nkb + nsplit - 1) / nsplit;
   nsplit = (nkb + kbps - 1) / kbps;                        // no empty splits
   const int grid = (int)std::min<int64_t>(tiles * nsplit, num_sms());
+  // L2-aware item order for operands that do not fit the L2 (see the kernel): groups of gm M-tiles whose part of C is ~40 MB
+  int gm = 0;
+  if (4.0 * (double)a->K * ((double)a->M + (double)a->N) > 96e6 && tiles > 2 * num_sms() && !(g_tc_dbg & 128))
+    gm = (int)std::max(1.0, l2_group_bytes() / (4.0 * TC_BM * (double)a->N));
   int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
   if ((a->flags & FP_G_COLSUM_A) && (reinterpret_cast<uintptr_t>(a->U) & 15)) vec_all = 0;
   ProfScope ps(TAG_GEMM_TC_TN, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
-  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0)));
+  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
   FP_LAUNCH_CHECK();
   return 0;
 }

@@ -161,7 +161,8 @@ int fp_set_precision(int32_t single_pass);
 int fp_tc_set_trace(void* buf);
 /* debug: ablation switches for timing experiments on the tensor-core GEMM kernels (1 skip the operand conversion, 2 skip the
  * epilogue's stores / reductions, 4 two of three products, 8 (NT) do not load B_lo: results are wrong while any of these
- * is set) and 32 = run long-contraction NT GEMMs as CTA pairs (cta_group::2; correct, measured slower, off by default) */
+ * is set), 32 = run long-contraction NT GEMMs as CTA pairs (cta_group::2; correct, measured slower, off by default) and
+ * 128 = the tile order that ignores the L2 (the round-1 order; results stay correct) */
 int fp_tc_set_debug(int32_t bits);
 /* debug: SM-clock stamps of CTA 0 of the fused conditioner kernel (cond_fused.cu) into a device int64[512] (NULL = off) */
 int fp_cf_set_trace(void* buf);

@@ -1,7 +1,7 @@
 """Timing ablation of the two GEMMs that carry half of the c3 training step (context projection forward, NT, and its weight
 gradient, TN) plus the hidden-512 block GEMMs.  Debug bits (fp_tc_set_debug; results are wrong while set):
 1 = splitter warps do no work, 2 = epilogue skips its global stores / reductions, 4 = two of three products,
-8 = (NT) the B_lo tile is not loaded, 32 = (NT) CTA pairs (cta_group::2; results stay correct)."""
+8 = (NT) the B_lo tile is not loaded, 32 = (NT) CTA pairs (cta_group::2; results stay correct), 128 = the tile order that ignores the L2 (results stay correct)."""
 import ctypes, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from floppity_deprecated_b200 import _lib
@@ -30,7 +30,7 @@ def nt(M, N, K, flags=0):
     a.A, a.lda, a.a_kmajor, a.B, a.ldb, a.b_kmajor = A.data_ptr(), K, 1, B.data_ptr(), K, 1
     a.C, a.ldc, a.M, a.N, a.K, a.flags, a.bias, a.split_k = C.data_ptr(), N, M, N, K, flags | _lib.G_BIAS, bias.data_ptr(), 1
     out = {}
-    for bits in (0, 1, 2, 4, 8, 12, 15, 32, 33):
+    for bits in (0, 128, 1, 4, 15, 32):
         L.fp_tc_set_debug(bits)
         us = timeit(lambda: L.fp_gemm_tc(ctypes.byref(a), hi.data_ptr(), lo.data_ptr(), s))
         out[bits] = (round(us, 1), round(2.0 * M * N * K / us / 1e6, 1))
@@ -45,7 +45,7 @@ def tn(M, N, R):
     a.A, a.lda, a.a_kmajor, a.B, a.ldb, a.b_kmajor = A.data_ptr(), M, 0, B.data_ptr(), N, 0
     a.C, a.ldc, a.M, a.N, a.K, a.flags, a.split_k = C.data_ptr(), N, M, N, R, _lib.G_ATOMIC, 1
     out = {}
-    for bits in (0, 1, 2, 4, 7):
+    for bits in (0, 128, 1, 4, 7):
         L.fp_tc_set_debug(bits)
         us = timeit(lambda: L.fp_gemm_tc_tn(ctypes.byref(a), s))
         out[bits] = (round(us, 1), round(2.0 * M * N * R / us / 1e6, 1))
