@@ -914,6 +914,17 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   nsplit = std::min(nsplit, std::max(1, nkb * TN_BK / 128));   // at least 128 batch rows per split
   constexpr int kchunk = TC_KCHUNK_BLOCKS * TC_BK / TN_BK;  // bound the truncating accumulation chain (1024 batch rows)
   nsplit = std::max(nsplit, (nkb + kchunk - 1) / kchunk);
+  // Whole waves: with a handful of output tiles (c3's 512 x 512 blocks: 16 tiles x 19 splits = 304 items on 148 SMs =
+  // 2.05 waves) the last round runs almost empty.  Take the split count in [nsplit, 2 nsplit] that fills its rounds best.
+  if (tiles * nsplit > num_sms() && tiles < num_sms()) {
+    int best = nsplit; double best_eff = 0.0;
+    for (int c = nsplit; c <= 2 * nsplit && c * 4 <= nkb; ++c) {
+      const int64_t items = tiles * c;
+      const double eff = (double)items / (double)(((items + num_sms() - 1) / num_sms()) * num_sms());
+      if (eff > best_eff + 0.02) { best_eff = eff; best = c; }
+    }
+    nsplit = best;
+  }
   const int kbps = (nkb + nsplit - 1) / nsplit;
   nsplit = (nkb + kbps - 1) / kbps;                        // no empty splits
   const int grid = (int)std::min<int64_t>(tiles * nsplit, num_sms());

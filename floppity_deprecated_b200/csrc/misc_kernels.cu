@@ -102,6 +102,30 @@ __global__ void k_glu_bwd(const float* __restrict__ dh, const float* __restrict_
   }
   dG[cr * ldg + j] = acc * sg * (1.f - sg);
 }
+// float4 version (H % 4 == 0, ldh % 4 == 0, ldg % 4 == 0, 16-byte aligned bases): four columns per thread
+__global__ void k_glu_bwd4(const float* __restrict__ dh, const float* __restrict__ u, const float* __restrict__ G,
+                           int64_t ldg, float* __restrict__ du, float* __restrict__ dG, int64_t Rc, int A, int H, int ldh,
+                           int sig_given) {
+  const int H4 = H >> 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Rc * H4) return;
+  const int64_t cr = i / H4; const int j = (int)(i - cr * H4) * 4;
+  const float4 g = *reinterpret_cast<const float4*>(G + cr * ldg + j);
+  float4 sg = g;
+  if (!sig_given) {
+    sg.x = 1.f / (1.f + expf(-g.x)); sg.y = 1.f / (1.f + expf(-g.y)); sg.z = 1.f / (1.f + expf(-g.z)); sg.w = 1.f / (1.f + expf(-g.w));
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int a = 0; a < A; ++a) {
+    const int64_t r = cr * A + a;
+    const float4 d = *reinterpret_cast<const float4*>(dh + r * ldh + j);
+    const float4 uu = *reinterpret_cast<const float4*>(u + r * ldh + j);
+    *reinterpret_cast<float4*>(du + r * ldh + j) = make_float4(d.x * sg.x, d.y * sg.y, d.z * sg.z, d.w * sg.w);
+    acc.x = fmaf(d.x, uu.x, acc.x); acc.y = fmaf(d.y, uu.y, acc.y); acc.z = fmaf(d.z, uu.z, acc.z); acc.w = fmaf(d.w, uu.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(dG + cr * ldg + j) = make_float4(acc.x * sg.x * (1.f - sg.x), acc.y * sg.y * (1.f - sg.y),
+                                                              acc.z * sg.z * (1.f - sg.z), acc.w * sg.w * (1.f - sg.w));
+}
 // in place: gate slots (every slot but the first of each layer) of the context projection [Rc, T*S*H] -> sigmoid
 __global__ void k_gate_sigmoid(float* __restrict__ ctx_all, int64_t n4, int H, int S) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -494,6 +518,11 @@ int launch_rows_affine(const float* x, const float* M, const float* pre, float s
 int launch_glu_bwd(const float* dh, const float* u, const float* G, int64_t ldg, float* du, float* dG, int64_t Rc, int A,
                    int H, int ldh, int sig_given, cudaStream_t s) {
   ProfScope ps(TAG_OTHER, 0.0, s);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if ((H & 3) == 0 && (ldh & 3) == 0 && (ldg & 3) == 0 && al16(dh) && al16(u) && al16(G) && al16(du) && al16(dG)) {
+    k_glu_bwd4<<<nblk(Rc * (H / 4), 256), 256, 0, s>>>(dh, u, G, ldg, du, dG, Rc, A, H, ldh, sig_given);
+    FP_LAUNCH_CHECK(); return 0;
+  }
   k_glu_bwd<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, u, G, ldg, du, dG, Rc, A, H, ldh, sig_given);
   FP_LAUNCH_CHECK(); return 0;
 }

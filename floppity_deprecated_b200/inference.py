@@ -559,7 +559,8 @@ class DirectPosterior:
             st = status.tolist()                      # (the count above already synchronised)
             _check_fp16_range(st)
             if st[0]:
-                raise AssertionError(f"the flow produced {st[0]} non-finite samples")
+                raise AssertionError(f"the flow produced {st[0]} non-finite samples ({st[1]} negative spline discriminants: "
+                                     "upstream's `assert (discriminant >= 0).all()`)")
             num_total += bs
             num_remaining = num_samples - num_accepted
             acceptance_rate = num_accepted / num_total
