@@ -510,7 +510,8 @@ def main():
             out_extra["posterior_raw_draws_per_s"] = world * zr.shape[0] * 8 / (ms_r * 1e-3)
             out_extra["posterior_samples_per_s"] = out_extra["posterior_raw_draws_per_s"] * acc
         out_extra["posterior_acceptance_rate"] = acc
-        th_q = post.sample((1 << 21,))
+        th_q = net.inverse_rows(torch.randn(1 << 21, c2.cfg.D, device=dev), net._standardize(x_obs.to(dev)))      # raw flow draws
+        th_q = torch.nan_to_num(th_q, nan=0.0, posinf=3.0, neginf=-3.0)
         ms_l = timed(lambda i: post.log_prob(th_q, norm_posterior=False), 8)
         out_extra["log_prob_per_s"] = world * th_q.shape[0] * 8 / (ms_l * 1e-3)
         out_extra["sampling_workload"] = (f"c2 flow after 400 seeded maximum-likelihood steps (rank 0's weights broadcast), {n_total} accepted "
