@@ -481,7 +481,7 @@ def main():
         c2 = build_workload("c2")
         # a short, seeded training run with the round-0 loss (maximum likelihood, what floppity.py:220 runs): the same
         # flow -- rank 0's -- at every N, so accepted samples/s are comparable across N
-        pre = _TrainEngine(c2.net, c2.prior, 4096, False, c2.cfg.atoms, True, 1e-3, 5.0)
+        pre = _TrainEngine(c2.net, c2.prior, 4096, False, c2.cfg.atoms, True, 2e-3, 5.0)
         gp = torch.Generator(device=dev).manual_seed(99)
         for i in range(400):
             pre.step(torch.randint(0, c2.rows, (4096,), device=dev, generator=gp), c2.theta_dev, c2.x_dev, c2.masks_dev)
