@@ -510,7 +510,7 @@ def main():
         net = c2.net.eval()
         x_obs = x_fix if x_fix is not None else make_data("c2", 4096, 0)[2][:1]      # ONE observation for every rank
         post = fb.DirectPosterior(net, c2.prior, max_sampling_batch_size=1 << 22).set_default_x(x_obs)
-        n_total = 1 << 24
+        n_total = (1 << 24) * world            # weak scaling, like the training leg: 2^24 accepted samples per GPU
         lo, hi = fdist.shard_rows(n_total) if world > 1 else (0, n_total)
         post.sample((1 << 16,))
         acc = post.leakage_correction(x_obs, num_rejection_samples=1 << 18)
