@@ -51,7 +51,8 @@ class GemmArgs(Structure):
                 ("Rsd", c_void_p), ("ldr", c_int64),
                 ("U", c_void_p), ("ldu", c_int64),
                 ("Msk", c_void_p), ("ldm", c_int64),
-                ("split_k", c_int32), ("mask_scale", c_float), ("drop_p", c_float), ("drop_seed", c_uint64)]
+                ("split_k", c_int32), ("mask_scale", c_float), ("drop_p", c_float), ("drop_seed", c_uint64),
+                ("a_scale", c_void_p), ("status", c_void_p)]
 
 
 _CFG = POINTER(NsfConfig)
@@ -72,6 +73,9 @@ SIGNATURES = {
     "fp_gemm": (c_int32, [POINTER(GemmArgs), _P]),
     "fp_gemm_tc": (c_int32, [POINTER(GemmArgs), _P, _P, _P]),
     "fp_split_tf32": (c_int32, [_P, _P, _P, c_int64, _P]),
+    "fp_gemm_tc16": (c_int32, [POINTER(GemmArgs), _P, _P, _P]),
+    "fp_split_f16": (c_int32, [_P, _P, _P, c_int64, _P]),
+    "fp_gemm_tc16_tn": (c_int32, [POINTER(GemmArgs), _P]),
     "fp_gemm_tc_tn": (c_int32, [POINTER(GemmArgs), _P]),
     "fp_tc_set_trace": (c_int32, [_P]),
     "fp_dropout_mask": (c_int32, [_P, c_int64, c_int32, c_float, c_uint64, _P]),

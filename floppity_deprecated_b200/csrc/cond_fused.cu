@@ -93,10 +93,6 @@ __device__ __forceinline__ void tmem_st_8(uint32_t taddr, const uint32_t (&v)[8]
                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-// instruction descriptor for kind::f16: D = f32, A = B = f16, both K-major
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -104,9 +100,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
                : "memory");
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // One column half (4 warps, 128 threads) of the epilogue group stages 64-column pieces of a [128 x *] result in its
 // own two shared-memory slots and hands them to the TMA store engine.

@@ -50,8 +50,13 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES + 1024 /*
 // MMAs: the big hi*hi products get their own accumulator (the small cross terms cannot disturb it) and
 // contractions longer than 1024 are cut into chunks whose partial sums are added in fp32 by the epilogue
 // (only for the plain/bias epilogue, which is all the long-K context projection needs).
-template <int EPI, bool PAIR>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// F16: 16-bit operand pieces (3xFP16, see tc_common.cuh): a stage holds 64 contraction indices -- the raw fp32 A tile as two
+// 16 KB boxes, converted IN PLACE into the fp16 hi tile (+0) and the scaled-residual lo tile (+16 KB), and the pre-split
+// fp16 B_hi / B_lo tiles (16 KB each): the same 64 KB stage carries twice the contraction depth, the MMAs of a k-block
+// take half the tensor-pipe time, and the TMA moves 32 instead of 48 KB per 32 contraction indices.
+constexpr int TC16_THREADS = TC_THREADS + 128;            // 3xFP16 variant: eight converting warps
+template <int EPI, bool PAIR, bool F16>
+__global__ void __launch_bounds__(F16 ? TC16_THREADS : TC_THREADS, 1)
 k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
              const __grid_constant__ CUtensorMap mapBl, const fp_gemm_args g, int nkb_total, int nchunks, int vec_all,
              long long* trace, int dbg, int gfast) {
@@ -64,6 +69,8 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   constexpr int B_TILE = BROWS * TC_BK * 4;
   constexpr int STAGE = 2 * TC_TILE_BYTES + 2 * B_TILE;       // A (raw -> hi), A_lo, B_hi, B_lo
   constexpr int STAGES = TC_STAGES * TC_STAGE_BYTES / STAGE;
+  constexpr int NSPLITW = F16 ? 8 : 4;                        // converting warps 2 .. 2 + NSPLITW - 1, then eight epilogue warps
+  constexpr int EPIW0 = 2 + NSPLITW;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_a = smem_u32(smem);                                  // shared-space address of the ring
@@ -106,7 +113,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 
   if (threadIdx.x == 0) {
     FP_TRACE(500);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], PAIR ? 8 : 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&ready[s], PAIR ? 8 : NSPLITW); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 16 : 8); }
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -136,10 +143,18 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* sb = smem + s * STAGE;
+          if (F16) {
+            mbar_expect_tx(&full_raw[s], 4 * TC_TILE_BYTES);
+            tma_load_2d(sb, &mapA, kb * 64, (int)m0, &full_raw[s]);
+            tma_load_2d(sb + TC_TILE_BYTES, &mapA, kb * 64 + 32, (int)m0, &full_raw[s]);
+            tma_load_2d(sb + 2 * TC_TILE_BYTES, &mapBh, kb * 64, n0, &full_raw[s]);
+            tma_load_2d(sb + 3 * TC_TILE_BYTES, &mapBl, kb * 64, n0, &full_raw[s]);
+          } else {
           mbar_expect_tx(&full_raw[s], TC_TILE_BYTES + ((dbg & 8) ? 1 : 2) * B_TILE);
           tma_load_2d(sb, &mapA, kb * TC_BK, (int)m0, &full_raw[s]);
           tma_load_2d(sb + 2 * TC_TILE_BYTES, &mapBh, kb * TC_BK, n0, &full_raw[s]);
           if (!(dbg & 8)) tma_load_2d(sb + 2 * TC_TILE_BYTES + B_TILE, &mapBl, kb * TC_BK, n0, &full_raw[s]);
+          }
           if (it < 60) FP_TRACE(it * 8 + 0);
         }
       }
@@ -147,7 +162,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(ROWS_M, TC_BN);
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(ROWS_M, TC_BN) : make_idesc_tf32(ROWS_M, TC_BN);
       uint32_t it = 0, tile_it = 0;
       for (int64_t st = cta_id; st < n_super; st += cta_step) {
         for (int kc = 0; kc < nchunks; ++kc, ++tile_it) {
@@ -174,7 +189,11 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             for (int k = 0; k < TC_BK / 8; ++k) {
               const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per UMMA_K inside the swizzle row
               const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (PAIR) {
+              if (F16) {          // 32 bytes per k-step = 16 fp16 contraction indices
+                umma_f16(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
+                if (!(dbg & 64)) umma_f16(t_x, a_lo + adv, b_hi + adv, idesc, acc);
+                if (!(dbg & (4 | 64))) umma_f16(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
+              } else if (PAIR) {
                 umma_tf32_pair(t_hh, a_hi + adv, b_hi + adv, idesc, acc);
                 if (!(dbg & 64)) umma_tf32_pair(t_x, a_lo + adv, b_hi + adv, idesc, acc);
                 if (!(dbg & (4 | 64))) umma_tf32_pair(t_x, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -193,10 +212,12 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
       }
     }
-  } else if (warp < 6) {
-    // ===== splitter warps 2..5: relu prologue + TF32 hi/lo split of the A tile, in place =====
+  } else if (warp < EPIW0) {
+    // ===== splitter warps: relu prologue + hi/lo split of the A tile, in place =====
     const int tid_s = threadIdx.x - 64;       // 0..127
     const bool relu_a = (g.flags & FP_G_RELU_A) != 0;
+    const float a_s = (F16 && g.a_scale) ? __ldg(g.a_scale) : 1.f;      // power-of-two operand scale (gradient operands)
+    float amax = 0.f;                                                     // fp16 range guard
     const int pf_fl = (EPI >= 0 ? EPI : g.flags) & (FP_G_GLU_RES | FP_G_RELUMASK | FP_G_ACCUM);
     const int pf_bytes = (pf_fl && vec_all) ? TC_BN * 4 : 0;
     uint32_t it = 0;
@@ -220,7 +241,48 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (tid_s == 0 && it < 60) FP_TRACE(it * 8 + 1);
         const uint32_t aA = smem_a + (uint32_t)(s * STAGE) + (uint32_t)tid_s * 16u;
         float4 v[TC_TILE_BYTES / 16 / 128];
-        if (!(dbg & 1)) {
+        if (F16) {
+          // (row, 8-index chunk) items; a quarter-warp takes chunks 0-3 of an even row and chunks 4-7 of the next (or the
+          // other way round): its eight 16-byte reads and its eight 16-byte writes each cover all 32 banks exactly once
+          const uint32_t sA = smem_a + (uint32_t)(s * STAGE);
+          const int q8 = tid_s >> 3, u = tid_s & 7;
+          float4 raw[8];
+          if (!(dbg & 1)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (i >> 1) * 64 + 2 * q8 + (u >> 2);
+            const int cp = (u & 3) + 4 * ((u >> 2) ^ (i & 1));
+            const uint32_t rowa = sA + (uint32_t)(cp >> 2) * (uint32_t)TC_TILE_BYTES + (uint32_t)r * 128u;
+            const uint32_t cc = 2u * (uint32_t)(cp & 3), sw = (uint32_t)(r & 7);
+            raw[2 * i] = lds128(rowa + ((cc ^ sw) << 4));
+            raw[2 * i + 1] = lds128(rowa + (((cc + 1u) ^ sw) << 4));
+          }
+          }
+          // hi / lo row r overwrite exactly the raw bytes of row r (both boxes), and a row pair belongs to ONE quarter-warp
+          // over its two passes: the in-place hazard is warp-local
+          __syncwarp();
+          if (!(dbg & 1)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (i >> 1) * 64 + 2 * q8 + (u >> 2);
+            const int cp = (u & 3) + 4 * ((u >> 2) ^ (i & 1));
+            float4 a = raw[2 * i], b = raw[2 * i + 1];
+            a.x *= a_s; a.y *= a_s; a.z *= a_s; a.w *= a_s; b.x *= a_s; b.y *= a_s; b.z *= a_s; b.w *= a_s;
+            if (relu_a) {
+              a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+              b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+            }
+            amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                                     fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+            uint4 hi, lo;
+            split_f16x2(a.x, a.y, hi.x, lo.x); split_f16x2(a.z, a.w, hi.y, lo.y);
+            split_f16x2(b.x, b.y, hi.z, lo.z); split_f16x2(b.z, b.w, hi.w, lo.w);
+            const uint32_t dst = sA + (uint32_t)r * 128u + (((uint32_t)cp ^ (uint32_t)(r & 7)) << 4);
+            sts128u(dst, hi);
+            sts128u(dst + (uint32_t)TC_TILE_BYTES, lo);
+          }
+          }
+        } else if (!(dbg & 1)) {
 #pragma unroll
         for (int i = 0; i < TC_TILE_BYTES / 16 / 128; ++i) v[i] = lds128(aA + (uint32_t)i * 2048u);
 #pragma unroll
@@ -238,11 +300,12 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (tid_s == 0 && it < 60) FP_TRACE(it * 8 + 2);
       }
     }
+    if (F16 && g.status && !(amax <= 6.0e4f)) atomicAdd(g.status + 2, 1);      // also counts NaN operands
   } else {
     // ===== epilogue warps 6..13: two warps per TMEM lane quarter, each owning one 64-column half =====
     // Warp-private: 32 accumulator rows x 32 columns go TMEM -> registers -> this warp's XOR-swizzled slab ->
     // registers with 8 lanes per row, so every global access of a warp covers four full 128-byte row segments.
-    const int ew = warp - 6;                   // 0..7
+    const int ew = warp - EPIW0;               // 0..7
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int half = ew >> 2;                  // column half
     const uint32_t slabw = cs_a + (uint32_t)ew * (uint32_t)TC_CS_WARP_BYTES;
@@ -252,6 +315,9 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int cch = lane & 7;                  // float4 chunk within the 32-column slab row
     const EpiArgs ea = make_epi(g);
     const bool single = (dbg & 64) != 0;       // single TF32 pass: the cross-term accumulator is never written
+    // 3xFP16: the cross terms carry the 2^11 of the scaled residual; the operand scale is undone on the sum
+    const float x_s = F16 ? FP16_LO_UNSCALE : 1.f;
+    const float o_s = (F16 && g.a_scale) ? 1.f / __ldg(g.a_scale) : 1.f;
     const int fl_rt = g.flags & FP_EPI_MASK;
     const bool need_ctx = ((EPI >= 0 ? EPI : fl_rt) & (FP_G_ADD_CTX | FP_G_GLU_RES)) != 0;
     const uint32_t cdiv = ea.ctx_div <= 0 ? 0xFFFFFFFFu : (uint32_t)ea.ctx_div;
@@ -302,7 +368,9 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               sts128(st_base + ((((uint32_t)(p * 4 + j)) ^ sw_st) << 4),
-                     single ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                     single ? make_float4(v[4 * j] * o_s, v[4 * j + 1] * o_s, v[4 * j + 2] * o_s, v[4 * j + 3] * o_s)
+                     : F16  ? make_float4(fmaf(x[4 * j], x_s, v[4 * j]) * o_s, fmaf(x[4 * j + 1], x_s, v[4 * j + 1]) * o_s,
+                                          fmaf(x[4 * j + 2], x_s, v[4 * j + 2]) * o_s, fmaf(x[4 * j + 3], x_s, v[4 * j + 3]) * o_s)
                             : make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
                                           v[4 * j + 3] + x[4 * j + 3]));
           }
@@ -376,6 +444,11 @@ static_assert(3 * TN_STAGES * 8 + 2 * 2 * 8 + 8 <= 256, "barrier block");
 // (MN-major for the tensor core), contraction over r split across CTAs, partial tiles added with vector atomics.
 // Work item = (output tile, k-split); every CTA walks items blockIdx.x, +gridDim.x, ...  Both operands are raw fp32
 // activations, so the splitter warps split BOTH (relu prologue on B for the relu'd activation operand).
+// F16: 3xFP16 operand pieces (see k_gemm_tc_nt): a stage holds 64 batch rows -- the raw fp32 tiles of A and B (four boxes of
+// 32 columns x 64 rows each, 32 KB per operand) are converted IN PLACE into MN-major fp16 hi (first 16 KB) and scaled-residual
+// lo (second 16 KB) tiles of two 64-column atoms; the four output rows of a batch row (hi / lo of two atoms) occupy exactly
+// the bytes of its four raw rows, and a warp converts whole row pairs, so the in-place hazard is warp-local.
+template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const fp_gemm_args g,
              int nkb_total, int nsplit, int vec_all, int dbg, int gm) {
@@ -448,18 +521,27 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const uint32_t ph = (it / TN_STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* sb = smem + s * TN_STAGE_BYTES;
+          if (F16) {
+            mbar_expect_tx(&full_raw[s], 4 * TN_TILE_BYTES);
+#pragma unroll
+            for (int gidx = 0; gidx < 4; ++gidx) {     // four boxes of 32 columns x 64 batch rows per operand
+              tma_load_2d(sb + gidx * 8192, &mapA, m0 + gidx * 32, kb * 64, &full_raw[s]);
+              tma_load_2d(sb + 2 * TN_TILE_BYTES + gidx * 8192, &mapB, n0 + gidx * 32, kb * 64, &full_raw[s]);
+            }
+          } else {
           mbar_expect_tx(&full_raw[s], 2 * TN_TILE_BYTES);
 #pragma unroll
           for (int gidx = 0; gidx < 4; ++gidx) {     // four 32-float MN groups per operand
             tma_load_2d(sb + gidx * GROUP_BYTES, &mapA, m0 + gidx * 32, kb * TN_BK, &full_raw[s]);
             tma_load_2d(sb + 2 * TN_TILE_BYTES + gidx * GROUP_BYTES, &mapB, n0 + gidx * 32, kb * TN_BK, &full_raw[s]);
           }
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN, 1, 1);
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(TC_BM, TC_BN, 1, 1) : make_idesc_tf32(TC_BM, TC_BN, 1, 1);
       uint32_t it = 0, tile_it = 0;
       for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
         int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
@@ -476,6 +558,20 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           mbar_wait(&ready[s], ph);
           tcgen05_fence_after();
           uint8_t* sb = smem + s * TN_STAGE_BYTES;
+          if (F16) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                          // 16 batch rows per MMA = two 8-row groups of 1024 B
+              const uint32_t koff = (uint32_t)k * 2048u;
+              const uint64_t a_hi = make_mnmajor_desc16(sb + koff, 8192u);
+              const uint64_t a_lo = make_mnmajor_desc16(sb + TN_TILE_BYTES + koff, 8192u);
+              const uint64_t b_hi = make_mnmajor_desc16(sb + 2 * TN_TILE_BYTES + koff, 8192u);
+              const uint64_t b_lo = make_mnmajor_desc16(sb + 3 * TN_TILE_BYTES + koff, 8192u);
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              umma_f16(t_hh, a_hi, b_hi, idesc, acc);
+              if (!(dbg & 64)) umma_f16(t_x, a_lo, b_hi, idesc, acc);
+              if (!(dbg & (4 | 64))) umma_f16(t_x, a_hi, b_lo, idesc, 1u);
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < TN_BK / 8; ++k) {
             const uint32_t koff = (uint32_t)k * 1024u;             // 8 k-rows of 128 B
@@ -508,6 +604,85 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const bool colsum = (g.flags & FP_G_COLSUM_A) != 0;
     float* const cs_out = g.U;
     uint32_t it = 0;
+    if (F16) {
+      // One warp converts one PAIR of batch rows of one operand per pass (2 x 128 columns = 32 items of 8 columns): lane ->
+      // atom a (64 columns), row of the pair, 8-column chunk cp; a quarter-warp takes chunks 0-3 of one row and 4-7 of the
+      // other, so its eight 16-byte reads and writes cover all 32 banks once.  Lanes l and l ^ 12 own the same columns.
+      const int sw_w = warp - 2;                                   // 0..7
+      const int qw = lane >> 3, u = lane & 7;
+      const int at = qw >> 1, rr = u >> 2;                         // atom, row within the pair
+      const int cp = (u & 3) + 4 * (rr ^ (qw & 1));                // 8-column chunk within the atom
+      const uint32_t src_off = (uint32_t)(2 * at + (cp >> 2)) * 8192u;      // raw box of these 8 columns
+      const uint32_t cc = 2u * (uint32_t)(cp & 3);
+      const float a_s = g.a_scale ? __ldg(g.a_scale) : 1.f;
+      float amax = 0.f;
+      for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
+        float cs8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % TN_STAGES;
+          const uint32_t ph = (it / TN_STAGES) & 1u;
+          mbar_wait(&full_raw[s], ph);
+          const uint32_t sS = smem_a + (uint32_t)(s * TN_STAGE_BYTES);
+          // pass p = 0..7: operand (p >> 2), row pair 4 * sw_w + (p & 3) + ... : 32 row pairs per operand over 8 warps
+          float4 raw[16];
+          if (!(dbg & 1)) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const int row = 2 * (8 * (p & 3) + sw_w) + rr;
+            const uint32_t ra = sS + (uint32_t)(p >> 2) * (uint32_t)(2 * TN_TILE_BYTES) + src_off + (uint32_t)row * 128u;
+            const uint32_t sw = (uint32_t)(row & 7);
+            raw[2 * p] = lds128(ra + ((cc ^ sw) << 4));
+            raw[2 * p + 1] = lds128(ra + (((cc + 1u) ^ sw) << 4));
+          }
+          }
+          __syncwarp();
+          if (!(dbg & 1)) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const int row = 2 * (8 * (p & 3) + sw_w) + rr;
+            float4 a = raw[2 * p], b = raw[2 * p + 1];
+            if (p < 4) {
+              a.x *= a_s; a.y *= a_s; a.z *= a_s; a.w *= a_s; b.x *= a_s; b.y *= a_s; b.z *= a_s; b.w *= a_s;
+              cs8[0] += a.x; cs8[1] += a.y; cs8[2] += a.z; cs8[3] += a.w; cs8[4] += b.x; cs8[5] += b.y; cs8[6] += b.z; cs8[7] += b.w;
+            } else if (relu_b) {
+              a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+              b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+            }
+            amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                                     fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+            uint4 hi, lo;
+            split_f16x2(a.x, a.y, hi.x, lo.x); split_f16x2(a.z, a.w, hi.y, lo.y);
+            split_f16x2(b.x, b.y, hi.z, lo.z); split_f16x2(b.z, b.w, hi.w, lo.w);
+            const uint32_t dst = sS + (uint32_t)(p >> 2) * (uint32_t)(2 * TN_TILE_BYTES) + (uint32_t)at * 8192u + (uint32_t)row * 128u +
+                                 (((uint32_t)cp ^ (uint32_t)(row & 7)) << 4);
+            sts128u(dst, hi);
+            sts128u(dst + (uint32_t)TN_TILE_BYTES, lo);
+          }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
+        }
+        if (colsum && n0 == 0 && kb0 < kb1) {
+          const float inv = 1.f / a_s;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cs8[j] = (cs8[j] + __shfl_xor_sync(0xffffffffu, cs8[j], 12)) * inv;
+          if (!(qw & 1)) {                                          // one lane of each (l, l ^ 12) pair
+            const int m = m0 + 64 * at + 8 * cp;
+            if (vec_all && m + 7 < (int)g.M) {
+              red_add_f32x4(cs_out + m, make_float4(cs8[0], cs8[1], cs8[2], cs8[3]));
+              red_add_f32x4(cs_out + m + 4, make_float4(cs8[4], cs8[5], cs8[6], cs8[7]));
+            } else {
+              for (int j = 0; j < 8; ++j) if (m + j < (int)g.M) red_add_f32(cs_out + m + j, cs8[j]);
+            }
+          }
+        }
+      }
+      if (g.status && !(amax <= 6.0e4f)) atomicAdd(g.status + 2, 1);
+    } else
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
       int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
       float4 cs[4];
@@ -571,6 +746,8 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int rsub = lane >> 3, cch = lane & 7;
     float* const gC = g.C; const int64_t g_ldc = g.ldc, gM = g.M; const int gN = g.N;
     const bool single = (dbg & 64) != 0;
+    const float x_s = F16 ? FP16_LO_UNSCALE : 1.f;
+    const float o_s = (F16 && g.a_scale) ? 1.f / __ldg(g.a_scale) : 1.f;
     uint32_t tile_it = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
       int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
@@ -592,7 +769,9 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(st_base + ((((uint32_t)(p * 4 + j)) ^ sw_st) << 4),
-                   single ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                   single ? make_float4(v[4 * j] * o_s, v[4 * j + 1] * o_s, v[4 * j + 2] * o_s, v[4 * j + 3] * o_s)
+                   : F16  ? make_float4(fmaf(x[4 * j], x_s, v[4 * j]) * o_s, fmaf(x[4 * j + 1], x_s, v[4 * j + 1]) * o_s,
+                                        fmaf(x[4 * j + 2], x_s, v[4 * j + 2]) * o_s, fmaf(x[4 * j + 3], x_s, v[4 * j + 3]) * o_s)
                           : make_float4(v[4 * j] + x[4 * j], v[4 * j + 1] + x[4 * j + 1], v[4 * j + 2] + x[4 * j + 2],
                                         v[4 * j + 3] + x[4 * j + 3]));
         }
@@ -652,6 +831,23 @@ __global__ void k_split_tf32(const float* __restrict__ x, float* __restrict__ hi
     float h = tf32_round(v);
     hi[i] = h;
     lo[i] = v - h;
+  }
+}
+
+// fp16 pieces for the 3xFP16 GEMMs: hi = fp16(x), lo = fp16((x - hi) * 2^11)
+__global__ void k_split_f16(const float* __restrict__ x, uint32_t* __restrict__ hi2, uint32_t* __restrict__ lo2, int64_t n) {
+  const int64_t np = n >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = *reinterpret_cast<const float2*>(x + 2 * i);
+    uint32_t h, l;
+    split_f16x2(v.x, v.y, h, l);
+    hi2[i] = h; lo2[i] = l;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    uint32_t h, l;
+    split_f16x2(x[n - 1], 0.f, h, l);
+    reinterpret_cast<uint16_t*>(hi2)[n - 1] = (uint16_t)(h & 0xFFFFu);
+    reinterpret_cast<uint16_t*>(lo2)[n - 1] = (uint16_t)(l & 0xFFFFu);
   }
 }
 
@@ -770,12 +966,18 @@ bool tc_single_pass();        // flow_engine.cu (fp_set_mode): reduced-precision
 // prefetch) while the previous kernel in the stream drains; it calls griddepcontrol.wait before touching memory.
 // FLOPPITY_PDL=0 falls back to plain stream order.
 template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_n(void (*kernel)(KArgs...), int grid, int threads, cudaStream_t stream, int cluster, Args... args);
+template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, cudaStream_t stream, int cluster, Args... args) {
+  return launch_pdl_n(kernel, grid, TC_THREADS, stream, cluster, args...);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_n(void (*kernel)(KArgs...), int grid, int threads, cudaStream_t stream, int cluster, Args... args) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("FLOPPITY_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
   cfg.dynamicSmemBytes = TC_SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -855,14 +1057,14 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   case (E): {                                                                                                         \
     static bool attr_set = false;                                                                                     \
     if (!attr_set) {                                                                                                  \
-      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
-      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     if (pair)                                                                                                         \
-      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true>, grid, stream, 2, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true, false>, grid, stream, 2, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
     else                                                                                                              \
-      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false>, grid, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false, false>, grid, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
     break;                                                                                                            \
   }
   int epi = a->flags & FP_EPI_MASK;
@@ -887,8 +1089,85 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   return 0;
 }
 
+// 3xFP16 variant: B_hi16 / B_lo16 = fp16 pieces of B [N, K] with leading dimension a->ldb in HALVES
+int launch_gemm_tc16(const fp_gemm_args* a, const void* B_hi16, const void* B_lo16, cudaStream_t stream) {
+  if (!tc_enabled() || !a->a_kmajor || !a->b_kmajor || !B_hi16 || !B_lo16) return FP_E_NOTREADY;
+  if ((a->lda & 3) || (a->ldb & 7) || (reinterpret_cast<uintptr_t>(a->A) & 15)) return FP_E_NOTREADY;
+  if ((reinterpret_cast<uintptr_t>(B_hi16) & 15) || (reinterpret_cast<uintptr_t>(B_lo16) & 15)) return FP_E_NOTREADY;
+  if (a->flags & (FP_G_RELU_B | FP_G_ATOMIC)) return FP_E_NOTREADY;
+  if (a->split_k > 1 || a->M < 1 || a->N < 1 || a->K < 1 || a->M > 2147483647LL) return FP_E_NOTREADY;
+  CUtensorMap mA, mBh, mBl;
+  if (!get_tensor_map(a->A, a->M, a->K, a->lda, &mA)) return FP_E_NOTREADY;
+  if (!get_tensor_map_f16(B_hi16, a->N, a->K, a->ldb, &mBh)) return FP_E_NOTREADY;
+  if (!get_tensor_map_f16(B_lo16, a->N, a->K, a->ldb, &mBl)) return FP_E_NOTREADY;
+  const int nkb = (int)((a->K + 63) / 64);
+  constexpr int kchunk = TC_KCHUNK_BLOCKS / 2;       // the same 1024 contraction indices per accumulation chain
+  const bool plain = (a->flags & ~(FP_G_RELU_A | FP_G_BIAS | FP_G_TF32X3)) == 0;
+  const int nchunks = (plain && nkb > kchunk) ? (nkb + kchunk - 1) / kchunk : 1;
+  int gfast = 0;
+  {
+    const bool m_fast = a->M <= (int64_t)a->N;
+    const double fast_bytes = 4.0 * (double)(m_fast ? a->M : (int64_t)a->N) * (double)a->K;      // fp32 A rows / fp16 hi + lo B rows
+    const double tile_bytes = 4.0 * TC_BM * (double)a->K;
+    if (fast_bytes > 64e6 && !(g_tc_dbg & 128)) gfast = (int)std::max(1.0, l2_group_bytes() / tile_bytes);
+  }
+  const int64_t tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + TC_BN - 1) / TC_BN);
+  const int grid = (int)std::min<int64_t>(tiles, num_sms());
+  ProfScope ps(TAG_GEMM_TC_NT, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
+  auto ok = [](const void* p, int64_t ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 3) == 0)); };
+  int vec_all = ok(a->C, a->ldc) ? 1 : 0;
+  if ((a->flags & FP_G_BIAS) && !ok(a->bias, 4)) vec_all = 0;
+  if ((a->flags & (FP_G_ADD_CTX | FP_G_GLU_RES)) && !ok(a->G, a->ldg)) vec_all = 0;
+  if ((a->flags & FP_G_GLU_RES) && (!ok(a->Rsd, a->ldr) || !ok(a->U, a->ldu))) vec_all = 0;
+  if ((a->flags & FP_G_RELUMASK) && !ok(a->Msk, a->ldm)) vec_all = 0;
+#define FP_TC_NT16_CASE(E)                                                                                            \
+  case (E): {                                                                                                         \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    FP_CUDA_OK(launch_pdl_n(k_gemm_tc_nt<(E), false, true>, grid, TC16_THREADS, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
+    break;                                                                                                            \
+  }
+  int epi = a->flags & FP_EPI_MASK;
+  switch (epi) {
+    case 0: case FP_G_BIAS: case FP_G_ADD_CTX: case FP_G_BIAS | FP_G_GLU_RES: case FP_G_RELUMASK:
+    case FP_G_RELUMASK | FP_G_ACCUM: case FP_G_ACCUM: case FP_G_BIAS | FP_G_DROP_OUT: break;
+    default: epi = -1;
+  }
+  switch (epi) {
+    FP_TC_NT16_CASE(0)
+    FP_TC_NT16_CASE(FP_G_BIAS)
+    FP_TC_NT16_CASE(FP_G_ADD_CTX)
+    FP_TC_NT16_CASE(FP_G_BIAS | FP_G_GLU_RES)
+    FP_TC_NT16_CASE(FP_G_RELUMASK)
+    FP_TC_NT16_CASE(FP_G_RELUMASK | FP_G_ACCUM)
+    FP_TC_NT16_CASE(FP_G_ACCUM)
+    FP_TC_NT16_CASE(FP_G_BIAS | FP_G_DROP_OUT)
+    FP_TC_NT16_CASE(-1)
+  }
+#undef FP_TC_NT16_CASE
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_split_f16(const float* x, void* hi16, void* lo16, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 7) || (reinterpret_cast<uintptr_t>(hi16) & 3) || (reinterpret_cast<uintptr_t>(lo16) & 3)) return FP_E_BADARG;
+  int blocks = (int)std::min<int64_t>((n / 2 + 255) / 256 + 1, 8 * num_sms());
+  ProfScope ps(TAG_OTHER, 0.0, stream);
+  k_split_f16<<<blocks, 256, 0, stream>>>(x, reinterpret_cast<uint32_t*>(hi16), reinterpret_cast<uint32_t*>(lo16), n);
+  FP_LAUNCH_CHECK();
+  return 0;
+}
+
 // wgrad: C[M,N] += A[R,M]^T * B[R,N]   (a_kmajor == 0, b_kmajor == 0, FP_G_ATOMIC [, FP_G_RELU_B])
-int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
+static int launch_gemm_tc_tn_fmt(const fp_gemm_args* a, cudaStream_t stream, bool f16);
+int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) { return launch_gemm_tc_tn_fmt(a, stream, false); }
+int launch_gemm_tc16_tn(const fp_gemm_args* a, cudaStream_t stream) { return launch_gemm_tc_tn_fmt(a, stream, true); }
+static int launch_gemm_tc_tn_fmt(const fp_gemm_args* a, cudaStream_t stream, bool f16) {
+  const int BK = f16 ? 64 : TN_BK;          // batch rows per stage
   if (!tc_enabled()) return FP_E_NOTREADY;
   if (a->a_kmajor || a->b_kmajor) return FP_E_NOTREADY;
   if ((a->flags & ~(FP_G_ATOMIC | FP_G_RELU_B | FP_G_COLSUM_A)) != 0 || !(a->flags & FP_G_ATOMIC)) return FP_E_NOTREADY;
@@ -897,22 +1176,24 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return FP_E_NOTREADY;
   if (a->M < 1 || a->N < 1 || a->K < 1 || a->M > 65536) return FP_E_NOTREADY;
   CUtensorMap mA, mB;
-  if (!get_tensor_map(a->A, a->K, a->M, a->lda, &mA, TN_BK, true)) return FP_E_NOTREADY;   // [R rows, M cols]
-  if (!get_tensor_map(a->B, a->K, a->N, a->ldb, &mB, TN_BK, true)) return FP_E_NOTREADY;   // [R rows, N cols]
+  // TF32: MN-major tiles written by the TMA itself (32-byte-atom swizzle); 3xFP16: raw boxes of 64 rows, plain 128-byte swizzle
+  if (!get_tensor_map(a->A, a->K, a->M, a->lda, &mA, BK, !f16)) return FP_E_NOTREADY;   // [R rows, M cols]
+  if (!get_tensor_map(a->B, a->K, a->N, a->ldb, &mB, BK, !f16)) return FP_E_NOTREADY;   // [R rows, N cols]
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  const int nkb = (int)((a->K + TN_BK - 1) / TN_BK);
+  const int nkb = (int)((a->K + BK - 1) / BK);
   const int64_t tiles = ((a->M + TC_BM - 1) / TC_BM) * ((a->N + TC_BN - 1) / TC_BN);
   int nsplit = (int)std::max<int64_t>(1, (num_sms() + tiles - 1) / tiles);
   // A few output tiles (the final layer's [290 x 128] is three): give every CTA ALL tiles of one batch range
   // (items c, c + nsplit, ... of CTA c share their k-range), so the operand the tiles have in common is re-read from
   // L2 microseconds later instead of from HBM by three CTAs that drift apart (221 MB of DRAM reads for 159 MB).
   if (tiles > 1 && tiles <= 8) nsplit = num_sms();
-  nsplit = std::min(nsplit, std::max(1, nkb * TN_BK / 128));   // at least 128 batch rows per split
-  constexpr int kchunk = TC_KCHUNK_BLOCKS * TC_BK / TN_BK;  // bound the truncating accumulation chain (1024 batch rows)
+  nsplit = std::min(nsplit, std::max(1, nkb * BK / 128));   // at least 128 batch rows per split
+  const int kchunk = TC_KCHUNK_BLOCKS * TC_BK / BK;  // bound the truncating accumulation chain (1024 batch rows)
   nsplit = std::max(nsplit, (nkb + kchunk - 1) / kchunk);
   // Whole waves: with a handful of output tiles (c3's 512 x 512 blocks: 16 tiles x 19 splits = 304 items on 148 SMs =
   // 2.05 waves) the last round runs almost empty.  Take the split count in [nsplit, 2 nsplit] that fills its rounds best.
@@ -935,7 +1216,10 @@ int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream) {
   int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
   if ((a->flags & FP_G_COLSUM_A) && (reinterpret_cast<uintptr_t>(a->U) & 15)) vec_all = 0;
   ProfScope ps(TAG_GEMM_TC_TN, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
-  FP_CUDA_OK(launch_pdl(k_gemm_tc_tn, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
+  if (f16)
+    FP_CUDA_OK(launch_pdl(k_gemm_tc_tn<true>, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
+  else
+    FP_CUDA_OK(launch_pdl(k_gemm_tc_tn<false>, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
   FP_LAUNCH_CHECK();
   return 0;
 }
@@ -980,6 +1264,17 @@ int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, v
 int fp_gemm_tc_tn(const fp_gemm_args* args, void* stream) {
   if (!args) return FP_E_BADARG;
   return fp::launch_gemm_tc_tn(args, (cudaStream_t)stream);
+}
+int fp_gemm_tc16(const fp_gemm_args* args, const void* B_hi16, const void* B_lo16, void* stream) {
+  if (!args) return FP_E_BADARG;
+  return fp::launch_gemm_tc16(args, B_hi16, B_lo16, (cudaStream_t)stream);
+}
+int fp_gemm_tc16_tn(const fp_gemm_args* args, void* stream) {
+  if (!args) return FP_E_BADARG;
+  return fp::launch_gemm_tc16_tn(args, (cudaStream_t)stream);
+}
+int fp_split_f16(const float* x, void* hi16, void* lo16, int64_t n, void* stream) {
+  return fp::launch_split_f16(x, hi16, lo16, n, (cudaStream_t)stream);
 }
 int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
   return fp::launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);

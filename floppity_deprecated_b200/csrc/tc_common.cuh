@@ -31,6 +31,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 operands, fp32 accumulation)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // ---- CTA pair (cta_group::2): two CTAs of a cluster on the two SMs of a TPC issue ONE MMA over 256 rows -----------------
 // Rank 0 (the leader) issues; both CTAs supply their 128 rows of A and their half of B at the SAME shared-memory offsets;
 // every CTA keeps its own 128 accumulator rows in its own tensor memory.
@@ -170,12 +182,27 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(const void* smem_tile, uin
   d |= (uint64_t)1 << 61;
   return d;
 }
+// MN-major operand tile of 16-bit elements, SWIZZLE_128B: atoms of 64 MN-elements (128 B) x 8 k-rows (1024 B);
+// LBO = stride between 64-element MN atoms, SBO = stride between 8-row k groups
+__device__ __forceinline__ uint64_t make_mnmajor_desc16(const void* smem_tile, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// instruction descriptor for kind::f16: D = f32, A = B = f16, K-major unless a_mn / b_mn
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // host side (gemm_tc.cu): cached cuTensorMapEncodeTiled for a 2-D fp32 row-major [rows, cols] tensor with leading
 // dimension ld (floats); box = 32 columns x box_rows rows, SWIZZLE_128B (atom32: SWIZZLE_128B_ATOM_32B)

@@ -129,6 +129,10 @@ typedef struct fp_gemm_args {
   float mask_scale;      /* FP_G_RELUMASK: C = Msk > 0 ? v * mask_scale : 0 ; 0 is read as 1 */
   float drop_p;          /* FP_G_DROP_OUT */
   uint64_t drop_seed;    /* FP_G_DROP_OUT */
+  const float* a_scale;  /* fp_gemm_tc16 / fp_gemm_tc16_tn: optional DEVICE scalar s (a power of two): the A operand is
+                          * converted as s * A and the result scaled back by 1/s -- brings gradient operands (~1/batch)
+                          * into fp16's range; NULL = 1 */
+  int32_t* status;       /* fp_gemm_tc16*: optional status words; [2] counts converting threads that met |s * A| > 6e4 */
 } fp_gemm_args;
 int fp_gemm(const fp_gemm_args* args, void* stream);
 /* Same contract on the tcgen05 tensor cores with the fp32-accurate 3xTF32 split (A split in-kernel, B_hi/B_lo
@@ -136,6 +140,15 @@ int fp_gemm(const fp_gemm_args* args, void* stream);
  * anything else (the caller then uses fp_gemm).  Set FLOPPITY_TC=0 to disable the tensor-core path. */
 int fp_gemm_tc(const fp_gemm_args* args, const float* B_hi, const float* B_lo, void* stream);
 int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* The same GEMM with 16-bit operand pieces ("3xFP16": x = hi + lo * 2^-11, hi = fp16(x), lo = fp16((x - hi) * 2^11); the
+ * same 22 mantissa bits as 3xTF32 at half the tensor-core time and half the shared-memory bytes per k-block, so twice the
+ * k-blocks are in flight).  B_hi16 / B_lo16 [N, K] fp16 with leading dimension args->ldb (HALVES, a multiple of 8) from
+ * fp_split_f16; A is converted in the kernel.  fp16's range is guarded: |a_scale * A| > 6e4 is counted in status[2]
+ * (values clamp).  Returns FP_E_NOTREADY when the shape is not supported. */
+int fp_gemm_tc16(const fp_gemm_args* args, const void* B_hi16, const void* B_lo16, void* stream);
+int fp_split_f16(const float* x, void* hi16, void* lo16, int64_t n, void* stream);
+/* fp_gemm_tc_tn with 3xFP16 operand pieces (both operands converted in the kernel; a_scale applies to A = the gradient) */
+int fp_gemm_tc16_tn(const fp_gemm_args* args, void* stream);
 /* weight-gradient form: C[M,N] += A[K,M]^T * B[K,N] (a_kmajor = b_kmajor = 0, flags = FP_G_ATOMIC [| FP_G_RELU_B]
  * [| FP_G_COLSUM_A with the bias-gradient vector [M] in `U`]); contraction split across CTAs, partial tiles added
  * with vector atomics.  FP_E_NOTREADY -> use fp_gemm (which ignores FP_G_COLSUM_A: the caller sums columns itself). */
