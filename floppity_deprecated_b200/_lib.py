@@ -82,10 +82,11 @@ SIGNATURES = {
     "fp_dropout_layer_seed": (c_uint64, [c_uint64, c_int32, c_int32]),
     "fp_set_mode": (c_int32, [c_int32, c_int32, c_int32, c_int32]),
     "fp_set_precision": (c_int32, [c_int32]),
+    "fp_set_gemm_format": (c_int32, [c_int32]),
     "fp_nsf_prepare": (c_int32, [_CFG, _P, _P, _P]),
     "fp_nsf_logprob_forward": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, c_int64, _P, _P, c_float, _P, _P, c_int32,
                                          c_uint64, _P, _P]),
-    "fp_nsf_logprob_backward": (c_int32, [_CFG, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_uint64, _P]),
+    "fp_nsf_logprob_backward": (c_int32, [_CFG, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_uint64, _P, _P]),
     "fp_nsf_finish_grads": (c_int32, [_CFG, _P, _P, _P, _P]),
     "fp_nsf_sample": (c_int32, [_CFG, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "fp_atom_choices": (c_int32, [_P, c_int64, c_int32, c_uint64, _P]),

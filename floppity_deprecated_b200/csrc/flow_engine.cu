@@ -22,6 +22,10 @@ namespace fp {
 int launch_gemm(const fp_gemm_args* a, cudaStream_t stream);
 int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, cudaStream_t stream);   // gemm_tc.cu
 int launch_gemm_tc_tn(const fp_gemm_args* a, cudaStream_t stream);
+int launch_gemm_tc16(const fp_gemm_args* a, const void* B_hi16, const void* B_lo16, cudaStream_t stream);
+int launch_gemm_tc16_tn(const fp_gemm_args* a, cudaStream_t stream);
+int launch_prepare_gemm16(const fp_nsf_config* cfg, const float* params, float* prepared, cudaStream_t stream);
+int launch_grad_scale(const float* d_logp, int64_t n, float* out, cudaStream_t s);
 int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
 int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params, float* t_hi, float* t_lo, cudaStream_t stream);
 bool tc_enabled();
@@ -63,9 +67,9 @@ __global__ void k_lu_prepare(const float*, float*, fp_nsf_config);
 __global__ void k_lu_finish(const float*, const float*, float*, fp_nsf_config);
 
 // ---- run-time switches of the conditioner paths (fp_set_mode; the environment gives the initial values) ----
-static int g_mode[5] = {-1, -1, -1, -1, -1};     // tc, fused, fused_fp16, smallh, single_pass
-static const char* const g_mode_env[5] = {"FLOPPITY_TC", "FLOPPITY_FUSED", "FLOPPITY_FUSED_FP16", "FLOPPITY_SMALLH",
-                                          "FLOPPITY_SINGLE_PASS"};
+static int g_mode[6] = {-1, -1, -1, -1, -1, -1};     // tc, fused, fused_fp16, smallh, single_pass, gemm_fp16
+static const char* const g_mode_env[6] = {"FLOPPITY_TC", "FLOPPITY_FUSED", "FLOPPITY_FUSED_FP16", "FLOPPITY_SMALLH",
+                                          "FLOPPITY_SINGLE_PASS", "FLOPPITY_GEMM_FP16"};
 static bool mode_on(int i) {
   if (g_mode[i] < 0) {
     const char* e = getenv(g_mode_env[i]);
@@ -78,6 +82,12 @@ bool tc_enabled() { return mode_on(0); }
 bool fused_enabled() { return mode_on(1); }
 bool cond_fused_f16() { return mode_on(2); }
 bool smallh_enabled() { return mode_on(3); }
+bool gemm_fp16() { return mode_on(5); }     // 3xFP16 operand pieces in the stand-alone tensor-core GEMMs (else 3xTF32)
+
+// per-call context of the 3xFP16 GEMMs: the device scalar that scales gradient operands into fp16's range (backward pass
+// only) and the status words that count operands beyond it
+struct GemmCtx { const float* gscale; int32_t* status; };
+static thread_local GemmCtx g_gctx = {nullptr, nullptr};
 
 #define FP_TRY(expr)            \
   do {                          \
@@ -123,6 +133,11 @@ static int wgrad(const float* dOut, int64_t ldo, int n_out, const float* act, in
   g.C = dW; g.ldc = ldw; g.M = n_out; g.N = k_in; g.K = R;
   g.flags = FP_G_ATOMIC | flags_extra | (db ? FP_G_COLSUM_A : 0);
   g.U = db;
+  if (gemm_fp16()) {
+    g.a_scale = g_gctx.gscale; g.status = g_gctx.status;
+    int r = launch_gemm_tc16_tn(&g, s);
+    if (r != FP_E_NOTREADY) return r;
+  }
   {
     int r = launch_gemm_tc_tn(&g, s);
     if (r != FP_E_NOTREADY) return r;
@@ -146,6 +161,13 @@ static fp_gemm_args dgrad_args(const float* dOut, int64_t ldo, int n_out, const 
 // forward GEMM against a weight matrix living at `woff` in the parameter buffer: tcgen05 3xTF32 when the shape
 // allows (pre-split weights in `prepared`), else the fp32 SIMT kernel
 static int gemm_weight(const Layout& L, const float* prepared, int64_t woff, fp_gemm_args* g, cudaStream_t s) {
+  if (prepared && gemm_fp16() && !L.smallH()) {      // fp16 copy of the same [N, K] matrix, same leading dimension (layout.h prepG16Hi)
+    fp_gemm_args g16 = *g;
+    g16.status = g_gctx.status;
+    int r = launch_gemm_tc16(&g16, reinterpret_cast<const uint16_t*>(prepared + L.prepG16Hi()) + 2 * woff,
+                             reinterpret_cast<const uint16_t*>(prepared + L.prepG16Lo()) + 2 * woff, s);
+    if (r != FP_E_NOTREADY) return r;
+  }
   if (prepared) {
     int r = launch_gemm_tc(g, prepared + L.prepHi() + woff, prepared + L.prepLo() + woff, s);
     if (r != FP_E_NOTREADY) return r;
@@ -164,6 +186,14 @@ static int dgrad_weight(const Layout& L, const float* prepared, int64_t toff, in
     g.B = prepared + L.prepTHi() + toff; g.ldb = ld_t; g.b_kmajor = 1;
     g.C = dIn; g.ldc = ldi; g.M = R; g.N = k_in; g.K = n_out; g.flags = flags; g.split_k = 1;
     g.Msk = Msk; g.ldm = ldm; g.mask_scale = mask_scale;
+    if (gemm_fp16() && !L.smallH()) {
+      fp_gemm_args g16 = g;
+      g16.ldb = Layout::ld16((int)ld_t);
+      g16.a_scale = g_gctx.gscale; g16.status = g_gctx.status;
+      int r = launch_gemm_tc16(&g16, reinterpret_cast<const uint16_t*>(prepared + L.prepGT16Hi()) + 2 * toff,
+                               reinterpret_cast<const uint16_t*>(prepared + L.prepGT16Lo()) + 2 * toff, s);
+      if (r != FP_E_NOTREADY) return r;
+    }
     int r = launch_gemm_tc(&g, prepared + L.prepTHi() + toff, prepared + L.prepTLo() + toff, s);
     if (r != FP_E_NOTREADY) return r;
   }
@@ -285,6 +315,10 @@ int fp_set_precision(int32_t single_pass) {
   if (single_pass >= 0) g_mode[4] = single_pass ? 1 : 0;
   return mode_on(4) ? 1 : 0;
 }
+int fp_set_gemm_format(int32_t fp16) {
+  if (fp16 >= 0) g_mode[5] = fp16 ? 1 : 0;
+  return mode_on(5) ? 1 : 0;
+}
 uint64_t fp_dropout_layer_seed(uint64_t seed, int32_t layer, int32_t block) { return layer_seed(seed, layer, block); }
 
 int64_t fp_nsf_param_count(const fp_nsf_config* cfg) {
@@ -356,6 +390,7 @@ int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepare
     FP_TRY(launch_split_tf32(params, prepared + L.prepHi(), prepared + L.prepLo(), L.total(), (cudaStream_t)stream));
     FP_TRY(launch_transpose_split_weights(cfg, params, prepared + L.prepTHi(), prepared + L.prepTLo(), (cudaStream_t)stream));
     FP_TRY(launch_cond_prepare(cfg, params, prepared, (cudaStream_t)stream));     // fp16 operand copies for the fused conditioner
+    if (!L.smallH()) FP_TRY(launch_prepare_gemm16(cfg, params, prepared, (cudaStream_t)stream));   // and for the 3xFP16 GEMMs
   }
   FP_TRY(launch_small_prepare(cfg, params, prepared, (cudaStream_t)stream));      // shared-memory images for hidden <= 64
   return 0;
@@ -386,6 +421,7 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
 
   float* ctx_all = ws + W.ctx_all;
   float* logdet = ws + W.logdet;
+  g_gctx = GemmCtx{nullptr, status};
   FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
   const int fused = use_fused(cfg, L, prepared, training != 0);
   if (fused) FP_TRY(launch_gate_sigmoid(ctx_all, Rc, L.Nctx, L.H, L.S, s));
@@ -419,7 +455,7 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
 
 int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const float* prepared, const float* ctx,
                             int64_t R, int64_t Rc, const float* zscale, const float* d_logp, float* grads,
-                            float* d_theta, float* workspace, uint64_t dropout_seed, void* stream) {
+                            float* d_theta, float* workspace, uint64_t dropout_seed, int32_t* status, void* stream) {
   FP_TRY(check_cfg(cfg));
   if (R <= 0) return 0;
   if (Rc <= 0 || R % Rc != 0) return FP_E_BADARG;
@@ -439,6 +475,13 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
   float* dctx_all = ws + W.dctx_all;
   const float* ctx_all = ws + W.ctx_all;
 
+  // 3xFP16 GEMMs: every gradient tensor of this pass is linear in d_logp (~ 1 / batch): one power-of-two scale brings them
+  // all into fp16's range (undone in the GEMM epilogues); operands beyond the range are counted in status[2]
+  g_gctx = GemmCtx{nullptr, status};
+  if (gemm_fp16() && tc_enabled() && fused != 2) {
+    FP_TRY(launch_grad_scale(d_logp, R, ws + W.gscale, s));
+    g_gctx.gscale = ws + W.gscale;
+  }
   // the shared-memory-resident backward adds its context gradients with reductions: start from zero
   if (fused == 2) FP_CUDA_OK(cudaMemsetAsync(dctx_all, 0, sizeof(float) * (size_t)Rc * (size_t)L.Nctx, s));
 
@@ -517,6 +560,7 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
   const int ctx_div = (Rc == 1) ? 0 : (int)(R / Rc);
   const int D = L.D;
   float* ctx_all = ws + W.ctx_all;
+  g_gctx = GemmCtx{nullptr, status};
   FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
   const int fused = use_fused(cfg, L, prepared, false);
   if (fused) FP_TRY(launch_gate_sigmoid(ctx_all, Rc, L.Nctx, L.H, L.S, s));

@@ -851,8 +851,32 @@ __global__ void k_split_f16(const float* __restrict__ x, uint32_t* __restrict__ 
   }
 }
 
+// fp16 pieces of the K-major weight matrices the forward GEMMs read: blockIdx.y = layer * (2 Bk + 2) + {2b: W1_b, 2b+1: W2_b,
+// 2Bk: W0x, 2Bk+1: Wf}; the copy of the tensor at float offset woff starts at half index 2 * woff (layout.h prepG16Hi)
+__global__ void k_split_f16_weights(const float* __restrict__ params, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                    fp_nsf_config cfg) {
+  const Layout L(&cfg);
+  const int per = 2 * L.Bk + 2;
+  const int layer = blockIdx.y / per, which = blockIdx.y % per;
+  int64_t woff, n;
+  if (which == per - 1) { woff = L.wf(layer); n = (int64_t)L.dP(layer) * L.H; }
+  else if (which == per - 2) { woff = L.w0x(layer); n = (int64_t)L.H * L.D; }
+  else { woff = (which & 1) ? L.w2(layer, which >> 1) : L.w1(layer, which >> 1); n = (int64_t)L.H * L.H; }
+  uint32_t* hi2 = reinterpret_cast<uint32_t*>(hi + 2 * woff);
+  uint32_t* lo2 = reinterpret_cast<uint32_t*>(lo + 2 * woff);
+  const float* x = params + woff;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; 2 * i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = x[2 * i], b = (2 * i + 1 < n) ? x[2 * i + 1] : 0.f;
+    uint32_t h, l;
+    split_f16x2(a, b, h, l);
+    hi2[i] = h; lo2[i] = l;
+  }
+}
+
 // transpose + split of every weight matrix the dgrad GEMMs need, one launch: blockIdx.y = tensor id
 // (layer * (2*Bk+2) + {0: W0x, 1+2b: W1_b, 2+2b: W2_b, 2Bk+1: Wf}), blockIdx.x = 32x32 tile
+// F16: fp16 hi / scaled-residual lo at half index 2 * dst (see layout.h prepGT16Hi), leading dimension rounded up to 8
+template <bool F16>
 __global__ void k_transpose_split_weights(const float* __restrict__ params, float* __restrict__ t_hi,
                                           float* __restrict__ t_lo, fp_nsf_config cfg) {
   __shared__ float tile[32][33];
@@ -880,9 +904,17 @@ __global__ void k_transpose_split_weights(const float* __restrict__ params, floa
     int c = c0 + i, r = r0 + threadIdx.x;      // dst[c][r]
     if (c < cols && r < rows) {
       float v = tile[threadIdx.x][i];
+      if (F16) {
+        uint32_t h2, l2;
+        split_f16x2(v, 0.f, h2, l2);
+        const int64_t o = 2 * dst + (int64_t)c * Layout::ld16(ld_dst) + r;
+        reinterpret_cast<uint16_t*>(t_hi)[o] = (uint16_t)(h2 & 0xFFFFu);
+        reinterpret_cast<uint16_t*>(t_lo)[o] = (uint16_t)(l2 & 0xFFFFu);
+      } else {
       float h = tf32_round(v);
       t_hi[dst + (int64_t)c * ld_dst + r] = h;
       t_lo[dst + (int64_t)c * ld_dst + r] = v - h;
+      }
     }
   }
 }
@@ -1239,8 +1271,31 @@ int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params
   int tiles = ((maxdim_r + 31) / 32) * ((maxdim_c + 31) / 32);
   dim3 grid(tiles, L.T * (2 * L.Bk + 2));
   ProfScope ps(TAG_OTHER, 0.0, stream);
-  k_transpose_split_weights<<<grid, dim3(32, 8), 0, stream>>>(params, t_hi, t_lo, *cfg);
+  k_transpose_split_weights<false><<<grid, dim3(32, 8), 0, stream>>>(params, t_hi, t_lo, *cfg);
   FP_LAUNCH_CHECK();
+  return 0;
+}
+
+// fp16 operand copies for the 3xFP16 GEMMs, once per optimiser step (after launch_split_tf32 / launch_transpose_split_weights)
+int launch_prepare_gemm16(const fp_nsf_config* cfg, const float* params, float* prepared, cudaStream_t stream) {
+  Layout L(cfg);
+  uint16_t* hi = reinterpret_cast<uint16_t*>(prepared + L.prepG16Hi());
+  uint16_t* lo = reinterpret_cast<uint16_t*>(prepared + L.prepG16Lo());
+  { int r = launch_split_f16(params + L.ctx_w, hi + 2 * L.ctx_w, lo + 2 * L.ctx_w, L.Nctx * L.C, stream); if (r) return r; }
+  ProfScope ps(TAG_OTHER, 0.0, stream);
+  {
+    const int64_t nmax = (int64_t)std::max(L.H, L.dPmax()) * L.H;
+    dim3 grid((unsigned)std::min<int64_t>((nmax / 2 + 255) / 256, 64), (unsigned)(L.T * (2 * L.Bk + 2)));
+    k_split_f16_weights<<<grid, 256, 0, stream>>>(params, hi, lo, *cfg);
+    FP_LAUNCH_CHECK();
+  }
+  {
+    int maxdim_r = std::max(L.H, L.dPmax()), maxdim_c = std::max(L.H, L.D);
+    int tiles = ((maxdim_r + 31) / 32) * ((maxdim_c + 31) / 32);
+    dim3 grid(tiles, L.T * (2 * L.Bk + 2));
+    k_transpose_split_weights<true><<<grid, dim3(32, 8), 0, stream>>>(params, prepared + L.prepGT16Hi(), prepared + L.prepGT16Lo(), *cfg);
+    FP_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -117,7 +117,17 @@ struct Layout {
   FP_LHD int64_t shLayerHalves(int i) const { return 2 * (shFwdHalves(i) + shBwdHalves(i)); }      // [F hi | F lo | B hi | B lo]
   FP_LHD int64_t shLayerOff(int i) const { int64_t o = 0; for (int l = 0; l < i; ++l) o += shLayerHalves(l); return o; }   // halves
   FP_LHD int64_t prepSmall() const { return (prepF16Lo() + f16Floats() + 63) & ~int64_t(63); }
-  FP_LHD int64_t prepAll() const { return prepSmall() + (smallH() ? ((shLayerOff(T) / 2 + 63) & ~int64_t(63)) : 0); }
+  FP_LHD int64_t prepSmallEnd() const { return prepSmall() + (smallH() ? ((shLayerOff(T) / 2 + 63) & ~int64_t(63)) : 0); }
+  // 3xFP16 stand-alone GEMMs (gemm_tc.cu, fp_gemm_tc16): fp16 hi / scaled-residual lo copies of the weights.  The copy of the
+  // tensor at float offset `woff` starts at BYTE offset 4 * woff of its region (half index 2 * woff: 16-byte aligned like
+  // the tensor itself) with the tensor's own leading dimension; the transposed copies likewise at 4 * toff with the
+  // leading dimension rounded up to 8 halves (ld16).
+  FP_LHD int64_t prepG16Hi() const { return (prepSmallEnd() + 63) & ~int64_t(63); }
+  FP_LHD int64_t prepG16Lo() const { return prepG16Hi() + ((total() + 63) & ~int64_t(63)); }
+  FP_LHD int64_t prepGT16Hi() const { return prepG16Lo() + ((total() + 63) & ~int64_t(63)); }
+  FP_LHD int64_t prepGT16Lo() const { return prepGT16Hi() + tTotal(); }
+  FP_LHD static int ld16(int ld) { return (ld + 7) & ~7; }
+  FP_LHD int64_t prepAll() const { return prepGT16Lo() + tTotal(); }
 };
 
 // workspace carve; identical arithmetic in forward and backward so saved activations are found again
@@ -127,7 +137,7 @@ struct Workspace {
   int64_t th_a, th_b, h, t, prm;
   // training
   int64_t th_st, th_sp, act;  // act: per-layer region
-  int64_t dth_a, dth_b, dh, dt, du, dprm, dctx_all, dub;
+  int64_t dth_a, dth_b, dh, dt, du, dprm, dctx_all, dub, gscale;
   int64_t total;
   int64_t R, Rc;
   int64_t act_layer_sz[64];
@@ -139,7 +149,7 @@ struct Workspace {
     auto take = [&](int64_t n) { int64_t r = o; o += al32(n); return r; };
     ctx_all = take(Rc * L.Nctx);
     logdet = take(R);
-    th_a = th_b = h = t = prm = th_st = th_sp = act = dth_a = dth_b = dh = dt = du = dprm = dctx_all = dub = 0;
+    th_a = th_b = h = t = prm = th_st = th_sp = act = dth_a = dth_b = dh = dt = du = dprm = dctx_all = dub = gscale = 0;
     if (!training) {
       th_a = take(R * L.D); th_b = take(R * L.D);
       h = take(R * L.ldH()); t = take(R * L.ldH()); prm = take(R * L.ldPmax());
@@ -161,6 +171,7 @@ struct Workspace {
       dctx_all = take(Rc * L.Nctx);
       // the fused small-hidden backward keeps every block's du / dt for the weight gradients that follow it
       dub = L.smallH() ? take((int64_t)2 * L.Bk * al32(R * L.ldH())) : 0;
+      gscale = take(4);      // power-of-two scale of the gradient operands of the 3xFP16 GEMMs (k_grad_scale)
     }
     total = o;
   }

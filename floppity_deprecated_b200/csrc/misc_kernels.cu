@@ -571,6 +571,35 @@ int launch_sum(const float* x, int64_t n, float scale, float* out, cudaStream_t 
   FP_LAUNCH_CHECK(); return 0;
 }
 
+// Power-of-two scale for the gradient operands of the 3xFP16 GEMMs: s = 2^-e with 2^(e-1) <= max|d_logp| < 2^e, so the
+// upstream gradient enters the backward pass with its largest element in [0.5, 1) (every later gradient tensor is linear
+// in it); s = 1 for an all-zero or non-finite upstream gradient.  One block.
+__global__ void k_grad_scale(const float* __restrict__ d_logp, int64_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(d_logp[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    float sc = 1.f;
+    if (m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)
+      e = max(-100, min(100, e));
+      sc = ldexpf(1.f, -e);
+    }
+    out[0] = sc;
+  }
+}
+int launch_grad_scale(const float* d_logp, int64_t n, float* out, cudaStream_t s) {
+  ProfScope ps(TAG_OTHER, 0.0, s);
+  k_grad_scale<<<1, 1024, 0, s>>>(d_logp, n, out);
+  FP_LAUNCH_CHECK(); return 0;
+}
+
 // keep flags of the dropout mask, for the parity tests (the oracle is handed the very mask the kernels drew)
 __global__ void k_dropout_mask(uint8_t* __restrict__ keep, int64_t R, int width, DropKey dk) {
   const int64_t n = R * (int64_t)width;

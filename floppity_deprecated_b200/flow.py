@@ -326,7 +326,8 @@ class NSFFlow(nn.Module):
             c.dropout_p = 0.0
         _lib.check(_lib.lib().fp_nsf_logprob_backward(
             c, _lib.ptr(self._flat), _lib.ptr(prepared), _lib.ptr(ctx_std), R, Rc, _lib.ptr(self._theta_scale),
-            _lib.ptr(d_logp), _lib.ptr(grads), _lib.ptr(d_theta), _lib.ptr(ws), seed, _lib.stream()),
+            _lib.ptr(d_logp), _lib.ptr(grads), _lib.ptr(d_theta), _lib.ptr(ws), seed,
+            _lib.ptr(self._last_status) if getattr(self, "_last_status", None) is not None else None, _lib.stream()),
             "fp_nsf_logprob_backward")
 
     def _finish_grads(self, grads, prepared):

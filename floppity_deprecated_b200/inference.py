@@ -71,9 +71,9 @@ class BoxUniform:
 def _check_fp16_range(st) -> None:
     if len(st) > 2 and st[2]:
         raise FloatingPointError(
-            f"{st[2]} operand pieces of the fused conditioner reached the edge of fp16's range (|value| > 6e4): the 3xFP16 "
-            "operand format does not cover this flow's activations -- set FLOPPITY_FUSED_FP16=0 (3xTF32 operands) and "
-            "check that the observations are z-scored")
+            f"{st[2]} operand pieces of the conditioner kernels reached the edge of fp16's range (|value| > 6e4): the 3xFP16 "
+            "operand format does not cover this flow's activations / gradients -- set FLOPPITY_FUSED_FP16=0 and "
+            "FLOPPITY_GEMM_FP16=0 (3xTF32 operands) and check that the observations are z-scored")
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -190,7 +190,7 @@ class _TrainEngine:
         _lib.check(L.fp_nsf_logprob_backward(
             c, _lib.ptr(net._flat), _lib.ptr(self.prepared), _lib.ptr(self._ctx), self.R, self.B,
             _lib.ptr(net._theta_scale), _lib.ptr(self.d_logp), _lib.ptr(self.grads), None, _lib.ptr(self.ws),
-            self.seed if c.dropout_p > 0 else 0, s), "logprob backward")
+            self.seed if c.dropout_p > 0 else 0, _lib.ptr(self.status), s), "logprob backward")
         _lib.check(L.fp_nsf_finish_grads(c, _lib.ptr(net._flat), _lib.ptr(self.prepared), _lib.ptr(self.grads), s), "finish grads")
         if self.emb_trainable:
             self.emb_grads.zero_()

@@ -170,6 +170,10 @@ int fp_set_mode(int32_t tc, int32_t fused, int32_t fused_fp16, int32_t smallh);
  * NOT within the 1e-4 parity bar: log_prob agrees with the fp32 path to ~1e-3 relative (tests state the tolerance) and is
  * reported apart in bench.py.  Negative argument = query.  Returns the current setting. */
 int fp_set_precision(int32_t single_pass);
+/* Operand format of the stand-alone tensor-core GEMMs (the wide-conditioner path and every unfused backward GEMM;
+ * FLOPPITY_GEMM_FP16): 1 = 3xFP16 pieces (default; fp32-accurate like 3xTF32 -- 11 + 11 mantissa bits -- with fp16's range
+ * guarded by status[2]), 0 = 3xTF32.  Negative argument = query.  Returns the current setting. */
+int fp_set_gemm_format(int32_t fp16);
 /* debug: SM-clock stamps of CTA 0 of the next fp_gemm_tc launches into a device int64[512] buffer (NULL = off) */
 int fp_tc_set_trace(void* buf);
 /* debug: ablation switches for timing experiments on the tensor-core GEMM kernels (1 skip the operand conversion, 2 skip the
@@ -195,11 +199,12 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
                            int32_t* status, void* stream);
 /* Backward of the above given d_logp [R]; ACCUMULATES into grads (same layout as params);
  * d_theta (may be NULL) [R, D] receives dL/dtheta (raw theta). Must follow a training=1 forward
- * with the same workspace. */
+ * with the same workspace.  status (may be NULL): status[2] counts gradient operands beyond fp16's range in the 3xFP16
+ * GEMMs (they are scaled by one power of two derived from max|d_logp|, so this needs gradients 6e4 times the upstream one). */
 int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const float* prepared,
                             const float* ctx, int64_t R, int64_t Rc, const float* zscale,
                             const float* d_logp, float* grads, float* d_theta, float* workspace,
-                            uint64_t dropout_seed, void* stream);
+                            uint64_t dropout_seed, int32_t* status, void* stream);
 /* d_ctx [Rc, C] = gradient wrt the context rows (for an embedding net trained jointly in front of the flow: sbi
  * FCEmbedding built at /root/reference/modules.py:21-45).  Call after fp_nsf_logprob_backward with the same workspace. */
 int fp_nsf_ctx_backward(const fp_nsf_config* cfg, const float* params, int64_t R, int64_t Rc, const float* workspace,

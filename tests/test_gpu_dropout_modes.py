@@ -23,21 +23,25 @@ from oracle import nsf_oracle as O
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
-# (tc, fused, fused_fp16, smallh)
+# (tc, fused, fused_fp16, smallh, gemm_fp16)
 MODES = {
-    "default": (1, 1, 1, 1),
-    "fused_3xtf32": (1, 1, 0, 1),
-    "gemm_chain_tc": (1, 0, 0, 0),
-    "simt_fp32": (0, 0, 0, 0),
+    "default": (1, 1, 1, 1, 1),
+    "fused_3xtf32": (1, 1, 0, 1, 0),
+    "gemm_chain_tc": (1, 0, 0, 0, 1),           # stand-alone tcgen05 GEMMs, 3xFP16 operand pieces (the default format)
+    "gemm_chain_tc_3xtf32": (1, 0, 0, 0, 0),    # ... 3xTF32
+    "simt_fp32": (0, 0, 0, 0, 0),
 }
 
 
 @pytest.fixture(params=list(MODES))
 def mode(request):
-    before = _lib.lib().fp_set_mode(-1, -1, -1, -1)
-    _lib.lib().fp_set_mode(*MODES[request.param])
+    L = _lib.lib()
+    before, before16 = L.fp_set_mode(-1, -1, -1, -1), L.fp_set_gemm_format(-1)
+    L.fp_set_mode(*MODES[request.param][:4])
+    L.fp_set_gemm_format(MODES[request.param][4])
     yield request.param
-    _lib.lib().fp_set_mode(before & 1, (before >> 1) & 1, (before >> 2) & 1, (before >> 3) & 1)
+    L.fp_set_mode(before & 1, (before >> 1) & 1, (before >> 2) & 1, (before >> 3) & 1)
+    L.fp_set_gemm_format(before16)
 
 
 def _pair(D, C, H, T, K, Bk, p, seed, n=1024):
@@ -275,6 +279,80 @@ def test_context_projection_at_real_spectrum_widths(C, N, M, pair_mode):
     _lib.check(L.fp_gemm_tc_tn(b, _lib.stream()), "ctx wgrad")
     want_w = (dOut.double().T @ A.double()).cpu().numpy()
     assert np.abs(dW.cpu().numpy() - want_w).max() < 2e-4 * np.abs(want_w).max()
+
+
+@pytest.mark.parametrize("M,N,K,lda,ldb", [(300, 200, 96, 96, 96), (1000, 512, 705, 708, 712), (130, 38400, 2000, 2000, 2000),
+                                            (777, 136, 64, 64, 64), (257, 384, 3000, 3000, 3000)])
+def test_fp16_piece_gemm_matches_fp64(M, N, K, lda, ldb):
+    """fp_gemm_tc16 (3xFP16 operand pieces, the default format of the stand-alone tensor-core GEMMs): against an fp64 product
+    at the same tolerance as the 3xTF32 kernel, ragged tiles, padded leading dimensions, K-chunked long contractions, the
+    relu prologue, a gradient-sized A operand brought into range by a_scale, and the range guard."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    Afull = torch.randn(M, lda, generator=g).cuda()
+    Bp = torch.zeros(N, ldb); Bp[:, :K] = torch.randn(N, K, generator=g) / np.sqrt(K); Bp = Bp.cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    h16 = torch.empty(N, ldb, device="cuda", dtype=torch.float16); l16 = torch.empty_like(h16)
+    _lib.check(L.fp_split_f16(_lib.ptr(Bp), _lib.ptr(h16), _lib.ptr(l16), Bp.numel(), _lib.stream()), "split16")
+    # the pieces reproduce the weights to 2^-22
+    rec = h16.double() + l16.double() / 2048.0
+    assert (rec - Bp.double()).abs().max() < 2.0 ** -21 * Bp.abs().max()
+    st = torch.zeros(4, dtype=torch.int32, device="cuda")
+
+    def run(A, flags, scale=None):
+        out = torch.empty(M, N, device="cuda")
+        a = _lib.GemmArgs()
+        a.A, a.lda, a.a_kmajor, a.B, a.ldb, a.b_kmajor = _lib.ptr(A), lda, 1, _lib.ptr(Bp), ldb, 1
+        a.C, a.ldc, a.M, a.N, a.K, a.flags, a.bias, a.split_k = _lib.ptr(out), N, M, N, K, flags | _lib.G_BIAS, _lib.ptr(bias), 1
+        a.status = _lib.ptr(st)
+        sc = None
+        if scale is not None:
+            sc = torch.tensor([scale], device="cuda"); a.a_scale = _lib.ptr(sc)
+        _lib.check(L.fp_gemm_tc16(a, _lib.ptr(h16), _lib.ptr(l16), _lib.stream()), "gemm16")
+        torch.cuda.synchronize()
+        return out
+
+    Bd = Bp[:, :K].double()
+    want = Afull[:, :K].double() @ Bd.T + bias.double()
+    got = run(Afull, 0)
+    assert (got.double() - want).abs().max() < 2e-5, (got.double() - want).abs().max()
+    want_r = Afull[:, :K].double().clamp_min(0) @ Bd.T + bias.double()
+    assert (run(Afull, _lib.G_RELU_A).double() - want_r).abs().max() < 2e-5
+    # gradient-sized operand (~1e-8): exact power-of-two scale in, out again in the epilogue
+    tiny = Afull * 1e-8
+    zb = bias.clone(); bias.zero_()
+    got_t = run(tiny, 0, scale=2.0 ** 26)
+    want_t = tiny[:, :K].double() @ Bd.T
+    assert (got_t.double() - want_t).abs().max() < 2e-5 * want_t.abs().max()
+    bias.copy_(zb)
+    assert st.tolist()[2] == 0
+    run(Afull * 1e5, 0)                                       # beyond fp16: values clamp, the guard counts
+    assert st.tolist()[2] > 0
+
+
+@pytest.mark.parametrize("M,N,R", [(200, 136, 1000), (512, 512, 4000), (708, 512, 2100), (1280, 2000, 130)])
+def test_fp16_piece_weight_gradient_matches_fp64(M, N, R):
+    """fp_gemm_tc16_tn: dW[M, N] += dOut[R, M]^T act[R, N] with both operands converted in the kernel (relu prologue on the
+    activations, bias gradient riding along), gradient-sized dOut scaled by a_scale."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(M + N + R)
+    dOut = (torch.randn(R, M, generator=g) * 1e-6).cuda()
+    act = torch.randn(R, N, generator=g).cuda()
+    sc = torch.tensor([2.0 ** 19], device="cuda")
+    st = torch.zeros(4, dtype=torch.int32, device="cuda")
+    for flags in (0, _lib.G_RELU_B):
+        dW = torch.zeros(M, N, device="cuda"); db = torch.zeros(M, device="cuda")
+        b = _lib.GemmArgs()
+        b.A, b.lda, b.a_kmajor, b.B, b.ldb, b.b_kmajor = _lib.ptr(dOut), M, 0, _lib.ptr(act), N, 0
+        b.C, b.ldc, b.M, b.N, b.K, b.split_k = _lib.ptr(dW), N, M, N, R, 1
+        b.flags, b.U, b.a_scale, b.status = _lib.G_ATOMIC | _lib.G_COLSUM_A | flags, _lib.ptr(db), _lib.ptr(sc), _lib.ptr(st)
+        _lib.check(L.fp_gemm_tc16_tn(b, _lib.stream()), "wgrad16")
+        ad = act.double().clamp_min(0) if flags else act.double()
+        want = dOut.double().T @ ad
+        assert (dW.double() - want).abs().max() < 2e-5 * want.abs().max()
+        cs = dOut.double().sum(0)
+        assert (db.double() - cs).abs().max() < 2e-5 * cs.abs().max()
+    assert st.tolist()[2] == 0
 
 
 def _kernel_launches(fn):
