@@ -44,7 +44,7 @@ WORKLOADS = {
 }
 CONFIG_INDEX = {"c1": 0, "c2": 1, "c3": 2, "c4": 3}
 # operand format of each tensor-core kernel: passes of the fp32-accurate split and the rate of one pass relative to bf16
-TENSOR_KERNELS = {"k_gemm_tc_nt": ("3xTF32", 6.0), "k_gemm_tc_tn": ("3xTF32", 6.0), "k_cond_fwd": ("3xFP16", 3.0),
+TENSOR_KERNELS = {"k_gemm_tc_nt": ("3xFP16", 3.0), "k_gemm_tc_tn": ("3xFP16", 3.0), "k_cond_fwd": ("3xFP16", 3.0),
                   "k_cond_small_fwd": ("3xFP16 mma.sync", 3.0), "k_cond_small_bwd": ("3xFP16 mma.sync", 3.0),
                   "k_small_wgrad": ("3xFP16 mma.sync", 3.0)}
 
@@ -292,8 +292,12 @@ def main():
         return float(ms.item())
 
     def tensor_fmt(name):
-        if name in ("k_gemm_tc_nt", "k_gemm_tc_tn") and L.fp_set_precision(-1) == 1:
-            return ("1xTF32 (reduced precision)", 2.0)
+        """(operand format, bf16-rate divisor): passes per fp32-accurate product x the rate of one pass relative to bf16."""
+        if name in ("k_gemm_tc_nt", "k_gemm_tc_tn"):
+            f16 = L.fp_set_gemm_format(-1) == 1
+            if L.fp_set_precision(-1) == 1:
+                return ("1xFP16 high pieces (reduced precision)", 1.0) if f16 else ("1xTF32 (reduced precision)", 2.0)
+            return ("3xFP16", 3.0) if f16 else ("3xTF32", 6.0)
         return TENSOR_KERNELS[name]
 
     def kernel_table(fn, n):
@@ -342,8 +346,8 @@ def main():
             roof = {"bound": "tensor", "achieved": d["achieved_tflops"], "peak": PK["tf_sust"] / div, "unit": "TFLOP/s",
                     "frac": tc, "traffic": None, "kernel": name, "share_of_step": d["share"], "avg_us": d["avg_us"],
                     "peak_source": f"{PK['source']}: bf16 sustained {PK['tf_sust']:.0f} TFLOP/s / {div:.0f} -- {fmt} operands: "
-                                   f"{'one TF32 pass' if div == 2.0 else 'three tensor-core passes per fp32-accurate product'}"
-                                   f"{' at the TF32 rate (half of bf16)' if div in (2.0, 6.0) else ''}",
+                                   f"{'one tensor-core pass' if div <= 2.0 else 'three tensor-core passes per fp32-accurate product'}"
+                                   f"{' at the TF32 rate (half of bf16)' if div in (2.0, 6.0) else ' at the fp16 rate (= bf16)'}",
                     "frac_of_bf16_peak": d["frac_of_bf16_peak"], "hbm_frac": hb}
         elif name == "k_gemm":
             fma = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -559,18 +563,30 @@ def main():
                 log(f"{key}: {r['ms_per_step']:.3f} ms/step, {r['value']:.0f} pairs/s")
                 del c
                 torch.cuda.empty_cache()
-            # the REDUCED-PRECISION variant of the wide conditioner, stated apart (one TF32 product per GEMM instead of the
-            # fp32-accurate three: ~1e-3 relative on log_prob, outside the 1e-4 parity bar -- never the default)
             WORKLOADS["c3"] = dict(loss="mle", batch=18944, rows=65536)
+            # the same step with 3xTF32 operand pieces in the stand-alone GEMMs (the format of the first half of round 2)
+            L.fp_set_gemm_format(0)
+            try:
+                c = build_workload("c3", 0.0)
+                r = measure(c, max(K // 4, 3), 3)
+                extras["c3_3xtf32_gemms"] = dict(config=workload_desc("c3", c.cfg, c.loss, c.B, c.rows, world, 0.0), **r)
+                log(f"c3 with 3xTF32 GEMMs: {r['ms_per_step']:.3f} ms/step, {r['value']:.0f} pairs/s")
+                del c
+            finally:
+                L.fp_set_gemm_format(1)
+            torch.cuda.empty_cache()
+            # the REDUCED-PRECISION variant of the wide conditioner, stated apart (one product per GEMM instead of the
+            # fp32-accurate three: ~1e-3 relative on log_prob, outside the 1e-4 parity bar -- never the default)
             L.fp_set_precision(1)
             try:
                 c = build_workload("c3", 0.0)
                 r = measure(c, max(K // 4, 3), 3)
-                extras["c3_reduced_precision_single_tf32_pass"] = dict(
+                extras["c3_reduced_precision_single_pass"] = dict(
                     config=workload_desc("c3", c.cfg, c.loss, c.B, c.rows, world, 0.0), **r,
-                    precision="ONE TF32 product per tensor-core GEMM (10-bit mantissa operands, fp32 accumulation); log_prob within "
-                              "5e-3 relative of the fp32 oracle (tests/test_gpu_dropout_modes.py), NOT within the 1e-4 bar")
-                log(f"c3 single-pass TF32: {r['ms_per_step']:.3f} ms/step, {r['value']:.0f} pairs/s")
+                    precision="ONE product of the high fp16 pieces per tensor-core GEMM (11-bit mantissa operands, fp32 accumulation); "
+                              "log_prob within 5e-3 relative of the fp32 oracle (tests/test_gpu_dropout_modes.py), NOT within the "
+                              "1e-4 bar")
+                log(f"c3 single pass: {r['ms_per_step']:.3f} ms/step, {r['value']:.0f} pairs/s")
                 del c
             finally:
                 L.fp_set_precision(0)

@@ -52,7 +52,8 @@ class GemmArgs(Structure):
                 ("U", c_void_p), ("ldu", c_int64),
                 ("Msk", c_void_p), ("ldm", c_int64),
                 ("split_k", c_int32), ("mask_scale", c_float), ("drop_p", c_float), ("drop_seed", c_uint64),
-                ("a_scale", c_void_p), ("status", c_void_p)]
+                ("a_scale", c_void_p), ("status", c_void_p),
+                ("pre_hi16", c_void_p), ("pre_lo16", c_void_p), ("pre_ld", c_int64)]
 
 
 _CFG = POINTER(NsfConfig)

@@ -26,6 +26,7 @@ int launch_gemm_tc16(const fp_gemm_args* a, const void* B_hi16, const void* B_lo
 int launch_gemm_tc16_tn(const fp_gemm_args* a, cudaStream_t stream);
 int launch_prepare_gemm16(const fp_nsf_config* cfg, const float* params, float* prepared, cudaStream_t stream);
 int launch_grad_scale(const float* d_logp, int64_t n, float* out, cudaStream_t s);
+int launch_split_f16(const float* x, void* hi16, void* lo16, int64_t n, cudaStream_t stream, int32_t* status);
 int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
 int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params, float* t_hi, float* t_lo, cudaStream_t stream);
 bool tc_enabled();
@@ -126,8 +127,10 @@ static int pick_split(int64_t M, int N, int64_t K) {
 // dW[N_out, K_in] += dOut[R, N_out]^T @ Act[R, K_in]   (both operands row-major over the batch)
 // db[N_out] += colsum(dOut) rides along when `db` is given (fused into the tensor-core kernel, else its own launch)
 static int wgrad(const float* dOut, int64_t ldo, int n_out, const float* act, int64_t lda, int k_in, int64_t R,
-                 float* dW, int64_t ldw, int flags_extra, cudaStream_t s, float* db = nullptr) {
+                 float* dW, int64_t ldw, int flags_extra, cudaStream_t s, float* db = nullptr, const void* act_hi16 = nullptr,
+                 const void* act_lo16 = nullptr) {
   fp_gemm_args g{};
+  g.pre_hi16 = act_hi16; g.pre_lo16 = act_lo16; g.pre_ld = lda;      // fp16 pieces of `act`, when the caller has them
   g.A = dOut; g.lda = ldo; g.a_kmajor = 0;   // logical A'[n_out, R], element (n, r) at dOut[r*ldo + n]
   g.B = act; g.ldb = lda; g.b_kmajor = 0;    // logical B'[k_in, R], element (k, r) at act[r*lda + k]
   g.C = dW; g.ldc = ldw; g.M = n_out; g.N = k_in; g.K = R;
@@ -288,10 +291,22 @@ static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const 
   return 0;
 }
 
+// The context rows are the A operand of every column tile of the context projection (300 tiles at c3) and the B operand of
+// every row tile of its weight gradient: with 3xFP16 GEMMs they are converted to fp16 pieces ONCE per pass (workspace ctx16:
+// hi [Rc, C] then lo [Rc, C], halves) instead of once per tile.
+static bool use_ctx16(const Layout& L, const float* prepared, int64_t Rc) {
+  return prepared && tc_enabled() && gemm_fp16() && !L.smallH() && (L.C & 7) == 0 && Rc >= 256 && L.Nctx >= 512;
+}
 static int context_projection(const Layout& L, const float* params, const float* prepared, const float* ctx, int64_t Rc,
-                              float* ctx_all, cudaStream_t s) {
+                              float* ctx_all, float* ctx16, cudaStream_t s) {
   fp_gemm_args g = gemm_nt(ctx, L.C, params + L.ctx_w, L.C, ctx_all, L.Nctx, Rc, (int)L.Nctx, L.C, FP_G_BIAS);
   g.bias = params + L.ctx_b;
+  if (ctx16 && use_ctx16(L, prepared, Rc)) {
+    uint16_t* hi = reinterpret_cast<uint16_t*>(ctx16);
+    uint16_t* lo = hi + Rc * L.C;
+    FP_TRY(launch_split_f16(ctx, hi, lo, Rc * L.C, s, g_gctx.status));
+    g.pre_hi16 = hi; g.pre_lo16 = lo; g.pre_ld = L.C;
+  }
   return gemm_weight(L, prepared, L.ctx_w, &g, s);
 }
 
@@ -422,7 +437,7 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
   float* ctx_all = ws + W.ctx_all;
   float* logdet = ws + W.logdet;
   g_gctx = GemmCtx{nullptr, status};
-  FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
+  FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, ws + W.ctx16, s));
   const int fused = use_fused(cfg, L, prepared, training != 0);
   if (fused) FP_TRY(launch_gate_sigmoid(ctx_all, Rc, L.Nctx, L.H, L.S, s));
 
@@ -529,7 +544,12 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
   if (d_theta) FP_TRY(launch_affine_bwd(dth_a, zscale, d_theta, R, D, s));
 
   // ---- context projection weights: dWctx += dctx_all^T @ ctx ; db += colsum(dctx_all)
-  FP_TRY(wgrad(dctx_all, L.Nctx, (int)L.Nctx, ctx, L.C, L.C, Rc, grads + L.ctx_w, L.C, 0, s, grads + L.ctx_b));
+  if (use_ctx16(L, prepared, Rc)) {      // the forward pass left the fp16 pieces of the context rows in the workspace
+    const uint16_t* hi = reinterpret_cast<const uint16_t*>(ws + W.ctx16);
+    FP_TRY(wgrad(dctx_all, L.Nctx, (int)L.Nctx, ctx, L.C, L.C, Rc, grads + L.ctx_w, L.C, 0, s, grads + L.ctx_b, hi, hi + Rc * L.C));
+  } else {
+    FP_TRY(wgrad(dctx_all, L.Nctx, (int)L.Nctx, ctx, L.C, L.C, Rc, grads + L.ctx_w, L.C, 0, s, grads + L.ctx_b));
+  }
   return 0;
 }
 
@@ -561,7 +581,7 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
   const int D = L.D;
   float* ctx_all = ws + W.ctx_all;
   g_gctx = GemmCtx{nullptr, status};
-  FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, s));
+  FP_TRY(context_projection(L, params, prepared, ctx, Rc, ctx_all, ws + W.ctx16, s));
   const int fused = use_fused(cfg, L, prepared, false);
   if (fused) FP_TRY(launch_gate_sigmoid(ctx_all, Rc, L.Nctx, L.H, L.S, s));
 

@@ -55,9 +55,13 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_CS_BYTES + 1024 /*
 // fp16 B_hi / B_lo tiles (16 KB each): the same 64 KB stage carries twice the contraction depth, the MMAs of a k-block
 // take half the tensor-pipe time, and the TMA moves 32 instead of 48 KB per 32 contraction indices.
 constexpr int TC16_THREADS = TC_THREADS + 128;            // 3xFP16 variant: eight converting warps
-template <int EPI, bool PAIR, bool F16>
-__global__ void __launch_bounds__(F16 ? TC16_THREADS : TC_THREADS, 1)
-k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+// FMT: 0 = 3xTF32, 1 = 3xFP16 with A converted in the kernel, 2 = 3xFP16 with A PRE-SPLIT by the caller (fp16 hi / lo copies
+// of an operand many tiles share, e.g. the context batch of the context projection: mapA / mapAl are its fp16 maps, the
+// converting warps idle and the MMA warp waits for the TMA directly).
+template <int EPI, bool PAIR, int FMT>
+__global__ void __launch_bounds__(FMT == 1 ? TC16_THREADS : TC_THREADS, 1)
+k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAl,
+             const __grid_constant__ CUtensorMap mapBh,
              const __grid_constant__ CUtensorMap mapBl, const fp_gemm_args g, int nkb_total, int nchunks, int vec_all,
              long long* trace, int dbg, int gfast) {
   // PAIR: the two CTAs of a cluster compute a 256 x 128 output block with cta_group::2 MMAs (rank 0 issues them): each CTA
@@ -69,7 +73,8 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   constexpr int B_TILE = BROWS * TC_BK * 4;
   constexpr int STAGE = 2 * TC_TILE_BYTES + 2 * B_TILE;       // A (raw -> hi), A_lo, B_hi, B_lo
   constexpr int STAGES = TC_STAGES * TC_STAGE_BYTES / STAGE;
-  constexpr int NSPLITW = F16 ? 8 : 4;                        // converting warps 2 .. 2 + NSPLITW - 1, then eight epilogue warps
+  constexpr bool F16 = FMT != 0, A16 = FMT == 2;
+  constexpr int NSPLITW = FMT == 1 ? 8 : 4;                   // converting warps 2 .. 2 + NSPLITW - 1, then eight epilogue warps
   constexpr int EPIW0 = 2 + NSPLITW;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,7 +148,13 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* sb = smem + s * STAGE;
-          if (F16) {
+          if (A16) {
+            mbar_expect_tx(&full_raw[s], 4 * TC_TILE_BYTES);
+            tma_load_2d(sb, &mapA, kb * 64, (int)m0, &full_raw[s]);
+            tma_load_2d(sb + TC_TILE_BYTES, &mapAl, kb * 64, (int)m0, &full_raw[s]);
+            tma_load_2d(sb + 2 * TC_TILE_BYTES, &mapBh, kb * 64, n0, &full_raw[s]);
+            tma_load_2d(sb + 3 * TC_TILE_BYTES, &mapBl, kb * 64, n0, &full_raw[s]);
+          } else if (F16) {
             mbar_expect_tx(&full_raw[s], 4 * TC_TILE_BYTES);
             tma_load_2d(sb, &mapA, kb * 64, (int)m0, &full_raw[s]);
             tma_load_2d(sb + TC_TILE_BYTES, &mapA, kb * 64 + 32, (int)m0, &full_raw[s]);
@@ -179,7 +190,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             if (PAIR) mbar_wait_cluster(&ready[s], ph);      // both CTAs' A tiles converted, both halves of B landed
-            else mbar_wait(&ready[s], ph);
+            else mbar_wait(A16 ? &full_raw[s] : &ready[s], ph);
             tcgen05_fence_after();
             if (it < 60) FP_TRACE(it * 8 + 3);
             uint8_t* sb = smem + s * STAGE;
@@ -221,7 +232,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int pf_fl = (EPI >= 0 ? EPI : g.flags) & (FP_G_GLU_RES | FP_G_RELUMASK | FP_G_ACCUM);
     const int pf_bytes = (pf_fl && vec_all) ? TC_BN * 4 : 0;
     uint32_t it = 0;
-    for (int64_t st = cta_id; st < n_super; st += cta_step) {
+    for (int64_t st = cta_id; st < n_super && !A16; st += cta_step) {
       for (int kb = 0; kb < nkb_total; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
@@ -448,9 +459,13 @@ static_assert(3 * TN_STAGES * 8 + 2 * 2 * 8 + 8 <= 256, "barrier block");
 // 32 columns x 64 rows each, 32 KB per operand) are converted IN PLACE into MN-major fp16 hi (first 16 KB) and scaled-residual
 // lo (second 16 KB) tiles of two 64-column atoms; the four output rows of a batch row (hi / lo of two atoms) occupy exactly
 // the bytes of its four raw rows, and a warp converts whole row pairs, so the in-place hazard is warp-local.
-template <bool F16>
+// B16 (with F16): the B operand (the activations every M-tile shares) was PRE-SPLIT by the caller into fp16 hi / lo copies:
+// the TMA writes its two 64-column atoms straight into the MN-major operand layout (mapB = hi, mapBl = lo) and only A is
+// converted.
+template <bool F16, bool B16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const fp_gemm_args g,
+k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+             const __grid_constant__ CUtensorMap mapBl, const fp_gemm_args g,
              int nkb_total, int nsplit, int vec_all, int dbg, int gm) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -526,7 +541,14 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
             for (int gidx = 0; gidx < 4; ++gidx) {     // four boxes of 32 columns x 64 batch rows per operand
               tma_load_2d(sb + gidx * 8192, &mapA, m0 + gidx * 32, kb * 64, &full_raw[s]);
-              tma_load_2d(sb + 2 * TN_TILE_BYTES + gidx * 8192, &mapB, n0 + gidx * 32, kb * 64, &full_raw[s]);
+              if (!B16) tma_load_2d(sb + 2 * TN_TILE_BYTES + gidx * 8192, &mapB, n0 + gidx * 32, kb * 64, &full_raw[s]);
+            }
+            if (B16) {
+#pragma unroll
+              for (int at = 0; at < 2; ++at) {         // two atoms of 64 columns x 64 batch rows, hi and lo
+                tma_load_2d(sb + 2 * TN_TILE_BYTES + at * 8192, &mapB, n0 + at * 64, kb * 64, &full_raw[s]);
+                tma_load_2d(sb + 3 * TN_TILE_BYTES + at * 8192, &mapBl, n0 + at * 64, kb * 64, &full_raw[s]);
+              }
             }
           } else {
           mbar_expect_tx(&full_raw[s], 2 * TN_TILE_BYTES);
@@ -627,10 +649,11 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           mbar_wait(&full_raw[s], ph);
           const uint32_t sS = smem_a + (uint32_t)(s * TN_STAGE_BYTES);
           // pass p = 0..7: operand (p >> 2), row pair 4 * sw_w + (p & 3) + ... : 32 row pairs per operand over 8 warps
-          float4 raw[16];
+          constexpr int NP = B16 ? 4 : 8;
+          float4 raw[2 * NP];
           if (!(dbg & 1)) {
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
+          for (int p = 0; p < NP; ++p) {
             const int row = 2 * (8 * (p & 3) + sw_w) + rr;
             const uint32_t ra = sS + (uint32_t)(p >> 2) * (uint32_t)(2 * TN_TILE_BYTES) + src_off + (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);
@@ -641,7 +664,7 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           __syncwarp();
           if (!(dbg & 1)) {
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
+          for (int p = 0; p < NP; ++p) {
             const int row = 2 * (8 * (p & 3) + sw_w) + rr;
             float4 a = raw[2 * p], b = raw[2 * p + 1];
             if (p < 4) {
@@ -835,14 +858,18 @@ __global__ void k_split_tf32(const float* __restrict__ x, float* __restrict__ hi
 }
 
 // fp16 pieces for the 3xFP16 GEMMs: hi = fp16(x), lo = fp16((x - hi) * 2^11)
-__global__ void k_split_f16(const float* __restrict__ x, uint32_t* __restrict__ hi2, uint32_t* __restrict__ lo2, int64_t n) {
+__global__ void k_split_f16(const float* __restrict__ x, uint32_t* __restrict__ hi2, uint32_t* __restrict__ lo2, int64_t n,
+                            int32_t* __restrict__ status) {
   const int64_t np = n >> 1;
+  float amax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
     const float2 v = *reinterpret_cast<const float2*>(x + 2 * i);
     uint32_t h, l;
     split_f16x2(v.x, v.y, h, l);
     hi2[i] = h; lo2[i] = l;
+    amax = fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y)));
   }
+  if (status && !(amax <= 6.0e4f)) atomicAdd(status + 2, 1);
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     uint32_t h, l;
     split_f16x2(x[n - 1], 0.f, h, l);
@@ -1089,14 +1116,14 @@ int launch_gemm_tc(const fp_gemm_args* a, const float* B_hi, const float* B_lo, 
   case (E): {                                                                                                         \
     static bool attr_set = false;                                                                                     \
     if (!attr_set) {                                                                                                  \
-      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
-      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
     if (pair)                                                                                                         \
-      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true, false>, grid, stream, 2, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), true, 0>, grid, stream, 2, mA, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
     else                                                                                                              \
-      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false, false>, grid, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<(E), false, 0>, grid, stream, 1, mA, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
     break;                                                                                                            \
   }
   int epi = a->flags & FP_EPI_MASK;
@@ -1128,8 +1155,14 @@ int launch_gemm_tc16(const fp_gemm_args* a, const void* B_hi16, const void* B_lo
   if ((reinterpret_cast<uintptr_t>(B_hi16) & 15) || (reinterpret_cast<uintptr_t>(B_lo16) & 15)) return FP_E_NOTREADY;
   if (a->flags & (FP_G_RELU_B | FP_G_ATOMIC)) return FP_E_NOTREADY;
   if (a->split_k > 1 || a->M < 1 || a->N < 1 || a->K < 1 || a->M > 2147483647LL) return FP_E_NOTREADY;
-  CUtensorMap mA, mBh, mBl;
-  if (!get_tensor_map(a->A, a->M, a->K, a->lda, &mA)) return FP_E_NOTREADY;
+  CUtensorMap mA, mAl, mBh, mBl;
+  // A pre-split by the caller (plain / bias epilogues, no prologue, no operand scale): no conversion in the kernel
+  const bool a16 = a->pre_hi16 && a->pre_lo16 && !(a->flags & ~(FP_G_BIAS | FP_G_TF32X3)) && !a->a_scale && !(a->pre_ld & 7) &&
+                   !(reinterpret_cast<uintptr_t>(a->pre_hi16) & 15) && !(reinterpret_cast<uintptr_t>(a->pre_lo16) & 15);
+  if (a16) {
+    if (!get_tensor_map_f16(a->pre_hi16, a->M, a->K, a->pre_ld, &mA)) return FP_E_NOTREADY;
+    if (!get_tensor_map_f16(a->pre_lo16, a->M, a->K, a->pre_ld, &mAl)) return FP_E_NOTREADY;
+  } else if (!get_tensor_map(a->A, a->M, a->K, a->lda, &mA)) return FP_E_NOTREADY;
   if (!get_tensor_map_f16(B_hi16, a->N, a->K, a->ldb, &mBh)) return FP_E_NOTREADY;
   if (!get_tensor_map_f16(B_lo16, a->N, a->K, a->ldb, &mBl)) return FP_E_NOTREADY;
   const int nkb = (int)((a->K + 63) / 64);
@@ -1156,13 +1189,28 @@ int launch_gemm_tc16(const fp_gemm_args* a, const void* B_hi16, const void* B_lo
   case (E): {                                                                                                         \
     static bool attr_set = false;                                                                                     \
     if (!attr_set) {                                                                                                  \
-      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<(E), false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)); \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    FP_CUDA_OK(launch_pdl_n(k_gemm_tc_nt<(E), false, true>, grid, TC16_THREADS, stream, 1, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
+    FP_CUDA_OK(launch_pdl_n(k_gemm_tc_nt<(E), false, 1>, grid, TC16_THREADS, stream, 1, mA, mA, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, g_tc_dbg | (tc_single_pass() ? 64 : 0), gfast)); \
     break;                                                                                                            \
   }
   int epi = a->flags & FP_EPI_MASK;
+  if (a16) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+      FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nt<FP_G_BIAS, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+      attr_set = true;
+    }
+    const int dbg = g_tc_dbg | (tc_single_pass() ? 64 : 0);
+    if (epi == FP_G_BIAS)
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<FP_G_BIAS, false, 2>, grid, stream, 1, mA, mAl, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, dbg, gfast));
+    else
+      FP_CUDA_OK(launch_pdl(k_gemm_tc_nt<0, false, 2>, grid, stream, 1, mA, mAl, mBh, mBl, *a, nkb, nchunks, vec_all, g_tc_trace, dbg, gfast));
+    FP_LAUNCH_CHECK();
+    return 0;
+  }
   switch (epi) {
     case 0: case FP_G_BIAS: case FP_G_ADD_CTX: case FP_G_BIAS | FP_G_GLU_RES: case FP_G_RELUMASK:
     case FP_G_RELUMASK | FP_G_ACCUM: case FP_G_ACCUM: case FP_G_BIAS | FP_G_DROP_OUT: break;
@@ -1184,12 +1232,12 @@ int launch_gemm_tc16(const fp_gemm_args* a, const void* B_hi16, const void* B_lo
   return 0;
 }
 
-int launch_split_f16(const float* x, void* hi16, void* lo16, int64_t n, cudaStream_t stream) {
+int launch_split_f16(const float* x, void* hi16, void* lo16, int64_t n, cudaStream_t stream, int32_t* status) {
   if (n <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(x) & 7) || (reinterpret_cast<uintptr_t>(hi16) & 3) || (reinterpret_cast<uintptr_t>(lo16) & 3)) return FP_E_BADARG;
   int blocks = (int)std::min<int64_t>((n / 2 + 255) / 256 + 1, 8 * num_sms());
   ProfScope ps(TAG_OTHER, 0.0, stream);
-  k_split_f16<<<blocks, 256, 0, stream>>>(x, reinterpret_cast<uint32_t*>(hi16), reinterpret_cast<uint32_t*>(lo16), n);
+  k_split_f16<<<blocks, 256, 0, stream>>>(x, reinterpret_cast<uint32_t*>(hi16), reinterpret_cast<uint32_t*>(lo16), n, status);
   FP_LAUNCH_CHECK();
   return 0;
 }
@@ -1209,12 +1257,20 @@ static int launch_gemm_tc_tn_fmt(const fp_gemm_args* a, cudaStream_t stream, boo
   if (a->M < 1 || a->N < 1 || a->K < 1 || a->M > 65536) return FP_E_NOTREADY;
   CUtensorMap mA, mB;
   // TF32: MN-major tiles written by the TMA itself (32-byte-atom swizzle); 3xFP16: raw boxes of 64 rows, plain 128-byte swizzle
+  // B pre-split by the caller (fp16 hi / lo copies of the activations, no relu prologue): boxes of 64 halves x 64 rows
+  const bool b16 = f16 && a->pre_hi16 && a->pre_lo16 && !(a->flags & FP_G_RELU_B) && !(a->pre_ld & 7) &&
+                   !(reinterpret_cast<uintptr_t>(a->pre_hi16) & 15) && !(reinterpret_cast<uintptr_t>(a->pre_lo16) & 15);
+  CUtensorMap mBl;
   if (!get_tensor_map(a->A, a->K, a->M, a->lda, &mA, BK, !f16)) return FP_E_NOTREADY;   // [R rows, M cols]
-  if (!get_tensor_map(a->B, a->K, a->N, a->ldb, &mB, BK, !f16)) return FP_E_NOTREADY;   // [R rows, N cols]
+  if (b16) {
+    if (!get_tensor_map_f16(a->pre_hi16, a->K, a->N, a->pre_ld, &mB, 64)) return FP_E_NOTREADY;
+    if (!get_tensor_map_f16(a->pre_lo16, a->K, a->N, a->pre_ld, &mBl, 64)) return FP_E_NOTREADY;
+  } else if (!get_tensor_map(a->B, a->K, a->N, a->ldb, &mB, BK, !f16)) return FP_E_NOTREADY;   // [R rows, N cols]
   static bool attr_set = false;
   if (!attr_set) {
-    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    FP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
   const int nkb = (int)((a->K + BK - 1) / BK);
@@ -1248,10 +1304,12 @@ static int launch_gemm_tc_tn_fmt(const fp_gemm_args* a, cudaStream_t stream, boo
   int vec_all = (((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && ((a->ldc & 3) == 0)) ? 1 : 0;
   if ((a->flags & FP_G_COLSUM_A) && (reinterpret_cast<uintptr_t>(a->U) & 15)) vec_all = 0;
   ProfScope ps(TAG_GEMM_TC_TN, 2.0 * (double)a->M * (double)a->N * (double)a->K, stream, gemm_algo_bytes(a));
-  if (f16)
-    FP_CUDA_OK(launch_pdl(k_gemm_tc_tn<true>, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
+  if (b16)
+    FP_CUDA_OK(launch_pdl(k_gemm_tc_tn<true, true>, grid, stream, 1, mA, mB, mBl, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
+  else if (f16)
+    FP_CUDA_OK(launch_pdl(k_gemm_tc_tn<true, false>, grid, stream, 1, mA, mB, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
   else
-    FP_CUDA_OK(launch_pdl(k_gemm_tc_tn<false>, grid, stream, 1, mA, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
+    FP_CUDA_OK(launch_pdl(k_gemm_tc_tn<false, false>, grid, stream, 1, mA, mB, mB, *a, nkb, nsplit, vec_all, g_tc_dbg | (tc_single_pass() ? 64 : 0), gm));
   FP_LAUNCH_CHECK();
   return 0;
 }
@@ -1281,7 +1339,7 @@ int launch_prepare_gemm16(const fp_nsf_config* cfg, const float* params, float* 
   Layout L(cfg);
   uint16_t* hi = reinterpret_cast<uint16_t*>(prepared + L.prepG16Hi());
   uint16_t* lo = reinterpret_cast<uint16_t*>(prepared + L.prepG16Lo());
-  { int r = launch_split_f16(params + L.ctx_w, hi + 2 * L.ctx_w, lo + 2 * L.ctx_w, L.Nctx * L.C, stream); if (r) return r; }
+  { int r = launch_split_f16(params + L.ctx_w, hi + 2 * L.ctx_w, lo + 2 * L.ctx_w, L.Nctx * L.C, stream, nullptr); if (r) return r; }
   ProfScope ps(TAG_OTHER, 0.0, stream);
   {
     const int64_t nmax = (int64_t)std::max(L.H, L.dPmax()) * L.H;
@@ -1329,7 +1387,7 @@ int fp_gemm_tc16_tn(const fp_gemm_args* args, void* stream) {
   return fp::launch_gemm_tc16_tn(args, (cudaStream_t)stream);
 }
 int fp_split_f16(const float* x, void* hi16, void* lo16, int64_t n, void* stream) {
-  return fp::launch_split_f16(x, hi16, lo16, n, (cudaStream_t)stream);
+  return fp::launch_split_f16(x, hi16, lo16, n, (cudaStream_t)stream, nullptr);
 }
 int fp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
   return fp::launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);

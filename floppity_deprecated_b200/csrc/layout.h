@@ -132,7 +132,7 @@ struct Layout {
 
 // workspace carve; identical arithmetic in forward and backward so saved activations are found again
 struct Workspace {
-  int64_t ctx_all, logdet;
+  int64_t ctx_all, logdet, ctx16;
   // inference
   int64_t th_a, th_b, h, t, prm;
   // training
@@ -149,6 +149,7 @@ struct Workspace {
     auto take = [&](int64_t n) { int64_t r = o; o += al32(n); return r; };
     ctx_all = take(Rc * L.Nctx);
     logdet = take(R);
+    ctx16 = take(Rc * L.C);      // fp16 hi | lo pieces of the context rows (3xFP16 context projection and its weight gradient)
     th_a = th_b = h = t = prm = th_st = th_sp = act = dth_a = dth_b = dh = dt = du = dprm = dctx_all = dub = gscale = 0;
     if (!training) {
       th_a = take(R * L.D); th_b = take(R * L.D);

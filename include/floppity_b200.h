@@ -133,6 +133,9 @@ typedef struct fp_gemm_args {
                           * converted as s * A and the result scaled back by 1/s -- brings gradient operands (~1/batch)
                           * into fp16's range; NULL = 1 */
   int32_t* status;       /* fp_gemm_tc16*: optional status words; [2] counts converting threads that met |s * A| > 6e4 */
+  const void* pre_hi16;  /* fp_gemm_tc16: optional fp16 pieces (fp_split_f16) of A [M, K]; fp_gemm_tc16_tn: of B [K, N] -- an */
+  const void* pre_lo16;  /* operand many tiles share is converted once by the caller instead of once per tile; leading      */
+  int64_t pre_ld;        /* dimension pre_ld in halves (a multiple of 8); no relu prologue / operand scale on that operand  */
 } fp_gemm_args;
 int fp_gemm(const fp_gemm_args* args, void* stream);
 /* Same contract on the tcgen05 tensor cores with the fp32-accurate 3xTF32 split (A split in-kernel, B_hi/B_lo

@@ -316,6 +316,16 @@ def test_fp16_piece_gemm_matches_fp64(M, N, K, lda, ldb):
     want = Afull[:, :K].double() @ Bd.T + bias.double()
     got = run(Afull, 0)
     assert (got.double() - want).abs().max() < 2e-5, (got.double() - want).abs().max()
+    if lda % 8 == 0:      # A pre-split by the caller (what the engine does with the context rows): no conversion in the kernel
+        ah, al = torch.empty(M, lda, device="cuda", dtype=torch.float16), torch.empty(M, lda, device="cuda", dtype=torch.float16)
+        _lib.check(L.fp_split_f16(_lib.ptr(Afull), _lib.ptr(ah), _lib.ptr(al), Afull.numel(), _lib.stream()), "split16 A")
+        out = torch.empty(M, N, device="cuda")
+        a = _lib.GemmArgs()
+        a.A, a.lda, a.a_kmajor, a.B, a.ldb, a.b_kmajor = _lib.ptr(Afull), lda, 1, _lib.ptr(Bp), ldb, 1
+        a.C, a.ldc, a.M, a.N, a.K, a.flags, a.bias, a.split_k = _lib.ptr(out), N, M, N, K, _lib.G_BIAS, _lib.ptr(bias), 1
+        a.pre_hi16, a.pre_lo16, a.pre_ld = _lib.ptr(ah), _lib.ptr(al), lda
+        _lib.check(L.fp_gemm_tc16(a, _lib.ptr(h16), _lib.ptr(l16), _lib.stream()), "gemm16 presplit")
+        assert (out.double() - want).abs().max() < 2e-5
     want_r = Afull[:, :K].double().clamp_min(0) @ Bd.T + bias.double()
     assert (run(Afull, _lib.G_RELU_A).double() - want_r).abs().max() < 2e-5
     # gradient-sized operand (~1e-8): exact power-of-two scale in, out again in the epilogue
@@ -353,6 +363,20 @@ def test_fp16_piece_weight_gradient_matches_fp64(M, N, R):
         cs = dOut.double().sum(0)
         assert (db.double() - cs).abs().max() < 2e-5 * cs.abs().max()
     assert st.tolist()[2] == 0
+    if N % 8 == 0:        # the activations pre-split by the caller: the TMA writes the MN-major operand tiles directly
+        bh, bl = torch.empty(R, N, device="cuda", dtype=torch.float16), torch.empty(R, N, device="cuda", dtype=torch.float16)
+        _lib.check(L.fp_split_f16(_lib.ptr(act), _lib.ptr(bh), _lib.ptr(bl), act.numel(), _lib.stream()), "split16 B")
+        dW = torch.zeros(M, N, device="cuda"); db = torch.zeros(M, device="cuda")
+        b = _lib.GemmArgs()
+        b.A, b.lda, b.a_kmajor, b.B, b.ldb, b.b_kmajor = _lib.ptr(dOut), M, 0, _lib.ptr(act), N, 0
+        b.C, b.ldc, b.M, b.N, b.K, b.split_k = _lib.ptr(dW), N, M, N, R, 1
+        b.flags, b.U, b.a_scale, b.status = _lib.G_ATOMIC | _lib.G_COLSUM_A, _lib.ptr(db), _lib.ptr(sc), _lib.ptr(st)
+        b.pre_hi16, b.pre_lo16, b.pre_ld = _lib.ptr(bh), _lib.ptr(bl), N
+        _lib.check(L.fp_gemm_tc16_tn(b, _lib.stream()), "wgrad16 presplit")
+        want = dOut.double().T @ act.double()
+        assert (dW.double() - want).abs().max() < 2e-5 * want.abs().max()
+        cs = dOut.double().sum(0)
+        assert (db.double() - cs).abs().max() < 2e-5 * cs.abs().max()
 
 
 def _kernel_launches(fn):

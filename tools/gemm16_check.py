@@ -124,4 +124,24 @@ if __name__ == "__main__":
     print("TN ragged  [705 x 510(ld 512)]: skipped (ld must be x4)", flush=True)
     if which == "all":
         print("TN ctx wgrad [38400 x 2000] over 18944 rows     ", tn(38400, 2000, R), flush=True)
+        # the same two context GEMMs with the shared operand pre-split by the caller
+        A = torch.randn(R, 2000, device="cuda"); B = torch.randn(38400, 2000, device="cuda") / 2000 ** 0.5
+        ah, al = torch.empty(R, 2000, device="cuda", dtype=torch.float16), torch.empty(R, 2000, device="cuda", dtype=torch.float16)
+        bh, bl = torch.empty_like(B, dtype=torch.float16), torch.empty_like(B, dtype=torch.float16)
+        L.fp_split_f16(A.data_ptr(), ah.data_ptr(), al.data_ptr(), A.numel(), s)
+        L.fp_split_f16(B.data_ptr(), bh.data_ptr(), bl.data_ptr(), B.numel(), s)
+        C = torch.empty(R, 38400, device="cuda"); bias = torch.randn(38400, device="cuda")
+        a = _lib.GemmArgs()
+        a.A, a.lda, a.a_kmajor, a.B, a.ldb, a.b_kmajor = A.data_ptr(), 2000, 1, B.data_ptr(), 2000, 1
+        a.C, a.ldc, a.M, a.N, a.K, a.flags, a.bias, a.split_k = C.data_ptr(), 38400, R, 38400, 2000, _lib.G_BIAS, bias.data_ptr(), 1
+        a.pre_hi16, a.pre_lo16, a.pre_ld = ah.data_ptr(), al.data_ptr(), 2000
+        print("NT ctx fwd, A pre-split: us", round(timeit(lambda: L.fp_gemm_tc16(ctypes.byref(a), bh.data_ptr(), bl.data_ptr(), s)), 1),
+              " split of A: us", round(timeit(lambda: L.fp_split_f16(A.data_ptr(), ah.data_ptr(), al.data_ptr(), A.numel(), s)), 1), flush=True)
+        dW = torch.zeros(38400, 2000, device="cuda"); db = torch.zeros(38400, device="cuda")
+        b = _lib.GemmArgs()
+        b.A, b.lda, b.a_kmajor, b.B, b.ldb, b.b_kmajor = C.data_ptr(), 38400, 0, A.data_ptr(), 2000, 0
+        b.C, b.ldc, b.M, b.N, b.K, b.split_k = dW.data_ptr(), 2000, 38400, 2000, R, 1
+        b.flags, b.U = _lib.G_ATOMIC | _lib.G_COLSUM_A, db.data_ptr()
+        b.pre_hi16, b.pre_lo16, b.pre_ld = ah.data_ptr(), al.data_ptr(), 2000
+        print("TN ctx wgrad, B pre-split: us", round(timeit(lambda: L.fp_gemm_tc16_tn(ctypes.byref(b), s)), 1), flush=True)
         print("NT ctx fwd [18944 x 2000] x [38400 x 2000]^T    ", nt(R, 38400, 2000), flush=True)
