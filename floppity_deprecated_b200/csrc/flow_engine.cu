@@ -27,6 +27,7 @@ int launch_gemm_tc16_tn(const fp_gemm_args* a, cudaStream_t stream);
 int launch_prepare_gemm16(const fp_nsf_config* cfg, const float* params, float* prepared, cudaStream_t stream);
 int launch_grad_scale(const float* d_logp, int64_t n, float* out, cudaStream_t s);
 int launch_split_f16(const float* x, void* hi16, void* lo16, int64_t n, cudaStream_t stream, int32_t* status);
+int launch_pad_rows(const float* in, int D, float* out, int Dp, int64_t R, cudaStream_t s);
 int launch_split_tf32(const float* x, float* hi, float* lo, int64_t n, cudaStream_t stream);
 int launch_transpose_split_weights(const fp_nsf_config* cfg, const float* params, float* t_hi, float* t_lo, cudaStream_t stream);
 bool tc_enabled();
@@ -83,7 +84,12 @@ bool tc_enabled() { return mode_on(0); }
 bool fused_enabled() { return mode_on(1); }
 bool cond_fused_f16() { return mode_on(2); }
 bool smallh_enabled() { return mode_on(3); }
-bool gemm_fp16() { return mode_on(5); }     // 3xFP16 operand pieces in the stand-alone tensor-core GEMMs (else 3xTF32)
+bool gemm_fp16() { return mode_on(5); }
+static bool pad_theta() {      // FLOPPITY_PAD_THETA=0: first-layer GEMMs of D % 8 != 0 flows stay on the SIMT kernel (A/B timing)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FLOPPITY_PAD_THETA"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}     // 3xFP16 operand pieces in the stand-alone tensor-core GEMMs (else 3xTF32)
 
 // per-call context of the 3xFP16 GEMMs: the device scalar that scales gradient operands into fp16's range (backward pass
 // only) and the status words that count operands beyond it
@@ -249,7 +255,7 @@ struct CondBufs {
 static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const float* params, const float* prepared, int i,
                                const float* theta_i,
                                const float* ctx_all, int64_t R, int ctx_div, const CondBufs& b, bool training,
-                               uint64_t seed, int fused, int32_t* status, cudaStream_t s) {
+                               uint64_t seed, int fused, int32_t* status, cudaStream_t s, float* th_pad = nullptr) {
   const int H = L.H, D = L.D, lH = L.ldH();      // lH: row stride of the hidden-activation buffers
   const float drop = training ? cfg->dropout_p : 0.f;
   if (fused == 2)   // hidden <= 64: the whole chain in one persistent kernel with the layer's weights resident in shared memory
@@ -263,7 +269,19 @@ static int conditioner_forward(const fp_nsf_config* cfg, const Layout& L, const 
   {  // initial layer: h0 = theta_i @ W0x^T + (ctx @ W0ctx^T + b0)   [the bracket is a column block of ctx_all]
     fp_gemm_args g = gemm_nt(theta_i, D, params + L.w0x(i), D, b.h[0], lH, R, H, D, FP_G_ADD_CTX);
     g.G = ctx_all + L.ctxCol(i, 0); g.ldg = L.Nctx; g.ctx_div = ctx_div;
-    FP_TRY(gemm_weight(L, prepared, L.w0x(i), &g, s));
+    int r0 = FP_E_NOTREADY;
+    if (th_pad && prepared && tc_enabled() && gemm_fp16() && pad_theta()) {
+      // D = 30: 120-byte theta rows are not TMA-addressable -- a copy padded to 32 floats (and the padded fp16 W0x) puts this
+      // GEMM on the tensor cores; the copy stays in the workspace for the weight gradient
+      const int Dp = Layout::ld16(D);
+      FP_TRY(launch_pad_rows(theta_i, D, th_pad, Dp, R, s));
+      fp_gemm_args g16 = g;
+      g16.A = th_pad; g16.lda = Dp; g16.ldb = Dp; g16.status = g_gctx.status;
+      r0 = launch_gemm_tc16(&g16, reinterpret_cast<const uint16_t*>(prepared + L.prepG16Hi()) + 2 * L.w0x(i),
+                            reinterpret_cast<const uint16_t*>(prepared + L.prepG16Lo()) + 2 * L.w0x(i), s);
+      if (r0 != 0 && r0 != FP_E_NOTREADY) return r0;
+    }
+    if (r0 != 0) FP_TRY(gemm_weight(L, prepared, L.w0x(i), &g, s));
   }
   for (int k = 0; k < L.Bk; ++k) {
     {  // t' = dropout(relu(h) @ W1^T + b1): relu(t') = dropout(relu(t)), (t' > 0) = relu mask AND keep mask
@@ -459,7 +477,8 @@ int fp_nsf_logprob_forward(const fp_nsf_config* cfg, const float* params, const 
       b.prm = ws + W.prm;
       th_next = (th_cur == ws + W.th_a) ? ws + W.th_b : ws + W.th_a;
     }
-    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, fused, status, s));
+    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, training != 0, dropout_seed, fused, status, s,
+                               (W.thp_sz > 0 && !fused) ? ws + W.thpad(training ? i : 0) : nullptr));
     FP_TRY(launch_rqs_apply(false, cfg, i & 1, th_cur, b.prm, th_next, th_sp, logdet, nullptr, R, status,
                             prepared + L.prepM(i), nullptr, 1.f, params + L.luBias(i), prepared + L.prepLogdet(i), L.ldP(i), s));
     th_cur = th_next;
@@ -538,7 +557,10 @@ int fp_nsf_logprob_backward(const fp_nsf_config* cfg, const float* params, const
     }
     // ---- initial layer: h0 = theta_i @ W0x^T + ctx slot 0
     FP_TRY(launch_ctx_reduce(dh, dctx_all + L.ctxCol(i, 0), L.Nctx, Rc, A, H, lH, s));
-    FP_TRY(wgrad(dh, lH, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, s));
+    if (W.thp_sz > 0 && !fused && prepared && tc_enabled() && gemm_fp16() && pad_theta())      // the padded theta copy the forward pass left (see there)
+      FP_TRY(wgrad(dh, lH, H, ws + W.thpad(i), Layout::ld16(D), D, R, grads + L.w0x(i), D, 0, s));
+    else
+      FP_TRY(wgrad(dh, lH, H, ws + W.thst(i), D, D, R, grads + L.w0x(i), D, 0, s));
     FP_TRY(dgrad_weight(L, prepared, L.tW0(i), H, dh, lH, H, params + L.w0x(i), D, D, R, dth_a, D, FP_G_ACCUM, nullptr, 0, 1.f, s));
   }
   if (d_theta) FP_TRY(launch_affine_bwd(dth_a, zscale, d_theta, R, D, s));
@@ -593,7 +615,8 @@ int fp_nsf_sample(const fp_nsf_config* cfg, const float* params, const float* pr
     for (int k = 0; k <= L.Bk; ++k) b.h[k] = ws + W.h;
     for (int k = 0; k < L.Bk; ++k) { b.t[k] = ws + W.t; b.u[k] = nullptr; }
     b.prm = ws + W.prm;
-    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, false, 0, fused, status, s));
+    FP_TRY(conditioner_forward(cfg, L, params, prepared, i, th_cur, ctx_all, R, ctx_div, b, false, 0, fused, status, s,
+                               (W.thp_sz > 0 && !fused) ? ws + W.thpad(0) : nullptr));
     // spline inverse of layer i fused with the inverse LULinear of layer i-1
     const float* M = (i > 0) ? prepared + L.prepMinv(i - 1) : nullptr;
     const float* pre = (i > 0) ? params + L.luBias(i - 1) : nullptr;

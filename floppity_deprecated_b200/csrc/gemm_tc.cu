@@ -889,6 +889,20 @@ __global__ void k_split_f16_weights(const float* __restrict__ params, uint16_t* 
   if (which == per - 1) { woff = L.wf(layer); n = (int64_t)L.dP(layer) * L.H; }
   else if (which == per - 2) { woff = L.w0x(layer); n = (int64_t)L.H * L.D; }
   else { woff = (which & 1) ? L.w2(layer, which >> 1) : L.w1(layer, which >> 1); n = (int64_t)L.H * L.H; }
+  if (which == per - 2 && (L.D & 7) != 0) {
+    // W0x [H, D] with D not a multiple of 8: rows padded to ld16(D) halves (zeros), when the region has room (D >= 4)
+    if (L.D < 4) return;
+    const int ld = Layout::ld16(L.D);
+    const int64_t np = (int64_t)L.H * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / ld), c = (int)(i % ld);
+      uint32_t h, l;
+      split_f16x2(c < L.D ? params[woff + (int64_t)r * L.D + c] : 0.f, 0.f, h, l);
+      hi[2 * woff + i] = (uint16_t)(h & 0xFFFFu);
+      lo[2 * woff + i] = (uint16_t)(l & 0xFFFFu);
+    }
+    return;
+  }
   uint32_t* hi2 = reinterpret_cast<uint32_t*>(hi + 2 * woff);
   uint32_t* lo2 = reinterpret_cast<uint32_t*>(lo + 2 * woff);
   const float* x = params + woff;

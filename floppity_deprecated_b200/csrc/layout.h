@@ -132,7 +132,7 @@ struct Layout {
 
 // workspace carve; identical arithmetic in forward and backward so saved activations are found again
 struct Workspace {
-  int64_t ctx_all, logdet, ctx16;
+  int64_t ctx_all, logdet, ctx16, thp, thp_sz;
   // inference
   int64_t th_a, th_b, h, t, prm;
   // training
@@ -149,6 +149,10 @@ struct Workspace {
     auto take = [&](int64_t n) { int64_t r = o; o += al32(n); return r; };
     ctx_all = take(Rc * L.Nctx);
     logdet = take(R);
+    // theta rows padded to a multiple of 8 floats (D = 30 -> 32: 120-byte rows are not TMA-addressable): the A operand of the
+    // first conditioner GEMM and the B operand of its weight gradient; one buffer per layer when training
+    thp_sz = ((L.D & 7) != 0 && L.D >= 4 && !L.smallH()) ? al32(R * Layout::ld16(L.D)) : 0;
+    thp = take((training ? L.T : 1) * thp_sz);
     ctx16 = take(Rc * L.C);      // fp16 hi | lo pieces of the context rows (3xFP16 context projection and its weight gradient)
     th_a = th_b = h = t = prm = th_st = th_sp = act = dth_a = dth_b = dh = dt = du = dprm = dctx_all = dub = gscale = 0;
     if (!training) {
@@ -176,6 +180,7 @@ struct Workspace {
     }
     total = o;
   }
+  int64_t thpad(int i) const { return thp + (int64_t)i * thp_sz; }      // valid when thp_sz > 0
   int64_t thst(int i) const { return th_st + (int64_t)i * al32(R * L.D); }
   int64_t thsp(int i) const { return th_sp + (int64_t)i * al32(R * L.D); }
   int64_t hsz() const { return al32(R * L.ldH()); }

@@ -423,13 +423,26 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   const float bc2 = 1.f - powf(b2, (float)step);
   const float step_size = lr / bc1;
   const float bc2s = sqrtf(bc2);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i] * gs;
-    float mi = m[i] + (1.f - b1) * (gi - m[i]);            // torch: exp_avg.lerp_(grad, 1-beta1)
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    float denom = sqrtf(vi) / bc2s + eps;
-    p[i] -= step_size * (mi / denom);
+  auto upd = [&](float& pi, float gr, float& mi, float& vi) {
+    const float gi = gr * gs;
+    mi = mi + (1.f - b1) * (gi - mi);                      // torch: exp_avg.lerp_(grad, 1-beta1)
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2s + eps;
+    pi -= step_size * (mi / denom);
+  };
+  // four 16-byte streams in, three out per thread and iteration (the buffers come from the caching allocator: 16-byte aligned)
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  const int64_t n4 = vec ? n >> 2 : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+    reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V; reinterpret_cast<float4*>(p)[i] = P;
+  }
+  for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
   }
 }
 
@@ -571,6 +584,21 @@ int launch_sum(const float* x, int64_t n, float scale, float* out, cudaStream_t 
   FP_LAUNCH_CHECK(); return 0;
 }
 
+// out[r, 0..Dp) = in[r, 0..D) followed by zeros (rows padded to a TMA-addressable stride)
+__global__ void k_pad_rows(const float* __restrict__ in, int D, float* __restrict__ out, int Dp, int64_t R) {
+  const int64_t n = R * Dp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / Dp; const int c = (int)(e - r * Dp);
+    out[e] = c < D ? in[r * D + c] : 0.f;
+  }
+}
+int launch_pad_rows(const float* in, int D, float* out, int Dp, int64_t R, cudaStream_t s) {
+  if (R <= 0) return 0;
+  ProfScope ps(TAG_OTHER, 0.0, s);
+  k_pad_rows<<<(int)std::min<int64_t>((R * Dp + 255) / 256, 8 * num_sms()), 256, 0, s>>>(in, D, out, Dp, R);
+  FP_LAUNCH_CHECK(); return 0;
+}
+
 // Power-of-two scale for the gradient operands of the 3xFP16 GEMMs: s = 2^-e with 2^(e-1) <= max|d_logp| < 2^e, so the
 // upstream gradient enters the backward pass with its largest element in [0.5, 1) (every later gradient tensor is linear
 // in it); s = 1 for an all-zero or non-finite upstream gradient.  One block.
@@ -656,7 +684,7 @@ int fp_grad_sumsq(const float* grads, int64_t n, float* sumsq, void* stream) {
 }
 int fp_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, const int32_t* step_dev, float max_norm, float grad_scale, const float* sumsq, void* stream) {
-  int blocks = (int)std::min<int64_t>((n + 255) / 256, 8 * num_sms());
+  int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, 8 * num_sms());
   if (blocks < 1) blocks = 1;
   ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_adam<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr, beta1, beta2, eps, step_dev, max_norm,

@@ -465,11 +465,11 @@ def test_small_hidden_kernel_handles_wide_ranges():
 
 
 def test_reduced_precision_single_pass_variant_is_close_and_stated_apart():
-    """fp_set_precision(1): ONE TF32 product per stand-alone tensor-core GEMM instead of the fp32-accurate three (the
-    wide-conditioner path).  It is NOT within the 1e-4 bar and is never the default: stated tolerance 5e-3 relative on
-    log_prob; the gradient as a whole keeps its direction (cosine > 0.999 with the oracle's) while single tensors may be off
-    by up to 20 % of their maximum (10-bit operands flip relu decisions); switching it off restores the fp32-accurate result
-    bit for bit."""
+    """fp_set_precision(1): ONE product (of the high operand pieces) per stand-alone tensor-core GEMM instead of the
+    fp32-accurate three (the wide-conditioner path).  It is NOT within the 1e-4 bar and is never the default: stated tolerance
+    5e-3 relative on log_prob; the gradient as a whole keeps its direction (cosine > 0.999 with the oracle's) while single
+    tensors may be off by up to 30 % of their maximum (11-bit operands flip relu decisions); switching it off restores the
+    fp32-accurate result bit for bit."""
     L = _lib.lib()
     D, C, H, T, K, Bk = SHAPES["hidden512"]
     onet, net, theta, x = _pair(D, C, H, T, K, Bk, 0.0, seed=12)
@@ -498,9 +498,9 @@ def test_reduced_precision_single_pass_variant_is_close_and_stated_apart():
     a = np.concatenate([g_fast[k].ravel() for k, _ in onet.named_parameters()])
     b = np.concatenate([p.grad.numpy().ravel() for _, p in onet.named_parameters()])
     cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
-    assert cos > 0.999 and worst < 0.2, (cos, worst)
+    assert cos > 0.999 and worst < 0.3, (cos, worst)
     net.eval()
     with torch.no_grad():
         again = net.log_prob(theta[:R].cuda(), x[:R].cuda()).cpu().numpy()
     assert np.array_equal(again, exact)
-    print(f"single-pass TF32 variant: log_prob {err:.1e} relative, gradient cosine {cos:.6f}, worst tensor {worst:.1e} of its maximum")
+    print(f"single-pass variant: log_prob {err:.1e} relative, gradient cosine {cos:.6f}, worst tensor {worst:.1e} of its maximum")
