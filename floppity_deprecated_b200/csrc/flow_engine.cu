@@ -418,10 +418,20 @@ int fp_nsf_prepare(const fp_nsf_config* cfg, const float* params, float* prepare
   ProfScope ps(TAG_OTHER, 0.0, (cudaStream_t)stream);
   k_lu_prepare<<<cfg->T, 128, sm, (cudaStream_t)stream>>>(params, prepared, *cfg);
   FP_LAUNCH_CHECK();
-  if (tc_enabled()) {   // TF32 hi / lo split of every weight, once per optimiser step
+  if (tc_enabled()) {   // operand copies of every weight, once per optimiser step
     Layout L(cfg);
-    FP_TRY(launch_split_tf32(params, prepared + L.prepHi(), prepared + L.prepLo(), L.total(), (cudaStream_t)stream));
-    FP_TRY(launch_transpose_split_weights(cfg, params, prepared + L.prepTHi(), prepared + L.prepTLo(), (cudaStream_t)stream));
+    if (gemm_fp16() && !L.smallH()) {
+      // 3xFP16 GEMMs (launch_prepare_gemm16 below): the TF32 copies are only the fall-back of matrices whose contraction length
+      // is not a multiple of 8 halves (c2's 500 spectral bins), so only those are made; the transposed fp16 copies are padded
+      // to 8 and never fall back
+      if (L.C & 7) FP_TRY(launch_split_tf32(params, prepared + L.prepHi(), prepared + L.prepLo(), L.layers, (cudaStream_t)stream));
+      if ((L.H & 7) || L.D < 4 || ((L.D & 7) && !pad_theta()) || (fused_enabled() && !cond_fused_f16()))      // (the fused kernel's 3xTF32 mode reads them too)
+        FP_TRY(launch_split_tf32(params + L.layers, prepared + L.prepHi() + L.layers, prepared + L.prepLo() + L.layers,
+                                 L.total() - L.layers, (cudaStream_t)stream));
+    } else {
+      FP_TRY(launch_split_tf32(params, prepared + L.prepHi(), prepared + L.prepLo(), L.total(), (cudaStream_t)stream));
+      FP_TRY(launch_transpose_split_weights(cfg, params, prepared + L.prepTHi(), prepared + L.prepTLo(), (cudaStream_t)stream));
+    }
     FP_TRY(launch_cond_prepare(cfg, params, prepared, (cudaStream_t)stream));     // fp16 operand copies for the fused conditioner
     if (!L.smallH()) FP_TRY(launch_prepare_gemm16(cfg, params, prepared, (cudaStream_t)stream));   // and for the 3xFP16 GEMMs
   }

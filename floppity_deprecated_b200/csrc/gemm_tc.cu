@@ -228,6 +228,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int tid_s = threadIdx.x - 64;       // 0..127
     const bool relu_a = (g.flags & FP_G_RELU_A) != 0;
     const float a_s = (F16 && g.a_scale) ? __ldg(g.a_scale) : 1.f;      // power-of-two operand scale (gradient operands)
+    const bool scaled = a_s != 1.f;
     float amax = 0.f;                                                     // fp16 range guard
     const int pf_fl = (EPI >= 0 ? EPI : g.flags) & (FP_G_GLU_RES | FP_G_RELUMASK | FP_G_ACCUM);
     const int pf_bytes = (pf_fl && vec_all) ? TC_BN * 4 : 0;
@@ -278,7 +279,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const int r = (i >> 1) * 64 + 2 * q8 + (u >> 2);
             const int cp = (u & 3) + 4 * ((u >> 2) ^ (i & 1));
             float4 a = raw[2 * i], b = raw[2 * i + 1];
-            a.x *= a_s; a.y *= a_s; a.z *= a_s; a.w *= a_s; b.x *= a_s; b.y *= a_s; b.z *= a_s; b.w *= a_s;
+            if (scaled) { a.x *= a_s; a.y *= a_s; a.z *= a_s; a.w *= a_s; b.x *= a_s; b.y *= a_s; b.z *= a_s; b.w *= a_s; }
             if (relu_a) {
               a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
               b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
@@ -637,10 +638,12 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const uint32_t src_off = (uint32_t)(2 * at + (cp >> 2)) * 8192u;      // raw box of these 8 columns
       const uint32_t cc = 2u * (uint32_t)(cp & 3);
       const float a_s = g.a_scale ? __ldg(g.a_scale) : 1.f;
+      const bool scaled = a_s != 1.f;
       float amax = 0.f;
       for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
         int m0, n0, kb0, kb1; item_decode(w, m0, n0, kb0, kb1);
         float cs8[8];
+        const bool do_cs = colsum && n0 == 0;                      // the tiles of the first column block carry the bias gradient
 #pragma unroll
         for (int j = 0; j < 8; ++j) cs8[j] = 0.f;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -668,8 +671,10 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const int row = 2 * (8 * (p & 3) + sw_w) + rr;
             float4 a = raw[2 * p], b = raw[2 * p + 1];
             if (p < 4) {
-              a.x *= a_s; a.y *= a_s; a.z *= a_s; a.w *= a_s; b.x *= a_s; b.y *= a_s; b.z *= a_s; b.w *= a_s;
-              cs8[0] += a.x; cs8[1] += a.y; cs8[2] += a.z; cs8[3] += a.w; cs8[4] += b.x; cs8[5] += b.y; cs8[6] += b.z; cs8[7] += b.w;
+              if (scaled) { a.x *= a_s; a.y *= a_s; a.z *= a_s; a.w *= a_s; b.x *= a_s; b.y *= a_s; b.z *= a_s; b.w *= a_s; }
+              if (do_cs) {
+                cs8[0] += a.x; cs8[1] += a.y; cs8[2] += a.z; cs8[3] += a.w; cs8[4] += b.x; cs8[5] += b.y; cs8[6] += b.z; cs8[7] += b.w;
+              }
             } else if (relu_b) {
               a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
               b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
@@ -689,7 +694,7 @@ k_gemm_tc_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           __syncwarp();
           if (lane == 0) mbar_arrive(&ready[s]);
         }
-        if (colsum && n0 == 0 && kb0 < kb1) {
+        if (do_cs && kb0 < kb1) {
           const float inv = 1.f / a_s;
 #pragma unroll
           for (int j = 0; j < 8; ++j) cs8[j] = (cs8[j] + __shfl_xor_sync(0xffffffffu, cs8[j], 12)) * inv;
