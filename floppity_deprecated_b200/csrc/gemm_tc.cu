@@ -230,7 +230,7 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const float a_s = (F16 && g.a_scale) ? __ldg(g.a_scale) : 1.f;      // power-of-two operand scale (gradient operands)
     const bool scaled = a_s != 1.f;
     float amax = 0.f;                                                     // fp16 range guard
-    const int pf_fl = (EPI >= 0 ? EPI : g.flags) & (FP_G_GLU_RES | FP_G_RELUMASK | FP_G_ACCUM);
+    const int pf_fl = (EPI >= 0 ? EPI : g.flags) & (FP_G_GLU_RES | FP_G_RELUMASK | FP_G_ACCUM | FP_G_ADD_CTX);
     const int pf_bytes = (pf_fl && vec_all) ? TC_BN * 4 : 0;
     uint32_t it = 0;
     for (int64_t st = cta_id; st < n_super && !A16; st += cta_step) {
@@ -245,6 +245,8 @@ k_gemm_tc_nt(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const uint32_t nb = (uint32_t)min(pf_bytes, (g.N - n0p) * 4) & ~15u;
           if (m < g.M && nb > 0) {
             if (pf_fl & FP_G_GLU_RES) l2_prefetch(g.Rsd + m * g.ldr + n0p, nb);
+            if ((pf_fl & (FP_G_GLU_RES | FP_G_ADD_CTX)) && (g.ldg & 3) == 0)      // gate / context slot of this row's context row
+              l2_prefetch(g.G + (g.ctx_div > 0 ? m / g.ctx_div : (int64_t)0) * g.ldg + n0p, nb);
             if (pf_fl & FP_G_RELUMASK) l2_prefetch(g.Msk + m * g.ldm + n0p, nb);
             if (pf_fl & FP_G_ACCUM) l2_prefetch(g.C + m * g.ldc + n0p, nb);
           }

@@ -554,8 +554,24 @@ int launch_gate_sigmoid(float* ctx_all, int64_t Rc, int64_t Nctx, int H, int S, 
   k_gate_sigmoid<<<(unsigned)std::min<int64_t>((n4 + 255) / 256, 16 * (int64_t)num_sms()), 256, 0, s>>>(ctx_all, n4, H, S);
   FP_LAUNCH_CHECK(); return 0;
 }
+// four columns per thread (16-byte accesses) when the rows allow it
+__global__ void k_ctx_reduce4(const float* __restrict__ dh, float* __restrict__ dG, int64_t ldg, int64_t Rc, int A, int H4, int ldh) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Rc * H4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t cr = i / H4; const int j = (int)(i - cr * H4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < A; ++a) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dh + (cr * A + a) * ldh + j));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dG + cr * ldg + j) = acc;
+  }
+}
 int launch_ctx_reduce(const float* dh, float* dG, int64_t ldg, int64_t Rc, int A, int H, int ldh, cudaStream_t s) {
   ProfScope ps(TAG_OTHER, 0.0, s);
+  if ((H & 3) == 0 && (ldh & 3) == 0 && (ldg & 3) == 0 && ((reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(dG)) & 15) == 0) {
+    k_ctx_reduce4<<<(int)std::min<int64_t>((Rc * (H / 4) + 255) / 256, 16 * num_sms()), 256, 0, s>>>(dh, dG, ldg, Rc, A, H / 4, ldh);
+    FP_LAUNCH_CHECK(); return 0;
+  }
   k_ctx_reduce<<<nblk(Rc * H, 256), 256, 0, s>>>(dh, dG, ldg, Rc, A, H, ldh);
   FP_LAUNCH_CHECK(); return 0;
 }
