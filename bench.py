@@ -542,6 +542,32 @@ def main():
         log(f"c5: {out_extra['posterior_samples_per_s']:.3g} accepted samples/s (acceptance {acc:.3f}), "
             f"{out_extra['log_prob_per_s']:.3g} log_prob/s  [{time.time() - t1:.1f} s]")
         del post, th_q
+        # ---- the same two calls on a c3-SHAPED flow (hidden 512 x 4 blocks, 15 transforms, 2000-bin context): its 114 M
+        # weights cannot be committed, so this is the seeded initialisation (identical on every rank and box) -- the
+        # acceptance rate of an untrained flow means nothing, raw draws/s and log_prob/s are what this states
+        try:
+            cfg3, th3, x3 = make_data("c3", 8192, 0)
+            torch.manual_seed(0)
+            net3 = fb.build_nsf(th3, x3, hidden_features=cfg3.hidden, num_transforms=cfg3.transforms, num_bins=cfg3.bins,
+                                num_blocks=cfg3.blocks, generator=torch.Generator().manual_seed(0)).to(dev).eval()
+            ctx3 = net3._standardize(x3[:1].to(dev))
+            z3 = torch.randn(1 << 20, cfg3.D, device=dev)
+            ms_r3 = timed(lambda i: net3.inverse_rows(z3, ctx3), 4)
+            th_q3 = torch.nan_to_num(net3.inverse_rows(z3, ctx3), nan=0.0, posinf=3.0, neginf=-3.0)
+            prior3 = fb.BoxUniform(-3 * torch.ones(cfg3.D), 3 * torch.ones(cfg3.D), device=dev)
+            post3 = fb.DirectPosterior(net3, prior3).set_default_x(x3[:1])
+            ms_l3 = timed(lambda i: post3.log_prob(th_q3, norm_posterior=False), 4)
+            out_extra["c3_shape_sampling"] = {
+                "raw_draws_per_s": world * z3.shape[0] * 4 / (ms_r3 * 1e-3), "log_prob_per_s": world * z3.shape[0] * 4 / (ms_l3 * 1e-3),
+                "fraction_inside_prior": float(((th_q3.abs() < 3).all(dim=1)).float().mean().item()),
+                "workload": f"seeded-initialisation c3 flow, {z3.shape[0]} rows per call and rank, one observation; "
+                            "flow.sample rows / posterior.log_prob(norm_posterior=False)"}
+            log(f"c5 on the c3 shape: {out_extra['c3_shape_sampling']['raw_draws_per_s']:.3g} raw draws/s, "
+                f"{out_extra['c3_shape_sampling']['log_prob_per_s']:.3g} log_prob/s")
+            del net3, post3, z3, th_q3
+            torch.cuda.empty_cache()
+        except Exception as exc:      # noqa: BLE001
+            out_extra["c3_shape_sampling"] = {"error": f"{type(exc).__name__}: {exc}"}
         # ======================================================== extras: the other configs, each with its own roofline
         extras = {}
         if world == 1 and not args.only_sampling:
