@@ -22,7 +22,25 @@ def nt(M, N, K, flags=0):
     return out
 
 
+def tn(M, N, R, flags=0):
+    A = torch.randn(R, M, device="cuda") * 1e-3; B = torch.randn(R, N, device="cuda")
+    C = torch.zeros(M, N, device="cuda"); db = torch.zeros(M, device="cuda")
+    sc = torch.tensor([512.0], device="cuda")
+    b = _lib.GemmArgs()
+    b.A, b.lda, b.a_kmajor, b.B, b.ldb, b.b_kmajor = A.data_ptr(), M, 0, B.data_ptr(), N, 0
+    b.C, b.ldc, b.M, b.N, b.K, b.split_k = C.data_ptr(), N, M, N, R, 1
+    b.flags, b.U, b.a_scale = _lib.G_ATOMIC | _lib.G_COLSUM_A | flags, db.data_ptr(), sc.data_ptr()
+    out = {}
+    for bits in (0, 1, 2, 3, 64, 65, 67):
+        L.fp_tc_set_debug(bits)
+        out[bits] = round(timeit(lambda: L.fp_gemm_tc16_tn(ctypes.byref(b), s)), 1)
+    L.fp_tc_set_debug(0)
+    return out
+
+
 if __name__ == "__main__":
     R = 18944
     print("NT16 block", nt(R, 512, 512, _lib.G_RELU_A), flush=True)
     print("NT16 ctx  ", nt(R, 38400, 2000), flush=True)
+    print("TN16 block [512 x 512] over 18944, relu_b", tn(512, 512, R, _lib.G_RELU_B), flush=True)
+    print("TN16 final [708 x 512] over 18944        ", tn(708, 512, R), flush=True)
