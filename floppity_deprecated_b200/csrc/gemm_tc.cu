@@ -2,19 +2,22 @@
 //
 // Same contract as the SIMT kernel (gemm_simt.cu): C[M,N] = pro(A)[M,K] * B[N,K]^T with the fused ResidualNet
 // epilogues (nflows ResidualNet reached from /root/reference/modules.py:63).  The reference computes these layers in
-// fp32; a single TF32/bf16 pass would miss the 1e-4 parity bar, so every product is evaluated as the 3xTF32 split
-//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo ,  x_hi = tf32(x), x_lo = x - x_hi      (error ~2^-21 |a||b|)
-// accumulated in fp32 TMEM accumulators (hi*hi and the cross terms separately, see the kernel comment).
+// fp32; a single TF32/bf16 pass would miss the 1e-4 parity bar, so every product is evaluated as a three-product split
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo                                              (error ~2^-21 |a||b|)
+// accumulated in fp32 TMEM accumulators (hi*hi and the cross terms separately, see the kernel comment), in one of two
+// operand formats:
+//   3xFP16 (default, fp_set_gemm_format): x_hi = fp16(x), x_lo = fp16((x - x_hi) * 2^11); 64 contraction indices per 64 KB
+//          stage, converted in place; gradient operands scaled by one power of two per backward pass; range guard.
+//   3xTF32: x_hi = tf32(x), x_lo = x - x_hi; 32 contraction indices per stage.
 //
-// Persistent warp-specialised CTA (320 threads, 128x128 output tiles, K in blocks of 32 fp32 = one 128-byte
-// swizzle row):
+// Persistent warp-specialised CTA (448 threads, 576 for 3xFP16; 128x128 output tiles; K in blocks of one 128-byte swizzle row):
 //   warp 0      TMA producer: cp.async.bulk.tensor loads of the raw fp32 A tile and the pre-split B_hi / B_lo tiles
 //               (weights are split once per optimiser step) into a 3-stage shared-memory ring (SWIZZLE_128B).
-//   warp 1      MMA issuer: one elected thread issues 3 products x 4 k-steps of tcgen05.mma.kind::tf32 (M128 N128 K8)
+//   warp 1      MMA issuer: one elected thread issues 3 products x 4 k-steps of tcgen05.mma (M128 N128, K8 tf32 / K16 f16)
 //               per stage from shared-memory descriptors; tcgen05.commit releases the stage / signals the epilogue.
-//   warps 2-5   splitter: relu prologue + hi/lo split of the A tile IN PLACE (elementwise, so the swizzle is
-//               irrelevant), fence.proxy.async, arrive on the stage's "ready" mbarrier.
-//   warps 6-9   epilogue: tcgen05.ld TMEM -> registers -> shared (32-column slab) -> coalesced float4 stores with
+//   warps 2..   splitter (4 warps, 8 for 3xFP16): relu prologue + hi/lo split of the A tile IN PLACE, fence.proxy.async,
+//               arrive on the stage's "ready" mbarrier.
+//   last 8      epilogue: tcgen05.ld TMEM -> registers -> shared (32-column slab) -> coalesced float4 stores with
 //               bias / context-add / GLU-gate+residual / relu-mask applied; overlaps the next tile's mainloop
 //               (two accumulator sets in TMEM).
 #include "common.cuh"
